@@ -1,0 +1,160 @@
+/* libpcb200 -- C ABI of the B200-native identity hot path (SCRFD detect -> 5-point align ->
+ * ArcFace embed -> bank distance) that replaces the ONNX Runtime / TensorRT / InsightFace / cv2
+ * calls inside the reference's FaceEmbedder (person_capture/face_embedder.py) and the
+ * per-face distance in Processor._fd_min (person_capture/gui_app.py:660-674).
+ *
+ * The reference has no native interface for this path (its boundary is the Python object
+ * FaceEmbedder, face_embedder.py:376-2508); this header follows the one native-binding
+ * precedent in the reference (hdr_preview/pc_hdr_vulkan.h:19-46 bound by ctypes in
+ * person_capture/hdr_preview.py:19-102): extern "C", opaque context, create/.../destroy --
+ * plus int return codes and pcb_last_error(), because this path has no CPU fallback and a
+ * failure must never be read as "no face".
+ *
+ * Conventions: every pointer named *_dev is a CUDA device pointer on the context's device
+ * (e.g. torch.Tensor.data_ptr()); *_host is host memory.  Calls are asynchronous and ordered
+ * on the context's stream; results are valid after pcb_sync() (or any call documented as
+ * synchronous).  All functions return 0 on success, non-zero on failure.
+ */
+#ifndef PCB200_H
+#define PCB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pcb_ctx pcb_ctx;
+
+#define PCB_FEAT_DIM 512
+#define PCB_CHIP 112
+
+/* ---- context ------------------------------------------------------------------------- */
+/* One context per GPU per thread.  `cuda_stream` may be NULL (the context creates its own). */
+pcb_ctx* pcb_create(int device, void* cuda_stream);
+void pcb_destroy(pcb_ctx* ctx);
+const char* pcb_last_error(pcb_ctx* ctx);
+/* Waits for the stream and checks the device-side error word (watchdogs, capacity overflow). */
+int pcb_sync(pcb_ctx* ctx);
+/* 0 = tcgen05/TMEM implicit GEMM (default), 1 = CUDA-core validation kernel (tests only). */
+int pcb_set_conv_impl(pcb_ctx* ctx, int impl);
+/* Number of kernels this library launched on the context since the last reset. */
+long long pcb_launch_count(pcb_ctx* ctx);
+void pcb_reset_launch_count(pcb_ctx* ctx);
+
+/* ---- graphs (replaces ort.InferenceSession construction, face_embedder.py:1102-1107, 891-915) */
+enum { PCB_OP_CONV = 1, PCB_OP_AFFINE = 2, PCB_OP_MAXPOOL3S2 = 3, PCB_OP_AVGPOOL2 = 4,
+       PCB_OP_UPSAMPLE_ADD = 5, PCB_OP_ADD = 6, PCB_OP_AFFINE_FLATTEN = 7, PCB_OP_FC = 8 };
+enum { PCB_ACT_NONE = 0, PCB_ACT_RELU = 1, PCB_ACT_PRELU = 2 };
+enum { PCB_MODEL_SCRFD = 0, PCB_MODEL_ARCFACE = 1 };
+
+typedef struct pcb_op {
+  int32_t kind;             /* PCB_OP_* */
+  int32_t in0, in1, out;    /* tensor ids; tensor 0 is the graph input; in1 = residual/second addend or -1 */
+  int32_t cin, cout, k, stride, act;
+  int64_t w_off;            /* byte offset in blob: fp16 [cout][cin][k][k] (FC: [cout][cin]); -1 if none */
+  int64_t scale_off;        /* fp32 [cout] */
+  int64_t bias_off;         /* fp32 [cout] */
+  int64_t slope_off;        /* fp32 [cout] (PReLU) or -1 */
+} pcb_op;
+
+/* Loads a graph into `slot`.  Tensor 0 is the stem-patch input produced by the pre-processing
+ * kernels: 27 channels = the 3x3 neighbourhood (ky,kx,rgb) of the normalised image, so the
+ * first op must be the stem convolution given as k=3 over cin=3 (stride 2 for SCRFD, 1 for
+ * ArcFace); the library executes it as a 1x1 GEMM over the patch tensor.
+ * `outputs` lists the tensor ids the graph produces (SCRFD: head maps of strides 8,16,32). */
+int pcb_model_load(pcb_ctx* ctx, int slot, const pcb_op* ops, int n_ops, int n_tensors,
+                   const void* blob_host, size_t blob_bytes, const int32_t* outputs, int n_outputs,
+                   const float* reg_scale3 /* SCRFD per-level bbox scale or NULL */);
+/* Debug/parity helper (synchronous): copy tensor `tid` of the last run of `slot` to host as
+ * fp32 NCHW [n][c][h][w]; returns dims through n,c,h,w.  out_host may be NULL to query dims. */
+int pcb_model_get_tensor(pcb_ctx* ctx, int slot, int tid, float* out_host, int* n, int* c, int* h, int* w);
+
+/* ---- K0: pre-scan downscale (replaces cv2.resize(..., INTER_AREA), gui_app.py:1505-1507) --- */
+/* uint8 BGR HWC [n][h][w][3] -> [n][nh][nw][3]; bit-exact with OpenCV's INTER_AREA. */
+int pcb_resize_area(pcb_ctx* ctx, const uint8_t* src_dev, int n, int h, int w,
+                    uint8_t* dst_dev, int nh, int nw);
+/* uint8 bilinear (cv2.resize default INTER_LINEAR; scale TTA at face_embedder.py:2263-2264). */
+int pcb_resize_linear(pcb_ctx* ctx, const uint8_t* src_dev, int n, int h, int w,
+                      uint8_t* dst_dev, int nh, int nw);
+
+/* ---- K1+K2+K3: one SCRFD pass (replaces scrfd.detect(img, input_size=(S,S)) with
+ *      scrfd.det_thresh = thresh, face_embedder.py:2176-2187; InsightFace SCRFD.detect/forward/nms)
+ *      followed by the reference's per-pass bookkeeping `_accumulate` + min-size filter
+ *      (face_embedder.py:2214-2245, 2317-2322). ------------------------------------------------ */
+enum { PCB_FIX_NONE = 0, PCB_FIX_SCALE = 1, PCB_FIX_PADPROBE = 2, PCB_FIX_UNPAD = 3 };
+
+typedef struct pcb_detect_args {
+  const uint8_t* frames_dev;   /* [n][h][w][3] BGR uint8 */
+  int32_t n, h, w;
+  int32_t S;                   /* square detector input, multiple of 32 */
+  float det_thresh;
+  int32_t rot_deg;             /* 0|90|180|270: detect on cv2.rotate(frame) without materialising it */
+  int32_t pad_replicate;       /* replicate border of this many px around the (rotated) frame */
+  int32_t fix_mode;            /* PCB_FIX_*: transform applied to dets before _accumulate */
+  float fix_scale_inv;         /* PCB_FIX_SCALE: boxes/kps *= fix_scale_inv (frame given is pre-scaled) */
+  int32_t orig_h, orig_w;      /* H0, W0 of the frame faces are reported in (== h,w unless SCALE) */
+  int32_t min_box_px;          /* scrfd_min_box_px (8) */
+  int32_t max_det;             /* capacity per frame of the output arrays */
+  /* outputs (device) */
+  float* det_dev;              /* [n][max_det][5]  x1,y1,x2,y2,score in (rotated/padded) image px, NMS order */
+  float* kps_dev;              /* [n][max_det][10] */
+  int32_t* raw_count_dev;      /* [n] detections after NMS (len(bboxes) in the reference) */
+  int32_t* acc_box_dev;        /* [n][max_det][4] int boxes in original-frame px after _accumulate + min-size */
+  float* acc_kps_dev;          /* [n][max_det][10] crop-local landmarks */
+  float* acc_score_dev;        /* [n][max_det] */
+  int32_t* acc_count_dev;      /* [n] */
+} pcb_detect_args;
+int pcb_detect(pcb_ctx* ctx, const pcb_detect_args* a);
+
+/* K1 alone: letterbox-resize + normalise + stem patch tensor.  out_dev is fp16
+ * [n][S/2+2][S/2+2][32] (P-layout, ring of zeros). det_img_dev (optional, may be NULL) receives
+ * the uint8 letterboxed image [n][S][S][3] for parity tests. */
+int pcb_letterbox(pcb_ctx* ctx, const uint8_t* frames_dev, int n, int h, int w, int S, int rot_deg,
+                  int pad_replicate, void* out_dev, uint8_t* det_img_dev);
+/* K3 alone on explicit head maps (fp16 P-layout [n][S/s+2][S/s+2][32] for s=8,16,32). */
+int pcb_decode_nms(pcb_ctx* ctx, const void* head8_dev, const void* head16_dev, const void* head32_dev,
+                   const float* reg_scale3_host, const pcb_detect_args* a, float det_scale);
+
+/* ---- K4: cross-pass suppression + alignment + quality (replaces face_embedder.py:2439-2463:
+ *      _iou suppression, crop, _canon_5pts, _align_by_5pts / _upright_by_eye_roll / resize,
+ *      _face_quality) ----------------------------------------------------------------------- */
+typedef struct pcb_align_args {
+  const uint8_t* frames_dev;   /* [n][h][w][3] */
+  int32_t n, h, w;
+  int32_t max_det;
+  const int32_t* acc_box_dev; const float* acc_kps_dev; const float* acc_score_dev; const int32_t* acc_count_dev;
+  int32_t max_faces;           /* capacity of the outputs below */
+  /* outputs (device) */
+  int32_t* face_count_dev;     /* [n] faces kept per frame */
+  int32_t* face_total_dev;     /* [1] */
+  int32_t* face_frame_dev;     /* [max_faces] frame index of each face (faces are grouped by frame, kept order) */
+  int32_t* face_box_dev;       /* [max_faces][4] xi1,yi1,xi2,yi2 */
+  int32_t* face_kind_dev;      /* [max_faces] 0 align, 1 eye-roll+align, 2 eye-roll+resize, 3 resize */
+  uint8_t* chips_dev;          /* [max_faces][112][112][3] BGR */
+  double* quality_dev;         /* [max_faces] */
+} pcb_align_args;
+int pcb_align(pcb_ctx* ctx, const pcb_align_args* a);
+
+/* ---- ArcFace (replaces _arcface_preprocess + arc_sess.run, face_embedder.py:1281-1288, 1369) -- */
+/* chips uint8 [f][112][112][3] BGR -> raw embeddings e(x) [f][512] and, if emb_flip_dev != NULL,
+ * e(flip x) [f][512] (cv2.flip(chip, 1), face_embedder.py:1297-1298). */
+int pcb_embed(pcb_ctx* ctx, const uint8_t* chips_dev, int f, float* emb_dev, float* emb_flip_dev);
+
+/* ---- K5: bank distance (replaces face_embedder.py:1383-1389 + Processor._fd_min,
+ *      gui_app.py:660-674) -------------------------------------------------------------------- */
+int pcb_set_bank(pcb_ctx* ctx, const float* bank_host /* [rows][512] */, int rows);
+/* feat = normalise(emb + (use_flip[i] ? emb_flip : 0)); fd = 1 - max_j(bank_j . feat); 9.0 if the
+ * bank is empty.  use_flip_dev may be NULL (no flip anywhere). */
+int pcb_match(pcb_ctx* ctx, const float* emb_dev, const float* emb_flip_dev, const uint8_t* use_flip_dev,
+              int f, float* feat_dev, float* fd_dev, int32_t* argmax_dev);
+
+/* ---- multi-GPU (no reference counterpart) ------------------------------------- */
+/* Thin wrapper over ncclAllGather on the context's stream; `nccl_comm` is an ncclComm_t. */
+int pcb_allgather_bytes(pcb_ctx* ctx, void* nccl_comm, const void* send_dev, void* recv_dev, size_t bytes_per_rank);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCB200_H */

@@ -1,0 +1,136 @@
+"""ORACLE (test infrastructure): restatement of InsightFace `model_zoo/scrfd.py::SCRFD`.
+
+Third-party dependency, not vendored in /root/reference: `insightface>=0.7.3`
+(reference requirements.txt:16).  The reference loads it by file path
+(person_capture/face_embedder.py:215-262) and calls `scrfd.detect(img, input_size=(S, S))`
+with `scrfd.det_thresh` set per call (face_embedder.py:2176-2187).  The algorithm below is
+restated from the published upstream source as summarised in SURVEY.md App. A.1; the
+reference has no test or golden vector for it -> parity unpinned.
+
+Uses real cv2 calls (cv2.resize, cv2.dnn.blobFromImage) so that the fixed-point arithmetic
+is OpenCV's own (cv2 4.13 here; the reference pins 4.9.0.80).
+"""
+from __future__ import annotations
+
+import numpy as np
+import cv2
+
+
+def distance2bbox(points, distance):
+    x1 = points[:, 0] - distance[:, 0]
+    y1 = points[:, 1] - distance[:, 1]
+    x2 = points[:, 0] + distance[:, 2]
+    y2 = points[:, 1] + distance[:, 3]
+    return np.stack([x1, y1, x2, y2], axis=-1)
+
+
+def distance2kps(points, distance):
+    preds = []
+    for i in range(0, distance.shape[1], 2):
+        px = points[:, i % 2] + distance[:, i]
+        py = points[:, i % 2 + 1] + distance[:, i + 1]
+        preds.append(px)
+        preds.append(py)
+    return np.stack(preds, axis=-1)
+
+
+class SCRFDOracle:
+    """`net.run(blob)` must return the 9 ONNX outputs (score x3, bbox x3, kps x3)."""
+
+    def __init__(self, net):
+        self.net = net
+        self.nms_thresh = 0.4
+        self.det_thresh = 0.5
+        self.center_cache = {}
+        self.input_mean = 127.5
+        self.input_std = 128.0
+        self.fmc = 3
+        self._feat_stride_fpn = [8, 16, 32]
+        self._num_anchors = 2
+        self.use_kps = True
+
+    def forward(self, img, threshold):
+        scores_list, bboxes_list, kpss_list = [], [], []
+        input_size = tuple(img.shape[0:2][::-1])
+        blob = cv2.dnn.blobFromImage(img, 1.0 / self.input_std, input_size,
+                                     (self.input_mean, self.input_mean, self.input_mean), swapRB=True)
+        net_outs = self.net.run(blob)
+        input_height, input_width = blob.shape[2], blob.shape[3]
+        fmc = self.fmc
+        for idx, stride in enumerate(self._feat_stride_fpn):
+            scores = net_outs[idx]
+            bbox_preds = net_outs[idx + fmc] * stride
+            kps_preds = net_outs[idx + fmc * 2] * stride
+            height = input_height // stride
+            width = input_width // stride
+            key = (height, width, stride)
+            if key in self.center_cache:
+                anchor_centers = self.center_cache[key]
+            else:
+                anchor_centers = np.stack(np.mgrid[:height, :width][::-1], axis=-1).astype(np.float32)
+                anchor_centers = (anchor_centers * stride).reshape((-1, 2))
+                if self._num_anchors > 1:
+                    anchor_centers = np.stack([anchor_centers] * self._num_anchors, axis=1).reshape((-1, 2))
+                if len(self.center_cache) < 100:
+                    self.center_cache[key] = anchor_centers
+            pos_inds = np.where(scores >= threshold)[0]
+            bboxes = distance2bbox(anchor_centers, bbox_preds)
+            pos_scores = scores[pos_inds]
+            pos_bboxes = bboxes[pos_inds]
+            scores_list.append(pos_scores)
+            bboxes_list.append(pos_bboxes)
+            kpss = distance2kps(anchor_centers, kps_preds)
+            kpss = kpss.reshape((kpss.shape[0], -1, 2))
+            kpss_list.append(kpss[pos_inds])
+        return scores_list, bboxes_list, kpss_list
+
+    def detect(self, img, input_size, max_num=0):
+        im_ratio = float(img.shape[0]) / img.shape[1]
+        model_ratio = float(input_size[1]) / input_size[0]
+        if im_ratio > model_ratio:
+            new_height = input_size[1]
+            new_width = int(new_height / im_ratio)
+        else:
+            new_width = input_size[0]
+            new_height = int(new_width * im_ratio)
+        det_scale = float(new_height) / img.shape[0]
+        resized_img = cv2.resize(img, (new_width, new_height))
+        det_img = np.zeros((input_size[1], input_size[0], 3), dtype=np.uint8)
+        det_img[:new_height, :new_width, :] = resized_img
+        scores_list, bboxes_list, kpss_list = self.forward(det_img, self.det_thresh)
+        scores = np.vstack(scores_list)
+        scores_ravel = scores.ravel()
+        # upstream: scores_ravel.argsort()[::-1] -- not a stable sort, ties are implementation
+        # defined.  The oracle pins ties: descending score, then ascending anchor
+        # row (a stable sort of the negated scores), and the CUDA path implements the same rule.
+        order = np.argsort(-scores_ravel, kind="stable")
+        bboxes = np.vstack(bboxes_list) / det_scale
+        kpss = np.vstack(kpss_list) / det_scale
+        pre_det = np.hstack((bboxes, scores)).astype(np.float32, copy=False)
+        pre_det = pre_det[order, :]
+        keep = self.nms(pre_det)
+        det = pre_det[keep, :]
+        kpss = kpss[order, :, :]
+        kpss = kpss[keep, :, :]
+        return det, kpss
+
+    def nms(self, dets):
+        thresh = self.nms_thresh
+        x1, y1, x2, y2, scores = dets[:, 0], dets[:, 1], dets[:, 2], dets[:, 3], dets[:, 4]
+        areas = (x2 - x1 + 1) * (y2 - y1 + 1)
+        order = np.argsort(-scores, kind="stable")
+        keep = []
+        while order.size > 0:
+            i = order[0]
+            keep.append(i)
+            xx1 = np.maximum(x1[i], x1[order[1:]])
+            yy1 = np.maximum(y1[i], y1[order[1:]])
+            xx2 = np.minimum(x2[i], x2[order[1:]])
+            yy2 = np.minimum(y2[i], y2[order[1:]])
+            w = np.maximum(0.0, xx2 - xx1 + 1)
+            h = np.maximum(0.0, yy2 - yy1 + 1)
+            inter = w * h
+            ovr = inter / (areas[i] + areas[order[1:]] - inter)
+            inds = np.where(ovr <= thresh)[0]
+            order = order[inds + 1]
+        return keep

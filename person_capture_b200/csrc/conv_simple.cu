@@ -1,0 +1,109 @@
+// CUDA-core direct convolution over the same P-layout / packed weights as conv_tc.cu.
+// Validation kernel only (pcb_set_conv_impl(ctx, 1) in tests): it lets the parity suite tell a
+// tensor-core descriptor bug from a graph/weight bug.  Never selected by the product path.
+#include "pcb_common.cuh"
+
+namespace {
+
+struct SimpleParams {
+  const __half* in;
+  const __half* w;
+  const float* scale;
+  const float* bias;
+  const float* slope;
+  const __half* residual;
+  __half* out;
+  float* out_f32;
+  int n, h, w_, cp_in;       // input logical dims
+  int ho, wo, cp_out, res_cp;
+  int cin_eff;               // channels to reduce over (<= cp_in)
+  int cout_store;            // channels to write
+  int taps, cin_w, stride, act, dense, out_f32_stride, out_f32_cols;
+};
+
+__global__ void conv_simple_kernel(const SimpleParams p) {
+  const long long total = p.dense ? (long long)p.n * p.cout_store : (long long)p.n * p.ho * p.wo * p.cout_store;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(idx % p.cout_store);
+    long long pix = idx / p.cout_store;
+    float acc = 0.f;
+    long long orow;
+    if (p.dense) {
+      const __half* a = p.in + pix * p.cp_in;
+      const __half* wr = p.w + (long long)co * p.cin_w;
+      for (int ci = 0; ci < p.cin_eff; ++ci) acc = fmaf(__half2float(a[ci]), __half2float(wr[ci]), acc);
+      orow = pix;
+    } else {
+      const int xo = (int)(pix % p.wo);
+      const int yo = (int)((pix / p.wo) % p.ho);
+      const int img = (int)(pix / ((long long)p.wo * p.ho));
+      const int hp = p.h + 2, wp = p.w_ + 2;
+      const int yc = yo * p.stride + 1, xc = xo * p.stride + 1;  // centre in padded input coords
+      for (int t = 0; t < p.taps; ++t) {
+        const int dy = p.taps == 9 ? t / 3 - 1 : 0, dx = p.taps == 9 ? t % 3 - 1 : 0;
+        const __half* a = p.in + (((long long)img * hp + yc + dy) * wp + xc + dx) * p.cp_in;
+        const __half* wr = p.w + ((long long)co * p.taps + t) * p.cin_w;
+        for (int ci = 0; ci < p.cin_eff; ++ci) acc = fmaf(__half2float(a[ci]), __half2float(wr[ci]), acc);
+      }
+      orow = ((long long)img * (p.ho + 2) + yo + 1) * (p.wo + 2) + xo + 1;
+    }
+    float y = fmaf(acc, p.scale[co], p.bias[co]);
+    if (p.out_f32) {
+      if (co < p.out_f32_cols) p.out_f32[orow * p.out_f32_stride + co] = y;
+      continue;
+    }
+    if (p.residual) y += __half2float(p.residual[orow * p.res_cp + co]);
+    if (p.act == PCB_ACT_RELU) y = fmaxf(y, 0.f);
+    else if (p.act == PCB_ACT_PRELU) y = y >= 0.f ? y : y * p.slope[co];
+    p.out[orow * p.cp_out + co] = __float2half_rn(y);
+  }
+}
+
+}  // namespace
+
+int pcb_conv_simple(pcb_ctx* c, const ConvArgs& a) {
+  const PTensor& in = *a.in;
+  const ConvWeights& w = *a.w;
+  SimpleParams p{};
+  p.in = in.data;
+  p.w = w.w;
+  p.scale = w.scale;
+  p.bias = w.bias;
+  p.slope = w.slope;
+  p.n = in.n;
+  p.h = in.h;
+  p.w_ = in.w;
+  p.cp_in = in.cp;
+  p.cin_eff = in.cp < w.cin_w ? in.cp : w.cin_w;
+  p.taps = w.taps;
+  p.cin_w = w.cin_w;
+  p.stride = in.dense ? 1 : a.stride;
+  p.act = a.act;
+  p.dense = in.dense ? 1 : 0;
+  if (in.dense) p.cin_w = w.cin_w;
+  if (a.out_f32) {
+    p.out_f32 = a.out_f32;
+    p.out_f32_stride = a.out_f32_stride;
+    p.out_f32_cols = w.cout;
+    p.cout_store = w.cout;
+    p.ho = p.wo = 1;
+  } else {
+    p.out = a.out->data;
+    p.ho = a.out->h;
+    p.wo = a.out->w;
+    p.cp_out = a.out->cp;
+    p.cout_store = a.out->cp;
+    if (a.residual) {
+      p.residual = a.residual->data;
+      p.res_cp = a.residual->cp;
+    }
+  }
+  const long long total = p.dense ? (long long)p.n * p.cout_store : (long long)p.n * p.ho * p.wo * p.cout_store;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148LL * 32) blocks = 148LL * 32;
+  if (blocks < 1) blocks = 1;
+  conv_simple_kernel<<<(int)blocks, 256, 0, c->stream>>>(p);
+  PCB_LAUNCH_CHECK(c, "conv_simple_kernel");
+  return PCB_OK;
+}

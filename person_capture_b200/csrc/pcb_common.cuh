@@ -1,0 +1,104 @@
+// Shared declarations for libpcb200 (sm_100a).  Internal header; the public C ABI is
+// include/pcb200.h.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/pcb200.h"
+
+#define PCB_OK 0
+#define PCB_ERR_CUDA 1
+#define PCB_ERR_ARG 2
+#define PCB_ERR_KERNEL 3   // device-side watchdog / overflow flag raised
+#define PCB_ERR_STATE 4
+
+// ---------------------------------------------------------------------------------------
+// Activation layout ("P-layout"): fp16 [N][H+2][W+2][Cp] with a one-pixel ring of zeros and
+// Cp = channels rounded up to 8.  A 3x3/pad-1 convolution over it is nine row-shifted views
+// of the same [rows, Cp] matrix (rows = N*(H+2)*(W+2)), which is what the TMA-fed implicit
+// GEMM in conv_tc.cu consumes.  Kernels only ever write interior pixels, so the ring stays
+// zero after the one-time memset at allocation.
+// ---------------------------------------------------------------------------------------
+struct PTensor {
+  __half* data = nullptr;
+  int n = 0, h = 0, w = 0, c = 0, cp = 0;  // logical dims, cp = padded channel stride
+  bool dense = false;                      // dense: [n][cp] rows without spatial ring (FC input)
+  size_t rows() const { return dense ? (size_t)n : (size_t)n * (h + 2) * (w + 2); }
+  size_t bytes() const { return rows() * cp * sizeof(__half); }
+};
+
+static inline int pcb_round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+struct ConvWeights {
+  // packed for the implicit GEMM: [npad][taps][cin_w] fp16 (zero padded), scale/bias/slope [npad] fp32
+  __half* w = nullptr;
+  float* scale = nullptr;
+  float* bias = nullptr;
+  float* slope = nullptr;
+  int cin = 0, cout = 0, k = 0, taps = 0;
+  int cin_w = 0;   // per-tap K extent in the packed weight (multiple of 64)
+  int npad = 0;    // rows in the packed weight (multiple of n_tile)
+  int n_tile = 0;  // UMMA N used for this layer
+};
+
+struct ConvArgs {
+  const PTensor* in;
+  const PTensor* out;       // fp16 P-layout output (or nullptr when out_f32 is used)
+  float* out_f32;           // dense fp32 output [rows][out_f32_stride] (FC)
+  int out_f32_stride;
+  const PTensor* residual;  // optional, same geometry as out
+  const ConvWeights* w;
+  int stride;               // 1 or 2 (spatial); ignored for dense
+  int act;                  // 0 none, 1 relu, 2 prelu
+};
+
+struct pcb_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int num_sms = 148;
+  std::string last_error;
+  int* d_err = nullptr;       // device error word (watchdog / overflow)
+  int* h_err = nullptr;       // pinned mirror
+  int conv_impl = 0;          // 0 = tcgen05 (product), 1 = CUDA-core validation kernel
+  long long launches = 0;     // kernels launched since the last pcb_reset_counters
+  std::vector<void*> allocs;  // everything cudaMalloc'ed through the context
+  struct Model* models[4] = {nullptr, nullptr, nullptr, nullptr};
+  float* bank = nullptr;
+  int bank_rows = 0, bank_cap = 0;
+  void* scratch = nullptr;
+  size_t scratch_bytes = 0;
+};
+
+int pcb_fail(pcb_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess);
+#define PCB_CUDA(ctx, call)                                                      \
+  do {                                                                           \
+    cudaError_t _e = (call);                                                     \
+    if (_e != cudaSuccess) return pcb_fail((ctx), PCB_ERR_CUDA, #call, _e);      \
+  } while (0)
+#define PCB_LAUNCH_CHECK(ctx, name)                                              \
+  do {                                                                           \
+    cudaError_t _e = cudaGetLastError();                                         \
+    if (_e != cudaSuccess) return pcb_fail((ctx), PCB_ERR_CUDA, name, _e);       \
+    (ctx)->launches++;                                                           \
+  } while (0)
+
+void* pcb_dev_alloc(pcb_ctx* c, size_t bytes, bool zero);
+
+// conv_tc.cu / conv_simple.cu
+int pcb_conv_tc(pcb_ctx* c, const ConvArgs& a);
+int pcb_conv_simple(pcb_ctx* c, const ConvArgs& a);
+// ops.cu
+int pcb_op_affine(pcb_ctx* c, const PTensor& in, const PTensor& out, const float* scale, const float* bias);
+int pcb_op_maxpool3s2(pcb_ctx* c, const PTensor& in, const PTensor& out);
+int pcb_op_avgpool2(pcb_ctx* c, const PTensor& in, const PTensor& out);
+int pcb_op_upsample_add(pcb_ctx* c, const PTensor& big, const PTensor& small, const PTensor& out);
+int pcb_op_add(pcb_ctx* c, const PTensor& a, const PTensor& b, const PTensor& out);
+int pcb_op_affine_flatten(pcb_ctx* c, const PTensor& in, const PTensor& out_dense, const float* scale, const float* bias);
