@@ -78,6 +78,10 @@ int pcb_resize_area(pcb_ctx* ctx, const uint8_t* src_dev, int n, int h, int w,
 /* uint8 bilinear (cv2.resize default INTER_LINEAR; scale TTA at face_embedder.py:2263-2264). */
 int pcb_resize_linear(pcb_ctx* ctx, const uint8_t* src_dev, int n, int h, int w,
                       uint8_t* dst_dev, int nh, int nw);
+/* cv2.resize(img, None, fx=, fy=, interpolation=INTER_AREA|INTER_LINEAR): dst is
+ * [n][cvRound(h*fy)][cvRound(w*fx)][3] and the sampling scale is the factor itself (not dst/src). */
+int pcb_resize_factor(pcb_ctx* ctx, const uint8_t* src_dev, int n, int h, int w, uint8_t* dst_dev,
+                      double fx, double fy, int inter_area);
 
 /* ---- K1+K2+K3: one SCRFD pass (replaces scrfd.detect(img, input_size=(S,S)) with
  *      scrfd.det_thresh = thresh, face_embedder.py:2176-2187; InsightFace SCRFD.detect/forward/nms)
@@ -105,6 +109,8 @@ typedef struct pcb_detect_args {
   float* acc_kps_dev;          /* [n][max_det][10] crop-local landmarks */
   float* acc_score_dev;        /* [n][max_det] */
   int32_t* acc_count_dev;      /* [n] */
+  int32_t* acc_unfiltered_dev; /* [n] optional (may be NULL): entries that survived _accumulate before the
+                                  min-size filter -- the reference breaks its scale-TTA loop on this list */
 } pcb_detect_args;
 int pcb_detect(pcb_ctx* ctx, const pcb_detect_args* a);
 
@@ -145,14 +151,12 @@ int pcb_embed(pcb_ctx* ctx, const uint8_t* chips_dev, int f, float* emb_dev, flo
 /* ---- K5: bank distance (replaces face_embedder.py:1383-1389 + Processor._fd_min,
  *      gui_app.py:660-674) -------------------------------------------------------------------- */
 int pcb_set_bank(pcb_ctx* ctx, const float* bank_host /* [rows][512] */, int rows);
-/* feat = normalise(emb + (use_flip[i] ? emb_flip : 0)); fd = 1 - max_j(bank_j . feat); 9.0 if the
- * bank is empty.  use_flip_dev may be NULL (no flip anywhere). */
+/* feat = normalise(emb + (use_flip[i] ? emb_flip : 0)); sim = max_j(bank_j . feat) in float32, so the
+ * caller forms fd = 1.0 - sim exactly as _fd_min does; sim = -8 (fd = 9.0, the reference's sentinel)
+ * when the bank is empty.  emb_flip_dev NULL: no flip; use_flip_dev NULL with emb_flip_dev set: flip
+ * everywhere.  feat_dev / argmax_dev may be NULL. */
 int pcb_match(pcb_ctx* ctx, const float* emb_dev, const float* emb_flip_dev, const uint8_t* use_flip_dev,
-              int f, float* feat_dev, float* fd_dev, int32_t* argmax_dev);
-
-/* ---- multi-GPU (no reference counterpart) ------------------------------------- */
-/* Thin wrapper over ncclAllGather on the context's stream; `nccl_comm` is an ncclComm_t. */
-int pcb_allgather_bytes(pcb_ctx* ctx, void* nccl_comm, const void* send_dev, void* recv_dev, size_t bytes_per_rank);
+              int f, float* feat_dev, float* sim_dev, int32_t* argmax_dev);
 
 #ifdef __cplusplus
 }

@@ -131,6 +131,27 @@ def loss_fn(raws, targets_batch):
     return total_cls / npos, total_reg / npos / 4, total_kps / npos / 10
 
 
+def recalibrate_bn(net, rng, size: int, batches: int = 80, batch: int = 12):
+    """Re-estimate BatchNorm running statistics as a cumulative average over fresh batches.
+
+    With ~1.5k steps of a one-cycle schedule the exponential running stats lag the final weights
+    (eval-mode recall collapses while batch-stat recall is ~95%); the exported folded scale/bias
+    come from these statistics, so they are recomputed before export.
+    """
+    for mod in net.modules():
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.reset_running_stats()
+            mod.momentum = None
+    net.train()
+    with torch.no_grad():
+        for _ in range(batches):
+            imgs = [make_sample(rng, size, None)[0] for _ in range(batch)]
+            x = np.stack(imgs)[..., ::-1].astype(np.float32)
+            x = (x - 127.5) / 128.0
+            net.head_raw(torch.from_numpy(np.ascontiguousarray(x.transpose(0, 3, 1, 2))))
+    net.eval()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("name")
@@ -142,6 +163,10 @@ def main():
     ap.add_argument("--lr", type=float, default=2e-3)
     ap.add_argument("--out", default=None)
     ap.add_argument("--resume", default=None)
+    ap.add_argument("--recalibrate-only", action="store_true")
+    ap.add_argument("--freeze-bn", action="store_true",
+                    help="fine-tune with BatchNorm in eval mode (fixed population statistics) so that the "
+                         "exported folded graph and the training-time graph are the same function")
     args = ap.parse_args()
     torch.set_num_threads(args.threads)
     torch.manual_seed(args.seed)
@@ -149,7 +174,22 @@ def main():
     net = SCRFD(args.name)
     if args.resume:
         net.load_state_dict(torch.load(args.resume))
-    net.train()
+    out = args.out or os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "weights", args.name + ".npz")
+    if args.recalibrate_only:
+        recalibrate_bn(net, rng, args.size)
+        np.savez(out, **net.export_folded())
+        print("recalibrated", out)
+        return
+    def set_train_mode():
+        net.train()
+        if args.freeze_bn:
+            for mod in net.modules():
+                if isinstance(mod, torch.nn.BatchNorm2d):
+                    mod.eval()
+
+    if args.freeze_bn:
+        recalibrate_bn(net, rng, args.size, batches=40)
+    set_train_mode()
     opt = torch.optim.AdamW(net.parameters(), lr=args.lr, weight_decay=1e-4)
     sched = torch.optim.lr_scheduler.OneCycleLR(opt, max_lr=args.lr, total_steps=args.steps, pct_start=0.1)
     out = args.out or os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "weights", args.name + ".npz")
@@ -179,7 +219,11 @@ def main():
             P = net.export_folded()
             np.savez(out, **P)
             torch.save(net.state_dict(), out.replace(".npz", ".pt"))
-            net.train()
+            set_train_mode()
+    if not args.freeze_bn:
+        recalibrate_bn(net, rng, args.size)
+    net.eval()
+    np.savez(out, **net.export_folded())
     print("saved", out)
 
 

@@ -1,0 +1,102 @@
+"""ctypes binding of libpcb200.so (include/pcb200.h).
+
+Follows the reference's own native-binding precedent (person_capture/hdr_preview.py:19-102:
+ctypes.CDLL + opaque context pointer).  There is no CPU fallback: if the shared library is
+missing or a call fails, this module raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpcb200.so")
+
+FEAT_DIM = 512
+CHIP = 112
+
+OP_CONV, OP_AFFINE, OP_MAXPOOL3S2, OP_AVGPOOL2, OP_UPSAMPLE_ADD, OP_ADD, OP_AFFINE_FLATTEN, OP_FC = range(1, 9)
+ACT_NONE, ACT_RELU, ACT_PRELU = 0, 1, 2
+MODEL_SCRFD, MODEL_ARCFACE = 0, 1
+FIX_NONE, FIX_SCALE, FIX_PADPROBE, FIX_UNPAD = 0, 1, 2, 3
+
+EXPORTS = (
+    "pcb_create", "pcb_destroy", "pcb_last_error", "pcb_sync", "pcb_set_conv_impl", "pcb_launch_count",
+    "pcb_reset_launch_count", "pcb_model_load", "pcb_model_get_tensor", "pcb_resize_area", "pcb_resize_linear", "pcb_resize_factor",
+    "pcb_detect", "pcb_letterbox", "pcb_decode_nms", "pcb_align", "pcb_embed", "pcb_set_bank", "pcb_match",
+)
+
+
+class PcbOp(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("in0", C.c_int32), ("in1", C.c_int32), ("out", C.c_int32),
+                ("cin", C.c_int32), ("cout", C.c_int32), ("k", C.c_int32), ("stride", C.c_int32), ("act", C.c_int32),
+                ("w_off", C.c_int64), ("scale_off", C.c_int64), ("bias_off", C.c_int64), ("slope_off", C.c_int64)]
+
+
+class DetectArgs(C.Structure):
+    _fields_ = [("frames_dev", C.c_void_p), ("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("S", C.c_int32),
+                ("det_thresh", C.c_float), ("rot_deg", C.c_int32), ("pad_replicate", C.c_int32), ("fix_mode", C.c_int32),
+                ("fix_scale_inv", C.c_float), ("orig_h", C.c_int32), ("orig_w", C.c_int32), ("min_box_px", C.c_int32),
+                ("max_det", C.c_int32),
+                ("det_dev", C.c_void_p), ("kps_dev", C.c_void_p), ("raw_count_dev", C.c_void_p),
+                ("acc_box_dev", C.c_void_p), ("acc_kps_dev", C.c_void_p), ("acc_score_dev", C.c_void_p),
+                ("acc_count_dev", C.c_void_p), ("acc_unfiltered_dev", C.c_void_p)]
+
+
+class AlignArgs(C.Structure):
+    _fields_ = [("frames_dev", C.c_void_p), ("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("max_det", C.c_int32),
+                ("acc_box_dev", C.c_void_p), ("acc_kps_dev", C.c_void_p), ("acc_score_dev", C.c_void_p),
+                ("acc_count_dev", C.c_void_p), ("max_faces", C.c_int32),
+                ("face_count_dev", C.c_void_p), ("face_total_dev", C.c_void_p), ("face_frame_dev", C.c_void_p),
+                ("face_box_dev", C.c_void_p), ("face_kind_dev", C.c_void_p), ("chips_dev", C.c_void_p),
+                ("quality_dev", C.c_void_p)]
+
+
+class PcbError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load libpcb200.so; raises if it has not been built (python __graft_entry__.py build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise PcbError(f"{LIB_PATH} not found: build it with `make -C person_capture_b200/csrc` "
+                       "(there is no CPU fallback for the identity path)")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, f32 = C.c_void_p, C.c_int, C.c_float
+    lib.pcb_create.restype = vp
+    lib.pcb_create.argtypes = [i32, vp]
+    lib.pcb_destroy.restype = None
+    lib.pcb_destroy.argtypes = [vp]
+    lib.pcb_last_error.restype = C.c_char_p
+    lib.pcb_last_error.argtypes = [vp]
+    lib.pcb_sync.argtypes = [vp]
+    lib.pcb_set_conv_impl.argtypes = [vp, i32]
+    lib.pcb_launch_count.restype = C.c_longlong
+    lib.pcb_launch_count.argtypes = [vp]
+    lib.pcb_reset_launch_count.restype = None
+    lib.pcb_reset_launch_count.argtypes = [vp]
+    lib.pcb_model_load.argtypes = [vp, i32, C.POINTER(PcbOp), i32, i32, vp, C.c_size_t, C.POINTER(C.c_int32), i32,
+                                   C.POINTER(C.c_float)]
+    lib.pcb_model_get_tensor.argtypes = [vp, i32, i32, vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+    lib.pcb_resize_area.argtypes = [vp, vp, i32, i32, i32, vp, i32, i32]
+    lib.pcb_resize_linear.argtypes = [vp, vp, i32, i32, i32, vp, i32, i32]
+    lib.pcb_resize_factor.argtypes = [vp, vp, i32, i32, i32, vp, C.c_double, C.c_double, i32]
+    lib.pcb_detect.argtypes = [vp, C.POINTER(DetectArgs)]
+    lib.pcb_letterbox.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp]
+    lib.pcb_decode_nms.argtypes = [vp, vp, vp, vp, C.POINTER(C.c_float), C.POINTER(DetectArgs), f32]
+    lib.pcb_align.argtypes = [vp, C.POINTER(AlignArgs)]
+    lib.pcb_embed.argtypes = [vp, vp, i32, vp, vp]
+    lib.pcb_set_bank.argtypes = [vp, vp, i32]
+    lib.pcb_match.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp]
+    for name in EXPORTS:
+        fn = getattr(lib, name)
+        if fn.restype is C.c_int:
+            pass
+    _lib = lib
+    return lib

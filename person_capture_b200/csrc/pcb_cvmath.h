@@ -55,7 +55,8 @@ PCB_HD uint8_t pcb_sat_u8(int v) { return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 :
 // ---------------------------------------------------------------------------------------
 struct PcbView {
   const uint8_t* base;   // frame [h][w][3]
-  int h, w;              // stored frame dims
+ int h, w;              // stored frame dims
+  int ld;                // row pitch in pixels (>= w; a crop view keeps the frame's pitch)
   int rot;               // 0 | 90 | 180 | 270 (cv2.ROTATE_90_CLOCKWISE = 90, COUNTERCLOCKWISE = 270)
   int pad;               // replicate border
   int vh, vw;            // dims of the virtual image = rotated dims + 2*pad
@@ -63,7 +64,7 @@ struct PcbView {
 
 PCB_HD PcbView pcb_make_view(const uint8_t* base, int h, int w, int rot, int pad) {
   PcbView v;
-  v.base = base; v.h = h; v.w = w; v.rot = rot; v.pad = pad;
+  v.base = base; v.h = h; v.w = w; v.ld = w; v.rot = rot; v.pad = pad;
   const int rh = (rot == 90 || rot == 270) ? w : h;
   const int rw = (rot == 90 || rot == 270) ? h : w;
   v.vh = rh + 2 * pad;
@@ -79,7 +80,7 @@ PCB_HD const uint8_t* pcb_view_px(const PcbView& v, int y, int x) {
   else if (v.rot == 180) { sy = v.h - 1 - ry; sx = v.w - 1 - rx; }
   else if (v.rot == 270) { sy = rx; sx = v.w - 1 - ry; }
   else { sy = ry; sx = rx; }
-  return v.base + ((long long)sy * v.w + sx) * 3;
+  return v.base + ((long long)sy * v.ld + sx) * 3;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -87,8 +88,10 @@ PCB_HD const uint8_t* pcb_view_px(const PcbView& v, int y, int x) {
 // ---------------------------------------------------------------------------------------
 struct PcbLinCoef { int s; int a0, a1; };
 
-PCB_HD PcbLinCoef pcb_lin_coef(int d, int src, int dst, bool horizontal, bool area_mode) {
-  const double inv = PCB_DDIV((double)dst, (double)src);
+// `inv` is OpenCV's inv_scale: dst/src when the caller gave dsize, fx/fy itself when it gave factors.
+PCB_HD double pcb_inv_scale(int src, int dst) { return PCB_DDIV((double)dst, (double)src); }
+
+PCB_HD PcbLinCoef pcb_lin_coef(int d, int src, int dst, bool horizontal, bool area_mode, double inv) {
   const double scale = PCB_DDIV(1.0, inv);
   int s;
   float f;
@@ -113,9 +116,10 @@ PCB_HD PcbLinCoef pcb_lin_coef(int d, int src, int dst, bool horizontal, bool ar
 }
 
 // one output pixel of cv::resize(view, (dw, dh), INTER_LINEAR) (or the INTER_AREA-on-upscale variant)
-PCB_HD void pcb_resize_linear_px(const PcbView& v, int dy, int dx, int dh, int dw, bool area_mode, uint8_t out[3]) {
-  const PcbLinCoef cx = pcb_lin_coef(dx, v.vw, dw, true, area_mode);
-  const PcbLinCoef cy = pcb_lin_coef(dy, v.vh, dh, false, area_mode);
+PCB_HD void pcb_resize_linear_px(const PcbView& v, int dy, int dx, int dh, int dw, bool area_mode, double inv_x, double inv_y,
+                                 uint8_t out[3]) {
+  const PcbLinCoef cx = pcb_lin_coef(dx, v.vw, dw, true, area_mode, inv_x);
+  const PcbLinCoef cy = pcb_lin_coef(dy, v.vh, dh, false, area_mode, inv_y);
   const int x0 = cx.s, x1 = pcb_iminf(cx.s + 1, v.vw - 1);
   const int y0 = pcb_clampi(cy.s, 0, v.vh - 1), y1 = pcb_clampi(cy.s + 1, 0, v.vh - 1);
   const uint8_t* p00 = pcb_view_px(v, y0, x0);
@@ -150,8 +154,8 @@ PCB_HD void pcb_resize_area_int_px(const PcbView& v, int dy, int dx, int isy, in
 // OpenCV's order.  Taps of destination index d: [s1-1 partial] [s1..s2) full [s2 partial].
 struct PcbAreaTaps { int s1, s2; float wl, wm, wr; bool has_l, has_r; };
 
-PCB_HD PcbAreaTaps pcb_area_taps(int d, int src, int dst) {
-  const double scale = PCB_DDIV(1.0, PCB_DDIV((double)dst, (double)src));
+PCB_HD PcbAreaTaps pcb_area_taps(int d, int src, int dst, double inv) {
+  const double scale = PCB_DDIV(1.0, inv);
   const double fs1 = PCB_DMUL((double)d, scale);
   const double fs2 = PCB_DADD(fs1, scale);
   const double rem = PCB_DSUB((double)src, fs1);
@@ -188,9 +192,9 @@ PCB_HD void pcb_area_hrow(const PcbView& v, int sy, const PcbAreaTaps& tx, float
   }
 }
 
-PCB_HD void pcb_resize_area_frac_px(const PcbView& v, int dy, int dx, int dh, int dw, uint8_t out[3]) {
-  const PcbAreaTaps tx = pcb_area_taps(dx, v.vw, dw);
-  const PcbAreaTaps ty = pcb_area_taps(dy, v.vh, dh);
+PCB_HD void pcb_resize_area_frac_px(const PcbView& v, int dy, int dx, int dh, int dw, double inv_x, double inv_y, uint8_t out[3]) {
+  const PcbAreaTaps tx = pcb_area_taps(dx, v.vw, dw, inv_x);
+  const PcbAreaTaps ty = pcb_area_taps(dy, v.vh, dh, inv_y);
   float sum[3] = {0.f, 0.f, 0.f};
   float buf[3];
   if (ty.has_l) {
@@ -210,12 +214,15 @@ PCB_HD void pcb_resize_area_frac_px(const PcbView& v, int dy, int dx, int dh, in
 
 // Dispatch of cv::resize for 8UC3, as OpenCV selects the kernel.
 enum { PCB_RS_LINEAR = 0, PCB_RS_AREA_INT = 1, PCB_RS_AREA_FRAC = 2, PCB_RS_LINEAR_AREAMODE = 3 };
-struct PcbResizePlan { int mode, isx, isy; };
+struct PcbResizePlan { int mode, isx, isy; double inv_x, inv_y; };
 
-PCB_HD PcbResizePlan pcb_resize_plan(int sh, int sw, int dh, int dw, bool inter_area) {
+// fx, fy > 0: cv2.resize(src, None, fx=, fy=) form (inv_scale = the factor itself); else dsize form.
+PCB_HD PcbResizePlan pcb_resize_plan(int sh, int sw, int dh, int dw, bool inter_area, double fx = 0.0, double fy = 0.0) {
   PcbResizePlan p;
-  const double scx = PCB_DDIV(1.0, PCB_DDIV((double)dw, (double)sw));
-  const double scy = PCB_DDIV(1.0, PCB_DDIV((double)dh, (double)sh));
+  p.inv_x = fx > 0.0 ? fx : pcb_inv_scale(sw, dw);
+  p.inv_y = fy > 0.0 ? fy : pcb_inv_scale(sh, dh);
+  const double scx = PCB_DDIV(1.0, p.inv_x);
+  const double scy = PCB_DDIV(1.0, p.inv_y);
   const int isx = pcb_cvround_d(scx), isy = pcb_cvround_d(scy);
   const bool fast = fabs(scx - isx) < 2.220446049250313e-16 && fabs(scy - isy) < 2.220446049250313e-16;
   p.isx = isx; p.isy = isy;
@@ -228,8 +235,8 @@ PCB_HD PcbResizePlan pcb_resize_plan(int sh, int sw, int dh, int dw, bool inter_
 
 PCB_HD void pcb_resize_px(const PcbView& v, const PcbResizePlan& p, int dy, int dx, int dh, int dw, uint8_t out[3]) {
   if (p.mode == PCB_RS_AREA_INT) pcb_resize_area_int_px(v, dy, dx, p.isy, p.isx, out);
-  else if (p.mode == PCB_RS_AREA_FRAC) pcb_resize_area_frac_px(v, dy, dx, dh, dw, out);
-  else pcb_resize_linear_px(v, dy, dx, dh, dw, p.mode == PCB_RS_LINEAR_AREAMODE, out);
+  else if (p.mode == PCB_RS_AREA_FRAC) pcb_resize_area_frac_px(v, dy, dx, dh, dw, p.inv_x, p.inv_y, out);
+  else pcb_resize_linear_px(v, dy, dx, dh, dw, p.mode == PCB_RS_LINEAR_AREAMODE, p.inv_x, p.inv_y, out);
 }
 
 // ---------------------------------------------------------------------------------------

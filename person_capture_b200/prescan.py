@@ -1,0 +1,801 @@
+"""Pre-scan driver: kept-span detection over a clip with the identity path on the GPU.
+
+Reference behaviour reproduced (person_capture/gui_app.py):
+  _fd_min :660-674 (on the GPU: pcb_match), _stream_ref_bank_update :922-986, reference-bank
+  build :4517-4556, _prescan :1140-1222 + :1468-1655 (stride sampling, fd9 gate, hysteresis,
+  pad/clamp/min-len/merge), bridge :1657-1668, _refine_edges :1671-1830, cache :787-920.
+Out of scope: UI command queue, decode/seek, Qt status, preview (frames come from a FrameSource).
+
+Two drivers produce the same spans/bank:
+  * prescan_sequential -- the reference's loop verbatim in structure: one FaceEmbedder.extract per
+    sample (GPU kernels, host policy), distances from pcb_match.
+  * prescan_batched    -- the throughput path: the GPU computes, for batches of
+    samples, a state-independent *superset* (upright pass; for upright-empty samples both rotated
+    probes and the heavy passes they trigger; e(x) and e(flip x) for every face), then the host
+    replays the reference's sequential state machine over those records, with distances against
+    the live bank recomputed on the GPU whenever the bank changes.  With torch.distributed, ranks
+    take contiguous time chunks, all-gather the per-face records (NCCL) and replay identically.
+The wall-clock refine budget of the reference (gui_app.py:1692-1696) is not reproduced
+(non-deterministic): refinement always completes.
+"""
+from __future__ import annotations
+
+import ast
+import hashlib
+import json
+import os
+from dataclasses import dataclass, field
+from pathlib import Path
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from .face_embedder import FaceEmbedder, _ROT_PAD
+
+FD_NONE = 9.0
+
+
+# --------------------------------------------------------------------------------------------
+# frame sources
+# --------------------------------------------------------------------------------------------
+class HostClip:
+    """Frames produced on the host (decode stand-in): get(i) -> uint8 BGR [H,W,3]."""
+
+    def __init__(self, get: Callable[[int], np.ndarray], total_frames: int):
+        self._get = get
+        self.total_frames = int(total_frames)
+
+    def host(self, i: int) -> np.ndarray:
+        return self._get(i)
+
+    def device_batch(self, eng, idxs: Sequence[int]) -> torch.Tensor:
+        return eng.to_device(np.stack([self._get(i) for i in idxs]))
+
+
+class DeviceClip:
+    """Frames already resident in HBM as a uint8 tensor [N,H,W,3] (north_star: pre-decoded in HBM)."""
+
+    def __init__(self, frames: torch.Tensor, first_index: int = 0):
+        assert frames.is_cuda and frames.dtype == torch.uint8 and frames.dim() == 4
+        self.frames = frames
+        self.first = int(first_index)
+        self.total_frames = self.first + frames.shape[0]
+
+    def host(self, i: int) -> np.ndarray:
+        return self.frames[i - self.first].cpu().numpy()
+
+    def device_batch(self, eng, idxs: Sequence[int]) -> torch.Tensor:
+        lo = idxs[0] - self.first
+        if list(idxs) == list(range(idxs[0], idxs[0] + len(idxs))):
+            return self.frames[lo:lo + len(idxs)]
+        with torch.cuda.stream(eng.stream):
+            sel = torch.as_tensor([i - self.first for i in idxs], device=self.frames.device)
+            return self.frames.index_select(0, sel)
+
+
+# --------------------------------------------------------------------------------------------
+# bank (host side: a few 512-d dot products per accepted face, as in the reference)
+# --------------------------------------------------------------------------------------------
+def _weights3(cfg) -> Tuple[float, float, float]:
+    w = getattr(cfg, "prescan_weights", (0.70, 0.25, 0.05))
+    if isinstance(w, str):
+        txt = w.strip()
+        if txt:
+            try:
+                w = json.loads(txt)
+            except Exception:
+                try:
+                    w = ast.literal_eval(txt)
+                except Exception:
+                    w = (0.70, 0.25, 0.05)
+    try:
+        if isinstance(w, (list, tuple)) and len(w) >= 3:
+            return float(w[0]), float(w[1]), float(w[2])
+    except Exception:
+        pass
+    return 0.70, 0.25, 0.05
+
+
+class RefBank:
+    """The live reference bank (rows are unit vectors) with the reference's streaming update."""
+
+    def __init__(self, cfg, rows: Optional[np.ndarray] = None):
+        self.cfg = cfg
+        self.rows: List[np.ndarray] = []
+        if rows is not None:
+            arr = np.asarray(rows, dtype=np.float32)
+            if arr.ndim == 1:
+                arr = arr.reshape(1, -1)
+            arr = arr / np.maximum(np.linalg.norm(arr, axis=1, keepdims=True), 1e-6)
+            self.rows = [r.copy() for r in arr]
+        self.version = 0
+
+    def array(self) -> Optional[np.ndarray]:
+        return np.vstack(self.rows).astype(np.float32) if self.rows else None
+
+    def __len__(self):
+        return len(self.rows)
+
+    def offer(self, vec, quality: float) -> str:
+        """-> 'skip' | 'added' | 'dup' | 'replaced' (gui_app.py:922-986)."""
+        if vec is None:
+            return "skip"
+        cfg = self.cfg
+        cap = max(1, int(getattr(cfg, "prescan_bank_max", 64)))
+        dedup = float(getattr(cfg, "prescan_diversity_dedup_cos", 0.968))
+        margin = float(getattr(cfg, "prescan_replace_margin", 0.010))
+        wa, wd, wq = _weights3(cfg)
+        v = np.asarray(vec, dtype=np.float32).reshape(-1)
+        nv = float(np.linalg.norm(v))
+        if nv <= 1e-6:
+            return "skip"
+        v = v / nv
+        if not self.rows:
+            self.rows.append(v)
+            self.version += 1
+            return "added"
+        B = np.vstack(self.rows).astype(np.float32)
+        sims = B @ v
+        top = float(sims.max())
+        if top >= dedup:
+            return "dup"
+        if len(self.rows) < cap:
+            self.rows.append(v)
+            self.version += 1
+            return "added"
+        cos_a = max(-1.0, min(1.0, float(np.dot(B[0], v))))
+        s_new = wa * (1.0 - float(np.sqrt(max(0.0, 2.0 - 2.0 * cos_a)))) + wd * (1.0 - top) \
+            + wq * float(min(max(quality or 0.0, 0.0), 1000.0) / 300.0)
+        G = B @ B.T
+        np.fill_diagonal(G, -1.0)
+        ca = np.clip(B @ B[0], -1.0, 1.0)
+        s_bank = wa * (1.0 - np.sqrt(np.maximum(0.0, 2.0 - 2.0 * ca))) + wd * (1.0 - G.max(axis=1))
+        worst = int(np.argmin(s_bank))
+        if s_new > float(s_bank[worst]) + margin:
+            self.rows[worst] = v
+            self.version += 1
+            return "replaced"
+        return "skip"
+
+
+def build_reference_bank(face: FaceEmbedder, ref_images: Sequence[np.ndarray], cfg) -> Optional[np.ndarray]:
+    """gui_app.py:4517-4556: every reference image and its mirror, best face, streaming update."""
+    bank = RefBank(cfg)
+    for img in ref_images:
+        for aug in (img, np.ascontiguousarray(img[:, ::-1])):
+            bf = FaceEmbedder.best_face(face.extract(aug))
+            if bf is not None and bf.get("feat") is not None:
+                bank.offer(bf["feat"], float(bf.get("quality", 0.0)))
+    return bank.array()
+
+
+# --------------------------------------------------------------------------------------------
+# span state machine (gui_app.py:1468-1655)
+# --------------------------------------------------------------------------------------------
+class SpanTracker:
+    def __init__(self, cfg, fps: int, total_frames: int):
+        self.cfg = cfg
+        self.fps = fps
+        self.total = int(total_frames)
+        self.stride = max(1, int(cfg.prescan_stride))
+        self.pad = int(round(cfg.prescan_pad_sec * fps))
+        self.min_len = int(round(cfg.prescan_min_segment_sec * fps))
+        self.enter = float(cfg.prescan_fd_enter)
+        self.exit = float(cfg.prescan_fd_exit)
+        self.exit_cool = int(round(max(0.0, float(getattr(cfg, "prescan_exit_cooldown_sec", 0.5))) * fps))
+        self.spans: List[Tuple[int, int]] = []
+        self.active = False
+        self.start = 0
+        self.neg_run = 0
+        self.fd9_streak = 0
+
+    def gate_skips(self) -> bool:
+        """fd9 skip gate evaluated before a sample (gui_app.py:1479-1492)."""
+        cfg = self.cfg
+        if self.active or not bool(getattr(cfg, "prescan_fd9_skip", True)):
+            return False
+        grace = max(0, int(getattr(cfg, "prescan_fd9_grace", 1)))
+        period = max(1, int(getattr(cfg, "prescan_fd9_probe_period", 2)))
+        return self.fd9_streak >= grace and (self.fd9_streak % period) != 0
+
+    def _close(self, s: int, e: int):
+        if e - s + 1 >= self.min_len:
+            if self.spans and s <= self.spans[-1][1] + 1:
+                self.spans[-1] = (self.spans[-1][0], max(self.spans[-1][1], e))
+            else:
+                self.spans.append((s, e))
+
+    def observe(self, idx: int, best: float):
+        self.fd9_streak = self.fd9_streak + 1 if best >= 8.99 else 0
+        if best <= self.enter:
+            if not self.active:
+                self.active = True
+                self.fd9_streak = 0
+                self.start = idx
+            self.neg_run = 0
+        elif self.active:
+            self.neg_run += 1
+            if self.neg_run * self.stride >= self.exit_cool or best >= self.exit:
+                self._close(max(0, self.start - self.pad), min(self.total - 1, idx + self.pad))
+                self.active = False
+                self.neg_run = 0
+                self.fd9_streak = 0
+
+    def finish(self) -> List[Tuple[int, int]]:
+        if self.active:
+            self._close(max(0, self.start - self.pad), self.total - 1)
+        return list(self.spans)
+
+
+def bridge_spans(spans, gap: int):
+    if not spans:
+        return spans
+    out = []
+    cs, ce = spans[0]
+    for s, e in spans[1:]:
+        if s - ce <= gap:
+            ce = max(ce, e)
+        else:
+            out.append((cs, ce))
+            cs, ce = s, e
+    out.append((cs, ce))
+    return out
+
+
+def sample_indices(total_frames: int, stride: int) -> List[int]:
+    return list(range(0, total_frames, max(1, stride)))
+
+
+# --------------------------------------------------------------------------------------------
+# face-side runtime configuration (gui_app.py:1162-1194, 1858-1868)
+# --------------------------------------------------------------------------------------------
+def _clamped_conf(cfg) -> float:
+    try:
+        return min(0.95, max(0.01, float(getattr(cfg, "prescan_face_conf", 0.5))))
+    except Exception:
+        return 0.5
+
+
+class _PrescanFaceMode:
+    def __init__(self, face: FaceEmbedder, cfg):
+        self.face, self.cfg = face, cfg
+
+    def __enter__(self):
+        f, cfg = self.face, self.cfg
+        self.saved = (f.conf, f.rot_adaptive)
+        f.conf = _clamped_conf(cfg)
+        f._probe_conf = float(getattr(cfg, "prescan_probe_conf", 0.03))
+        f._prescan_period = int(getattr(cfg, "prescan_rot_probe_period", 3))
+        f._prescan_probe_imgsz = int(getattr(cfg, "prescan_probe_imgsz", 512))
+        f._prescan_no_upscale_det = bool(getattr(cfg, "prescan_no_upscale_det", True))
+        f._high_90 = int(getattr(cfg, "prescan_heavy_90", 1536))
+        f._high_180 = int(getattr(cfg, "prescan_heavy_180", 1280))
+        f.configure_rotation_strategy(adaptive=False)
+        f.set_prescan_fast(True, mode="rr")
+        f.set_prescan_hint(escalate=False)
+        return f
+
+    def __exit__(self, *exc):
+        f = self.face
+        f.configure_rotation_strategy(adaptive=bool(self.saved[1]))
+        f.set_prescan_fast(False)
+        f.set_prescan_hint(escalate=False)
+        f.conf = self.saved[0]
+        return False
+
+
+def _downscaled_dims(h: int, w: int, wmax: int) -> Tuple[int, int]:
+    nh = int(round(h * (wmax / float(w))))
+    return nh, wmax
+
+
+def _maybe_downscale_host(face: FaceEmbedder, frame: np.ndarray, wmax: int, guard_positive: bool):
+    """The INTER_AREA pre-scan downscale (gui_app.py:1505-1507; refine adds `Wmax > 0`, :1744) on the GPU."""
+    h, w = frame.shape[:2]
+    if w > wmax and (wmax > 0 or not guard_positive):
+        eng = face.engine
+        if guard_positive:
+            sc = float(wmax) / float(w)
+            nh, nw = int(round(h * sc)), int(round(w * sc))
+        else:
+            nh, nw = _downscaled_dims(h, w, wmax)
+        out = eng.resize(eng.to_device(frame[None]), nh, nw, area=True)
+        eng.sync()
+        return out[0].cpu().numpy()
+    return frame
+
+
+# --------------------------------------------------------------------------------------------
+# sequential driver
+# --------------------------------------------------------------------------------------------
+def _fds_for_last_faces(face: FaceEmbedder, bank: RefBank) -> np.ndarray:
+    """fd of every face returned by the last extract() against `bank`, computed by pcb_match."""
+    eng = face.engine
+    feats = face.last_feats_dev
+    f = face.last_face_count
+    eng.set_bank(bank.array())
+    _, sim, _ = eng.match(feats, None, None, f)
+    eng.sync()
+    return 1.0 - sim[:f].cpu().numpy().astype(np.float64)
+
+
+def prescan_sequential(clip, fps: int, face: FaceEmbedder, ref_feat, cfg, log: Optional[list] = None):
+    """-> (spans, bank).  `fps` is int(round(fps)) as the reference passes it (gui_app.py:5049)."""
+    total = clip.total_frames
+    bank = RefBank(cfg, ref_feat)
+    trk = SpanTracker(cfg, fps, total)
+    wmax = int(getattr(cfg, "prescan_max_width", 0))
+    fd_add = float(getattr(cfg, "prescan_fd_add", trk.enter))
+    cooldown = int(getattr(cfg, "prescan_add_cooldown_samples", 5))
+    last_add = -10 ** 9
+    with _PrescanFaceMode(face, cfg):
+        for sample_idx, idx in enumerate(sample_indices(total, trk.stride)):
+            face._prescan_rr_mode = "full" if trk.active else "rr"
+            face.set_prescan_hint(escalate=trk.active)
+            best = FD_NONE
+            skipped = trk.gate_skips()
+            nfaces = 0
+            if not skipped:
+                frame = _maybe_downscale_host(face, clip.host(idx), wmax, guard_positive=False)
+                faces = face.extract(frame)
+                nfaces = len(faces)
+                if faces:
+                    fds = _fds_for_last_faces(face, bank)
+                    for j, f in enumerate(faces):
+                        fd = float(fds[j])
+                        best = min(best, fd)
+                        if fd <= fd_add and (sample_idx - last_add) >= cooldown and f["quality"] >= cfg.face_quality_min:
+                            if bank.offer(f["feat"], float(f["quality"])) in ("added", "replaced"):
+                                last_add = sample_idx
+                                fds = _fds_for_last_faces(face, bank)   # later faces see the updated bank
+            if log is not None:
+                log.append(dict(idx=idx, skip=skipped, best=best, active_before=trk.active, nfaces=nfaces))
+            trk.observe(idx, best)
+        spans = trk.finish()
+        spans = _post_process(spans, clip, fps, face, bank, ref_feat, cfg, trk, wmax)
+    out_bank = bank.array()
+    return spans, (out_bank if out_bank is not None else ref_feat)
+
+
+def _post_process(spans, clip, fps, face, bank: RefBank, ref_feat, cfg, trk: SpanTracker, wmax: int):
+    gap = int(round(cfg.prescan_bridge_gap_sec * fps))
+    do_bridge = getattr(cfg, "prescan_bridge_gap_sec", 0) > 0
+    if spans and do_bridge:
+        spans = bridge_spans(spans, gap)
+    spans = _refine_edges(spans, clip, fps, face, bank, ref_feat, cfg, trk, wmax)
+    if spans and do_bridge:
+        spans = bridge_spans(spans, gap)
+    return spans
+
+
+def _refine_edges(spans, clip, fps, face, bank: RefBank, ref_feat, cfg, trk: SpanTracker, wmax: int):
+    """gui_app.py:1671-1830 without the wall-clock budget."""
+    if not spans:
+        return spans
+    total = clip.total_frames
+    stride_ref = max(1, min(int(max(1, cfg.prescan_stride) // 4), int(getattr(cfg, "prescan_refine_stride_min", 3))))
+    win = int(round(max(0.0, float(getattr(cfg, "prescan_boundary_refine_sec", 0.75))) * fps))
+    search = max(int(round(max(0.0, float(cfg.prescan_pad_sec)) * fps)), win)
+    trim = bool(getattr(cfg, "prescan_trim_pad", True))
+    skip_trailing = bool(getattr(cfg, "prescan_skip_trailing_refine", True))
+    rr_old = face._prescan_rr_mode
+    face._prescan_rr_mode = "full"
+    face.set_prescan_hint(escalate=True)
+    use_bank = bank if len(bank) else RefBank(cfg, ref_feat)
+
+    def hit(j: int) -> bool:
+        frame = _maybe_downscale_host(face, clip.host(j), wmax, guard_positive=True)
+        faces = face.extract(frame)
+        if not faces:
+            return False
+        return bool((_fds_for_last_faces(face, use_bank) <= trk.enter).any())
+
+    out = []
+    for s, e in spans:
+        ls, le = s, e
+        first = None
+        j = s
+        while j <= min(e, s + search):
+            if hit(j):
+                first = j
+                break
+            j += stride_ref
+        if first is not None and trim:
+            ls = max(s, first)
+        last = None
+        if not (skip_trailing and e >= total - 1):
+            j = max(ls, e - search)
+            while j <= e:
+                if hit(j):
+                    last = j
+                j += stride_ref
+        if last is not None and trim:
+            le = min(e, last)
+        if le >= ls and (le - ls + 1) >= trk.min_len:
+            out.append((ls, le))
+    face.set_prescan_hint(escalate=False)
+    face._prescan_rr_mode = rr_old
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# batched driver: GPU superset + host replay
+# --------------------------------------------------------------------------------------------
+@dataclass
+class _Variant:
+    """Faces of one sample from one candidate final pass, in kept order."""
+    box: np.ndarray        # [k,4] int32
+    quality: np.ndarray    # [k] float64
+    rows: np.ndarray       # [k] row indices into the face table
+
+
+@dataclass
+class SampleRecord:
+    idx: int
+    up: Optional[_Variant] = None
+    hits: Dict[int, int] = field(default_factory=dict)        # rotation -> probe hits
+    heavy_raw: Dict[int, int] = field(default_factory=dict)   # rotation -> heavy-pass NMS count
+    heavy: Dict[int, _Variant] = field(default_factory=dict)
+
+
+class FaceTable:
+    """All faces of the superset: normalised features without / with flip-TTA (device + host)."""
+
+    def __init__(self):
+        self.feat_plain: List[torch.Tensor] = []
+        self.feat_flip: List[torch.Tensor] = []
+        self.count = 0
+
+    def append(self, fp: torch.Tensor, ff: torch.Tensor, k: int) -> np.ndarray:
+        rows = np.arange(self.count, self.count + k)
+        self.feat_plain.append(fp[:k])
+        self.feat_flip.append(ff[:k])
+        self.count += k
+        return rows
+
+    def finalize(self, eng):
+        with torch.cuda.stream(eng.stream):
+            if self.count:
+                self.plain = torch.cat(self.feat_plain, 0).contiguous()
+                self.flip = torch.cat(self.feat_flip, 0).contiguous()
+            else:
+                self.plain = eng.empty((1, L.FEAT_DIM), torch.float32)
+                self.flip = eng.empty((1, L.FEAT_DIM), torch.float32)
+        self.feat_plain, self.feat_flip = [], []
+
+
+def _collect_variant(eng, frames, det, idx_list, records, key, table: FaceTable, max_faces: int):
+    """Align + embed (+flip) every accumulated face of `det` (batch over idx_list)."""
+    al = eng.align(frames, det, max_faces=max_faces)
+    eng.sync()
+    total = int(al.face_total.cpu()[0])
+    counts = al.face_count.cpu().numpy()
+    if total == 0:
+        return
+    emb, emb_flip = eng.embed(al.chips, total, True)
+    fp, _, _ = eng.match(emb, None, None, total)          # normalise(e(x))
+    ff, _, _ = eng.match(emb, emb_flip, None, total)      # normalise(e(x) + e(flip x))
+    rows = table.append(fp, ff, total)
+    boxes = al.face_box[:total].cpu().numpy()
+    qual = al.quality[:total].cpu().numpy()
+    off = 0
+    for b, sidx in enumerate(idx_list):
+        k = int(counts[b])
+        if k:
+            v = _Variant(boxes[off:off + k].astype(np.int32), qual[off:off + k].astype(np.float64), rows[off:off + k])
+            if key == "up":
+                records[sidx].up = v
+            else:
+                records[sidx].heavy[key] = v
+        off += k
+
+
+def compute_superset(clip, idxs: Sequence[int], face: FaceEmbedder, cfg, batch: int = 32, max_faces: int = 4096):
+    """GPU stage of the batched pre-scan for the samples `idxs` (fast pre-scan settings must be active)."""
+    eng = face.engine
+    wmax = int(getattr(cfg, "prescan_max_width", 0))
+    records: Dict[int, SampleRecord] = {}
+    table = FaceTable()
+    for b0 in range(0, len(idxs), batch):
+        chunk = list(idxs[b0:b0 + batch])
+        frames = clip.device_batch(eng, chunk)
+        n, h, w, _ = frames.shape
+        if w > wmax:
+            nh, nw = _downscaled_dims(h, w, wmax)
+            frames = eng.resize(frames, nh, nw, area=True)
+            h, w = nh, nw
+        dyn = face.upright_size(h, w, None)
+        heavy90, heavy180 = face.heavy_sizes(h, w, dyn)
+        for i in chunk:
+            records[i] = SampleRecord(i)
+        det0 = eng.detect(frames, dyn, face.conf, min_box=int(face.scrfd_min_box_px), max_det=face.max_det)
+        eng.sync()
+        acc0 = det0.acc_count.cpu().numpy()
+        _collect_variant(eng, frames, det0, chunk, records, "up", table, max_faces)
+        empty = [b for b in range(n) if acc0[b] == 0]
+        if not empty:
+            continue
+        with torch.cuda.stream(eng.stream):
+            sub = frames.index_select(0, torch.as_tensor(empty, device=frames.device)).contiguous()
+        sub_idx = [chunk[b] for b in empty]
+        probes = {deg: eng.detect(sub, face.probe_size(dyn), face.probe_conf_value(), rot=deg, max_det=face.max_det)
+                  for deg in (90, 270)}
+        eng.sync()
+        for deg in (90, 270):
+            hits = probes[deg].raw_count.cpu().numpy()
+            for j, sidx in enumerate(sub_idx):
+                records[sidx].hits[deg] = int(hits[j])
+            sel = [j for j in range(len(sub_idx)) if hits[j] > 0]
+            if not sel:
+                continue
+            with torch.cuda.stream(eng.stream):
+                sub2 = sub.index_select(0, torch.as_tensor(sel, device=sub.device)).contiguous()
+            sel_idx = [sub_idx[j] for j in sel]
+            hv = eng.detect(sub2, face.heavy_size_fast(deg, heavy90, heavy180), face.rotated_conf(deg), rot=deg, pad=_ROT_PAD,
+                            fix_mode=L.FIX_UNPAD, min_box=0, max_det=face.max_det)
+            eng.sync()
+            raw = hv.raw_count.cpu().numpy()
+            for j, sidx in enumerate(sel_idx):
+                records[sidx].heavy_raw[deg] = int(raw[j])
+            _collect_variant(eng, sub2, hv, sel_idx, records, deg, table, max_faces)
+    table.finalize(eng)
+    return records, table
+
+
+class _LiveDistances:
+    """fd of every table row against the live bank, for both flip variants; recomputed on the GPU
+    (pcb_match) whenever the bank version changes."""
+
+    def __init__(self, eng, table: FaceTable):
+        self.eng, self.table = eng, table
+        self.version = None
+        self.fd_plain = self.fd_flip = None
+
+    def get(self, bank: RefBank):
+        if self.version != bank.version or self.fd_plain is None:
+            eng, t = self.eng, self.table
+            if t.count == 0:
+                self.fd_plain = self.fd_flip = np.zeros((0,), np.float64)
+            else:
+                eng.set_bank(bank.array())
+                _, s0, _ = eng.match(t.plain, None, None, t.count)
+                _, s1, _ = eng.match(t.flip, None, None, t.count)
+                eng.sync()
+                self.fd_plain = 1.0 - s0[:t.count].cpu().numpy().astype(np.float64)
+                self.fd_flip = 1.0 - s1[:t.count].cpu().numpy().astype(np.float64)
+            self.version = bank.version
+        return self.fd_plain, self.fd_flip
+
+
+def replay(records: Dict[int, SampleRecord], table: FaceTable, feats_host, idxs: Sequence[int], fps: int, total_frames: int,
+           face: FaceEmbedder, ref_feat, cfg, log: Optional[list] = None):
+    """Host replay of the reference's sequential loop over precomputed superset records."""
+    bank = RefBank(cfg, ref_feat)
+    trk = SpanTracker(cfg, fps, total_frames)
+    dist = _LiveDistances(face.engine, table)
+    fd_add = float(getattr(cfg, "prescan_fd_add", trk.enter))
+    cooldown = int(getattr(cfg, "prescan_add_cooldown_samples", 5))
+    last_add = -10 ** 9
+    plain_h, flip_h = feats_host
+    for sample_idx, idx in enumerate(idxs):
+        rec = records[idx]
+        active = trk.active
+        best = FD_NONE
+        skipped = trk.gate_skips()
+        nfaces = 0
+        if not skipped:
+            face._frame_idx += 1
+            chosen = rec.up
+            if chosen is None:
+                face._no_face_streak += 1
+                face._rot_cycle += 1
+                if active:
+                    order = (90, 270)
+                else:
+                    order = ((90, 270)[face._prescan_rr % 2],)
+                    face._prescan_rr += 1
+                for deg in order:
+                    if rec.hits.get(deg, 0) == 0 or rec.heavy_raw.get(deg, 0) == 0:
+                        continue
+                    if deg in rec.heavy:
+                        chosen = rec.heavy[deg]
+                        break
+            else:
+                face._no_face_streak = 0
+                face._last_face_idx = face._frame_idx
+                face._rot_cycle = 0
+            if chosen is not None:
+                k = len(chosen.rows)
+                nfaces = k
+                area = (chosen.box[:, 2] - chosen.box[:, 0]) * (chosen.box[:, 3] - chosen.box[:, 1])
+                order = sorted(range(k), key=lambda i: (chosen.quality[i], area[i]), reverse=True)
+                for i in order:
+                    row = int(chosen.rows[i])
+                    fdp, fdf = dist.get(bank)
+                    fd = float(fdf[row] if active else fdp[row])
+                    best = min(best, fd)
+                    q = float(chosen.quality[i])
+                    if fd <= fd_add and (sample_idx - last_add) >= cooldown and q >= cfg.face_quality_min:
+                        vec = (flip_h if active else plain_h)[row]
+                        if bank.offer(vec, q) in ("added", "replaced"):
+                            last_add = sample_idx
+        if log is not None:
+            log.append(dict(idx=idx, skip=skipped, best=best, active_before=active, nfaces=nfaces))
+        trk.observe(idx, best)
+    return trk, bank
+
+
+def prescan_batched(clip, fps: int, face: FaceEmbedder, ref_feat, cfg, batch: int = 32, log: Optional[list] = None,
+                    dist_group=None):
+    """Throughput pre-scan.  With torch.distributed initialised (dist_group or the default group), the
+    sample list is split into contiguous chunks per rank, per-face records are all-gathered and every
+    rank replays the same sequence."""
+    import torch.distributed as dist
+    total = clip.total_frames
+    stride = max(1, int(cfg.prescan_stride))
+    idxs = sample_indices(total, stride)
+    world, rank = 1, 0
+    if dist.is_available() and dist.is_initialized():
+        world, rank = dist.get_world_size(dist_group), dist.get_rank(dist_group)
+    if int(getattr(cfg, "prescan_probe_imgsz", 512)) > int(face.fast_no_face_imgsz):
+        raise RuntimeError("prescan_batched requires prescan_probe_imgsz <= fast_no_face_imgsz (the upright size would "
+                           "depend on the no-face streak, SURVEY.md H1); use prescan_sequential")
+    with _PrescanFaceMode(face, cfg):
+        per = (len(idxs) + world - 1) // world
+        mine = idxs[rank * per:(rank + 1) * per]
+        records, table = compute_superset(clip, mine, face, cfg, batch=batch)
+        face.engine.sync()
+        plain_h = table.plain[:table.count].cpu().numpy() if table.count else np.zeros((0, L.FEAT_DIM), np.float32)
+        flip_h = table.flip[:table.count].cpu().numpy() if table.count else np.zeros((0, L.FEAT_DIM), np.float32)
+        if world > 1:
+            records, table, plain_h, flip_h = _gather_shards(face.engine, records, table, plain_h, flip_h, world, dist_group)
+        trk, bank = replay(records, table, (plain_h, flip_h), idxs, fps, total, face, ref_feat, cfg, log)
+        spans = trk.finish()
+        wmax = int(getattr(cfg, "prescan_max_width", 0))
+        spans = _post_process(spans, clip, fps, face, bank, ref_feat, cfg, trk, wmax)
+    out_bank = bank.array()
+    return spans, (out_bank if out_bank is not None else ref_feat)
+
+
+def _gather_shards(eng, records, table, plain_h, flip_h, world, group):
+    """All-gather per-face records: features through NCCL (device tensors), the small per-sample
+    metadata through all_gather_object."""
+    import torch.distributed as dist
+    counts = [None] * world
+    dist.all_gather_object(counts, table.count, group=group)
+    recs = [None] * world
+    dist.all_gather_object(recs, records, group=group)
+    cap = max(max(counts), 1)
+    dev = table.plain.device if table.count else eng.tdev
+    backend_cuda = dist.get_backend(group) == "nccl"
+    send = torch.zeros((2, cap, L.FEAT_DIM), dtype=torch.float32, device=dev if backend_cuda else "cpu")
+    if table.count:
+        send[0, :table.count] = table.plain[:table.count] if backend_cuda else torch.from_numpy(plain_h)
+        send[1, :table.count] = table.flip[:table.count] if backend_cuda else torch.from_numpy(flip_h)
+    recv = [torch.empty_like(send) for _ in range(world)]
+    if backend_cuda:
+        torch.cuda.current_stream().wait_stream(eng.stream)
+    dist.all_gather(recv, send, group=group)
+    merged: Dict[int, SampleRecord] = {}
+    plains, flips = [], []
+    base = 0
+    for r in range(world):
+        for idx, rec in recs[r].items():
+            for v in [rec.up] + list(rec.heavy.values()):
+                if v is not None:
+                    v.rows = v.rows + base
+            merged[idx] = rec
+        plains.append(recv[r][0, :counts[r]])
+        flips.append(recv[r][1, :counts[r]])
+        base += counts[r]
+    new = FaceTable()
+    new.count = base
+    allp = torch.cat(plains, 0) if base else torch.zeros((1, L.FEAT_DIM))
+    allf = torch.cat(flips, 0) if base else torch.zeros((1, L.FEAT_DIM))
+    if backend_cuda:
+        torch.cuda.current_stream().synchronize()
+    new.plain = allp.to(eng.tdev).contiguous() if eng is not None else allp
+    new.flip = allf.to(eng.tdev).contiguous() if eng is not None else allf
+    return merged, new, allp[:base].cpu().numpy(), allf[:base].cpu().numpy()
+
+
+# --------------------------------------------------------------------------------------------
+# prescan cache (gui_app.py:787-920): same key derivation, file name and array layout
+# --------------------------------------------------------------------------------------------
+CACHE_KEYS = (
+    "prescan_stride", "prescan_max_width", "prescan_decode_max_w", "prescan_face_conf", "prescan_fd_enter", "prescan_fd_add",
+    "prescan_fd_exit", "prescan_add_cooldown_samples", "prescan_rot_probe_period", "prescan_probe_imgsz",
+    "prescan_no_upscale_det", "prescan_probe_conf", "prescan_heavy_90", "prescan_heavy_180", "prescan_min_segment_sec",
+    "prescan_pad_sec", "prescan_bridge_gap_sec", "prescan_exit_cooldown_sec", "prescan_boundary_refine_sec",
+    "prescan_refine_stride_min", "prescan_trim_pad", "prescan_skip_trailing_refine", "prescan_refine_budget_sec",
+    "prescan_bank_max", "prescan_diversity_dedup_cos", "prescan_replace_margin", "prescan_fd9_skip", "prescan_fd9_grace",
+    "prescan_fd9_probe_period", "prescan_weights", "face_model", "clip_face_backbone", "clip_face_pretrained", "use_arcface",
+)
+
+
+def _identity_of(path: str) -> dict:
+    p = str(path or "").strip()
+    if not p:
+        return {"path": "", "missing": True}
+    ap = os.path.abspath(p)
+    try:
+        st = os.stat(ap)
+    except Exception:
+        return {"path": ap, "missing": True}
+    return {"path": ap, "size": int(st.st_size or 0), "mtime_ns": int(st.st_mtime_ns)}
+
+
+def _plain(v):
+    if isinstance(v, (tuple, list)):
+        return [_plain(x) for x in v]
+    if isinstance(v, (np.floating, np.integer)):
+        return v.item()
+    return v
+
+
+def cache_meta(cfg, fps: float, total_frames: int) -> dict:
+    meta = {
+        "version": 1,
+        "video": _identity_of(getattr(cfg, "video", "")),
+        "refs": [_identity_of(p) for p in (q.strip() for q in str(getattr(cfg, "ref", "") or "").split(";")) if p],
+        "fps": round(float(fps or 0.0), 6),
+        "total_frames": int(total_frames or 0),
+        "settings": {k: _plain(getattr(cfg, k, None)) for k in CACHE_KEYS},
+    }
+    meta["key"] = hashlib.sha256(json.dumps(meta, sort_keys=True, separators=(",", ":")).encode("utf-8")).hexdigest()
+    return meta
+
+
+def cache_file(cfg, meta: dict, root=None) -> Path:
+    base = Path(root) if root is not None else Path(str(getattr(cfg, "prescan_cache_dir", "prescan_cache") or "prescan_cache"))
+    return base / f"{meta.get('key') or ''}.npz"
+
+
+def save_cache(cfg, fps: float, total_frames: int, spans, ref_face_feat, root=None) -> Optional[Path]:
+    mode = str(getattr(cfg, "prescan_cache_mode", "auto") or "auto").lower()
+    if mode not in ("auto", "refresh", "reuse"):
+        return None
+    meta = cache_meta(cfg, fps, total_frames)
+    path = cache_file(cfg, meta, root)
+    path.parent.mkdir(parents=True, exist_ok=True)
+    if ref_face_feat is None:
+        feat, has = np.zeros((0, 0), np.float32), np.array([0], np.uint8)
+    else:
+        feat = np.asarray(ref_face_feat, np.float32)
+        feat = feat.reshape(1, -1) if feat.ndim == 1 else feat
+        has = np.array([1], np.uint8)
+    tmp = path.with_suffix(path.suffix + ".tmp")
+    with open(tmp, "wb") as fh:
+        np.savez_compressed(fh, meta=np.array(json.dumps(meta, sort_keys=True), dtype=np.str_),
+                            spans=np.asarray(spans or [], np.int64).reshape(-1, 2), ref_face_feat=feat, has_ref=has)
+    os.replace(tmp, path)
+    return path
+
+
+def load_cache(cfg, fps: float, total_frames: int, root=None):
+    """-> (hit, spans, ref_feat, meta)"""
+    mode = str(getattr(cfg, "prescan_cache_mode", "auto") or "auto").lower()
+    if mode not in ("auto", "reuse"):
+        return False, [], None, None
+    meta = cache_meta(cfg, fps, total_frames)
+    path = cache_file(cfg, meta, root)
+    if not path.is_file():
+        return False, [], None, meta
+    try:
+        with np.load(str(path), allow_pickle=False) as z:
+            stored = json.loads(str(z["meta"].item()))
+            if stored.get("key") != meta["key"] or stored.get("version") != meta["version"]:
+                return False, [], None, meta
+            arr = np.asarray(z["spans"], np.int64).reshape(-1, 2)
+            spans = [(int(s), int(e)) for s, e in arr.tolist() if e >= s]
+            has = bool(int(np.asarray(z["has_ref"]).reshape(-1)[0])) if "has_ref" in z.files else False
+            ref = None
+            if has and "ref_face_feat" in z.files:
+                a = np.asarray(z["ref_face_feat"], np.float32)
+                if a.size:
+                    ref = a.reshape(a.shape[0], -1) if a.ndim >= 2 else a.reshape(1, -1)
+            return True, spans, ref, meta
+    except Exception:
+        return False, [], None, meta

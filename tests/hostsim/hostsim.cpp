@@ -12,6 +12,14 @@ void hs_resize(const uint8_t* src, int h, int w, int rot, int pad, uint8_t* dst,
     for (int x = 0; x < dw; ++x) pcb_resize_px(v, p, y, x, dh, dw, dst + ((long long)y * dw + x) * 3);
 }
 
+void hs_resize_factor(const uint8_t* src, int h, int w, uint8_t* dst, double fx, double fy, int inter_area) {
+  PcbView v = pcb_make_view(src, h, w, 0, 0);
+  const int dh = pcb_cvround_d((double)h * fy), dw = pcb_cvround_d((double)w * fx);
+  PcbResizePlan p = pcb_resize_plan(h, w, dh, dw, inter_area != 0, fx, fy);
+  for (int y = 0; y < dh; ++y)
+    for (int x = 0; x < dw; ++x) pcb_resize_px(v, p, y, x, dh, dw, dst + ((long long)y * dw + x) * 3);
+}
+
 void hs_view(const uint8_t* src, int h, int w, int rot, int pad, uint8_t* dst) {
   PcbView v = pcb_make_view(src, h, w, rot, pad);
   for (int y = 0; y < v.vh; ++y)

@@ -1,0 +1,329 @@
+"""GPU parity tests, kernel by kernel, through the C ABI (libpcb200.so) against the CPU oracle.
+
+Bars: bit-exact for byte / integer / index work (K0, K1, K3, K4 chips); tolerances stated in each
+test for floating point (convolutions: fp16 storage + fp32 accumulate vs fp32 oracle).
+"""
+import numpy as np
+import pytest
+import torch
+import cv2
+
+import pcb_test_helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev(eng, arr):
+    t = eng.to_device(arr)
+    eng.sync()
+    return t
+
+
+# ---------------------------------------------------------------- K0
+@pytest.mark.parametrize("h,w,nh,nw,area", [
+    (1080, 1920, 540, 960, True),     # config 2: exact 2x (vectorised kernel)
+    (360, 640, 234, 416, True),       # config 1: fractional area table
+    (300, 450, 100, 150, True),       # integer 3x
+    (150, 90, 112, 112, True),        # INTER_AREA with one up-scaled axis
+    (77, 53, 112, 112, False),        # bilinear up-scale
+    (540, 960, 288, 512, False),      # bilinear down-scale
+    (200, 256, 100, 128, False),      # INTER_LINEAR with exact 2x == INTER_AREA
+])
+def test_resize_bit_exact(engine_25g_r50, h, w, nh, nw, area):
+    eng = engine_25g_r50
+    rng = np.random.default_rng(h * 7 + w)
+    imgs = np.stack([H.smooth_image(rng, h, w) for _ in range(2)])
+    out = eng.resize(_dev(eng, imgs), nh, nw, area=area)
+    eng.sync()
+    got = out.cpu().numpy()
+    for i in range(2):
+        ref = cv2.resize(imgs[i], (nw, nh), interpolation=cv2.INTER_AREA if area else cv2.INTER_LINEAR)
+        assert np.array_equal(got[i], ref)
+
+
+# ---------------------------------------------------------------- K1
+@pytest.mark.parametrize("h,w,S,rot,pad", [
+    (540, 960, 512, 0, 0), (234, 416, 416, 0, 0), (234, 416, 416, 90, 0), (234, 416, 1536, 270, 24),
+    (360, 640, 640, 180, 24), (512, 512, 640, 0, 0), (700, 650, 1280, 0, 0), (576, 1024, 512, 0, 0),
+])
+def test_letterbox_bit_exact(engine_25g_r50, h, w, S, rot, pad):
+    eng = engine_25g_r50
+    rng = np.random.default_rng(S + rot + h)
+    img = H.smooth_image(rng, h, w)
+    patches, det = eng.letterbox(_dev(eng, img[None]), S, rot=rot, pad=pad, want_det_img=True)
+    eng.sync()
+    # oracle: InsightFace letterbox with real cv2 calls
+    ROT = {90: cv2.ROTATE_90_CLOCKWISE, 180: cv2.ROTATE_180, 270: cv2.ROTATE_90_COUNTERCLOCKWISE}
+    src = cv2.rotate(img, ROT[rot]) if rot else img
+    if pad:
+        src = cv2.copyMakeBorder(src, pad, pad, pad, pad, cv2.BORDER_REPLICATE)
+    im_ratio = float(src.shape[0]) / src.shape[1]
+    if im_ratio > 1.0:
+        nh, nw = S, int(S / im_ratio)
+    else:
+        nw, nh = S, int(S * im_ratio)
+    ref = np.zeros((S, S, 3), np.uint8)
+    ref[:nh, :nw] = cv2.resize(src, (nw, nh))
+    assert np.array_equal(det.cpu().numpy()[0], ref)
+    # patch tensor == 3x3 stride-2 neighbourhood of blobFromImage(ref)
+    blob = cv2.dnn.blobFromImage(ref, 1.0 / 128, (S, S), (127.5, 127.5, 127.5), swapRB=True)[0]   # [3,S,S]
+    bp = np.pad(blob, ((0, 0), (1, 1), (1, 1)))
+    P = patches.cpu().numpy()[0].astype(np.float32)     # [S/2+2, S/2+2, 32]
+    half = S // 2
+    for ky in range(3):
+        for kx in range(3):
+            want = bp[:, ky:ky + S:2, kx:kx + S:2]        # [3, half, half]
+            got = P[1:half + 1, 1:half + 1, (ky * 3 + kx) * 3:(ky * 3 + kx) * 3 + 3].transpose(2, 0, 1)
+            assert np.array_equal(got, want), (ky, kx)
+    assert not P[0].any() and not P[:, 0].any() and not P[..., 27:].any()
+
+
+# ---------------------------------------------------------------- K2 (graphs)
+def _scrfd_heads(eng, name, blob_img, S, impl):
+    """Run letterbox + SCRFD graph on the GPU; return the three raw head maps [30,h,w]."""
+    from person_capture_b200 import _lib as L
+    eng.set_conv_impl(impl)
+    res = eng.detect(_dev(eng, blob_img[None]), S, 0.5)
+    eng.sync()
+    g = eng.graphs[L.MODEL_SCRFD]
+    return [eng.get_tensor(L.MODEL_SCRFD, t)[0, :30] for t in g.outputs], res
+
+
+@pytest.mark.parametrize("name,fix,S", [("scrfd_2.5g_bnkps", "engine_25g_r50", 320), ("scrfd_10g_bnkps", "engine_10g_r50", 512)])
+@pytest.mark.parametrize("impl", [1, 0])
+def test_scrfd_heads_match_oracle(request, name, fix, S, impl):
+    """fp16 conv path vs fp32 oracle on identical weights: head maps agree to 2e-2 absolute on logits
+    / distances (values are O(1..10)); impl 1 = CUDA-core validation kernel, 0 = tcgen05."""
+    eng = request.getfixturevalue(fix)
+    from person_capture_b200 import synth, _lib as L
+    clip = synth.ClipSpec(S, S, 10, seed=3, target_segments=[(0, 9)])
+    img = clip.frame(2)
+    heads, _ = _scrfd_heads(eng, name, img, S, impl)
+    eng.set_conv_impl(0)
+    net = H.oracle_scrfd(name)
+    blob = cv2.dnn.blobFromImage(img, 1.0 / 128, (S, S), (127.5, 127.5, 127.5), swapRB=True)
+    import torch as T
+    raws = [r[0].numpy() for r in net.head_raw(T.from_numpy(blob))]
+    for lvl, (g, r) in enumerate(zip(heads, raws)):
+        assert g.shape == r.shape
+        err = np.abs(g - r)
+        assert err.max() < 0.06 and err.mean() < 4e-3, (lvl, float(err.max()), float(err.mean()))
+
+
+@pytest.mark.parametrize("impl", [1, 0])
+def test_arcface_embeddings_match_oracle(engine_25g_r50, impl):
+    """cosine(e_gpu, e_oracle) >= 0.999 (north_star tolerance) on R50, with and without flip."""
+    eng = engine_25g_r50
+    from person_capture_b200 import synth
+    rng = np.random.default_rng(11)
+    chips = []
+    for i in range(5):
+        canvas = synth.background(rng, 150, 150, clutter=2)
+        synth.paste_face(canvas, 40 + i, 75, 75, 112, float(rng.uniform(-5, 5)))
+        chips.append(np.ascontiguousarray(canvas[19:131, 19:131]))
+    chips = np.stack(chips)
+    eng.set_conv_impl(impl)
+    emb, emb_flip = eng.embed(_dev(eng, chips), len(chips), True)
+    eng.sync()
+    eng.set_conv_impl(0)
+    from oracle.face_embedder import arcface_preprocess
+    X = np.stack([arcface_preprocess(c) for c in chips] + [arcface_preprocess(cv2.flip(c, 1)) for c in chips])
+    ref = H.oracle_arcface("arcface_r50").run(X)
+    ge, gf = emb.cpu().numpy(), emb_flip.cpu().numpy()
+    for i in range(len(chips)):
+        assert H.cos(ge[i], ref[i]) >= 0.999, (i, H.cos(ge[i], ref[i]))
+        assert H.cos(gf[i], ref[len(chips) + i]) >= 0.999
+    # distinct identities must not collapse onto each other
+    assert H.cos(ref[0], ref[1]) < 0.9
+
+
+# ---------------------------------------------------------------- K3
+class _FakeNet:
+    def __init__(self, outs):
+        self.outs = outs
+
+    def run(self, blob):
+        return self.outs
+
+
+@pytest.mark.parametrize("S,thr,seed,rot,pad,fix", [(512, 0.5, 0, 0, 0, 0), (416, 0.03, 1, 0, 0, 0), (640, 0.3, 2, 90, 24, 3),
+                                                    (320, 0.2, 3, 270, 0, 0), (512, 0.2, 4, 0, 16, 2)])
+def test_decode_nms_bit_exact(engine_25g_r50, S, thr, seed, rot, pad, fix):
+    """Same head maps on both sides -> identical NMS keep lists, boxes, landmarks and accumulated ints."""
+    from oracle.scrfd_detect import SCRFDOracle
+    from oracle.face_embedder import FaceEmbedderOracle
+    from person_capture_b200 import _lib as L
+    eng = engine_25g_r50
+    rng = np.random.default_rng(seed)
+    H0, W0 = (300, 400)
+    vh, vw = ((W0, H0) if rot in (90, 270) else (H0, W0))
+    vh, vw = vh + 2 * pad, vw + 2 * pad
+    reg_scale = np.array([1.1, 0.9, 1.3], np.float32)
+    heads_t, outs_sc, outs_bb, outs_kp = [], [], [], []
+    for s in (8, 16, 32):
+        h = S // s
+        logit = rng.normal(-6.0, 2.0, (h, h, 2)).astype(np.float16)
+        # plant clusters of high scores with plausible boxes
+        for _ in range(12):
+            y, x = rng.integers(0, h, 2)
+            logit[y, x, rng.integers(0, 2)] = np.float16(rng.uniform(-1, 6))
+        reg = rng.uniform(0.5, 6.0, (h, h, 8)).astype(np.float16)
+        kps = rng.uniform(-3.0, 3.0, (h, h, 20)).astype(np.float16)
+        hm = np.zeros((1, h + 2, h + 2, 32), np.float16)
+        hm[0, 1:-1, 1:-1, 0:2] = logit
+        hm[0, 1:-1, 1:-1, 2:10] = reg
+        hm[0, 1:-1, 1:-1, 10:30] = kps
+        heads_t.append(_dev(eng, hm))
+        sc = (1.0 / (1.0 + np.exp(-logit.astype(np.float64)))).astype(np.float32).reshape(-1, 1)
+        outs_sc.append(sc)
+        outs_bb.append((reg.astype(np.float32) * reg_scale[len(outs_bb)]).reshape(-1, 4))
+        outs_kp.append(kps.astype(np.float32).reshape(-1, 10))
+    # oracle: InsightFace post-processing on the same tensors, fed through a fake net
+    det = SCRFDOracle(_FakeNet(outs_sc + outs_bb + outs_kp))
+    det.det_thresh = thr
+    img = np.zeros((vh, vw, 3), np.uint8)
+    bbs, kpss = det.detect(img, (S, S))
+    im_ratio = float(vh) / vw
+    new_h = S if im_ratio > 1.0 else int(S * im_ratio)
+    det_scale = float(new_h) / vh
+    res = eng.decode_nms(heads_t, reg_scale, S, thr, det_scale, (H0, W0), rot=rot, pad=pad, fix_mode=fix, min_box=8, max_det=512)
+    eng.sync()
+    n = int(res.raw_count.cpu()[0])
+    assert n == len(bbs)
+    assert np.array_equal(res.det.cpu().numpy()[0, :n], bbs.astype(np.float32))
+    assert np.array_equal(res.kps.cpu().numpy()[0, :n].reshape(n, 5, 2), kpss.astype(np.float32))
+    # accumulate (+ per-pass fix) as the oracle FaceEmbedder does it
+    acc = []
+    for i in range(n):
+        bb = np.asarray(bbs[i]).copy()
+        kp = np.asarray(kpss[i]).copy()
+        if fix == L.FIX_UNPAD:
+            bb[:4] -= np.array([pad] * 4, dtype=bb.dtype)
+            kp[..., 0] -= pad
+            kp[..., 1] -= pad
+        elif fix == L.FIX_PADPROBE:
+            bb[:4] -= np.array([pad] * 4, dtype=np.float32)
+            bb[0] = max(0.0, min(float(W0 - 1), float(bb[0])))
+            bb[1] = max(0.0, min(float(H0 - 1), float(bb[1])))
+            bb[2] = max(bb[0] + 1.0, min(float(W0), float(bb[2])))
+            bb[3] = max(bb[1] + 1.0, min(float(H0), float(bb[3])))
+            kp = np.asarray(kp, dtype=np.float32)
+            kp[..., 0] = np.clip(kp[..., 0] - pad, 0, W0 - 1)
+            kp[..., 1] = np.clip(kp[..., 1] - pad, 0, H0 - 1)
+        from oracle.face_embedder import _unrotate
+        x1, y1, x2, y2 = [int(v) for v in bb[:4]]
+        ax, ay = _unrotate(x1, y1, rot, W0, H0)
+        bx, by = _unrotate(x2, y2, rot, W0, H0)
+        xa1, ya1, xa2, ya2 = min(ax, bx), min(ay, by), max(ax, bx), max(ay, by)
+        xa1 = max(0, min(W0 - 1, xa1)); ya1 = max(0, min(H0 - 1, ya1))
+        xa2 = max(xa1 + 1, min(W0, xa2)); ya2 = max(ya1 + 1, min(H0, ya2))
+        if xa2 - xa1 <= 2 or ya2 - ya1 <= 2 or xa2 - xa1 < 8 or ya2 - ya1 < 8:
+            continue
+        pts = []
+        for px, py in np.asarray(kp, np.float32).reshape(-1, 2):
+            ox, oy = _unrotate(float(px), float(py), rot, W0, H0)
+            pts.append([float(ox - xa1), float(oy - ya1)])
+        acc.append(((xa1, ya1, xa2, ya2), np.asarray(pts, np.float32), float(bb[4])))
+    m = int(res.acc_count.cpu()[0])
+    assert m == len(acc)
+    gb = res.acc_box.cpu().numpy()[0, :m]
+    gk = res.acc_kps.cpu().numpy()[0, :m].reshape(m, 5, 2)
+    for i in range(m):
+        assert tuple(gb[i]) == acc[i][0]
+        assert np.array_equal(gk[i], acc[i][1])
+
+
+# ---------------------------------------------------------------- K4
+def test_align_chips_bit_exact(engine_25g_r50):
+    """Given accumulated boxes + landmarks, chips equal cv2's LMedS + warpAffine bit for bit and quality
+    matches np.var(Laplacian) to 1e-9 relative; also exercises suppression and the resize fallback."""
+    from oracle import face_embedder as OF
+    from person_capture_b200 import synth
+    from person_capture_b200.engine import DetectResult
+    eng = engine_25g_r50
+    rng = np.random.default_rng(5)
+    n, Hh, Ww, max_det = 3, 300, 400, 16
+    frames = np.stack([synth.background(rng, Hh, Ww) for _ in range(n)])
+    acc_box = np.zeros((n, max_det, 4), np.int32)
+    acc_kps = np.zeros((n, max_det, 10), np.float32)
+    acc_score = np.zeros((n, max_det), np.float32)
+    acc_count = np.zeros((n,), np.int32)
+    truth = []
+    for i in range(n):
+        k = 0
+        for j in range(4):
+            side = int(rng.integers(30, 140))
+            x1 = int(rng.integers(0, Ww - side)); y1 = int(rng.integers(0, Hh - side))
+            pts = (synth.ARC_DST / 112.0 * side + rng.normal(0, 0.03 * side, (5, 2))).astype(np.float32)
+            if j == 3:
+                pts = pts[::-1].copy() * np.float32(0.2)   # non-canonical, tiny roll -> plain resize
+            acc_box[i, k] = (x1, y1, x1 + side, y1 + side)
+            acc_kps[i, k] = pts.reshape(-1)
+            acc_score[i, k] = np.float32(rng.uniform(0.5, 1.0))
+            k += 1
+        # a duplicate of entry 0 with a lower score must be suppressed (IoU >= 0.45)
+        acc_box[i, k] = acc_box[i, 0] + np.array([1, 1, 1, 1])
+        acc_kps[i, k] = acc_kps[i, 0]
+        acc_score[i, k] = acc_score[i, 0] - np.float32(0.1)
+        k += 1
+        acc_count[i] = k
+    det = DetectResult(None, None, None, _dev(eng, acc_box), _dev(eng, acc_kps), _dev(eng, acc_score), _dev(eng, acc_count), None)
+    fr = _dev(eng, frames)
+    al = eng.align(fr, det, max_faces=64)
+    eng.sync()
+    total = int(al.face_total.cpu()[0])
+    gi = 0
+    exact = 0
+    for i in range(n):
+        dets = [(tuple(int(v) for v in acc_box[i, j]), acc_kps[i, j].reshape(5, 2), float(acc_score[i, j])) for j in range(acc_count[i])]
+        dets.sort(key=lambda t: (t[2], (t[0][2] - t[0][0]) * (t[0][3] - t[0][1])), reverse=True)
+        kept = []
+        for box, pts, sc in dets:
+            if all(OF.iou_int(box, q[0]) < 0.45 for q in kept):
+                kept.append((box, pts, sc))
+        assert int(al.face_count.cpu()[i]) == len(kept)
+        for (x1, y1, x2, y2), pts, _ in kept:
+            crop = frames[i][y1:y2, x1:x2]
+            canon = OF.canon_5pts(pts)
+            chip = OF.align_by_5pts(crop, canon) if canon is not None else OF.upright_by_eye_roll(crop, pts)
+            got = al.chips[gi].cpu().numpy()
+            assert tuple(al.face_box[gi].cpu().numpy()) == (x1, y1, x2, y2)
+            assert int(al.face_frame[gi].cpu()) == i
+            if np.array_equal(got, chip):
+                exact += 1
+            else:
+                # the only tolerated difference: LS vs LM final fit flipping a 1/32-px sample position
+                assert np.abs(got.astype(int) - chip.astype(int)).max() <= 2 and (got != chip).mean() < 0.02
+            q = OF.face_quality(got)
+            assert abs(float(al.quality[gi].cpu()) - q) <= 1e-9 * max(1.0, q)
+            gi += 1
+    assert gi == total
+    assert exact >= int(0.95 * total)
+
+
+# ---------------------------------------------------------------- K5
+def test_match_against_numpy(engine_25g_r50):
+    eng = engine_25g_r50
+    rng = np.random.default_rng(9)
+    f, B = 37, 1000
+    emb = rng.normal(size=(f, 512)).astype(np.float32)
+    embf = rng.normal(size=(f, 512)).astype(np.float32)
+    bank = rng.normal(size=(B, 512)).astype(np.float32)
+    bank /= np.linalg.norm(bank, axis=1, keepdims=True)
+    bank[17] = (emb[3] + embf[3]) / np.linalg.norm(emb[3] + embf[3])
+    use = (rng.random(f) < 0.5).astype(np.uint8)
+    use[3] = 1
+    eng.set_bank(bank)
+    feat, sim, arg = eng.match(_dev(eng, emb), _dev(eng, embf), _dev(eng, use), f)
+    eng.sync()
+    v = emb + embf * use[:, None]
+    v = v / np.maximum(np.linalg.norm(v, axis=1, keepdims=True), 1e-6)
+    sims = v @ bank.T
+    assert np.allclose(feat.cpu().numpy(), v, atol=2e-6)
+    assert np.allclose(sim.cpu().numpy(), sims.max(1), atol=5e-6)      # |dfd| <= 1e-3 is the north_star bar
+    assert np.array_equal(arg.cpu().numpy(), sims.argmax(1))
+    assert int(arg.cpu()[3]) == 17 and abs(float(sim.cpu()[3]) - 1.0) < 1e-5
+    eng.set_bank(None)
+    _, sim0, _ = eng.match(_dev(eng, emb), None, None, f)
+    eng.sync()
+    assert np.all(1.0 - sim0.cpu().numpy() == 9.0)                      # reference sentinel fd = 9.0
