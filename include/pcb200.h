@@ -43,6 +43,12 @@ int pcb_set_conv_impl(pcb_ctx* ctx, int impl);
 long long pcb_launch_count(pcb_ctx* ctx);
 void pcb_reset_launch_count(pcb_ctx* ctx);
 
+/* Profiling for bench.py: when on, every convolution launch is bracketed by CUDA events on the
+ * context's stream and its algorithmic FLOPs (2*out_px*cout*cin*taps from the layer shape) are
+ * accumulated.  pcb_profile_read synchronises and returns the totals since the last reset. */
+int pcb_set_profile(pcb_ctx* ctx, int on);
+int pcb_profile_read(pcb_ctx* ctx, double* conv_ms, double* conv_flops, long long* conv_launches, int reset);
+
 /* ---- graphs (replaces ort.InferenceSession construction, face_embedder.py:1102-1107, 891-915) */
 enum { PCB_OP_CONV = 1, PCB_OP_AFFINE = 2, PCB_OP_MAXPOOL3S2 = 3, PCB_OP_AVGPOOL2 = 4,
        PCB_OP_UPSAMPLE_ADD = 5, PCB_OP_ADD = 6, PCB_OP_AFFINE_FLATTEN = 7, PCB_OP_FC = 8 };

@@ -22,7 +22,7 @@ FIX_NONE, FIX_SCALE, FIX_PADPROBE, FIX_UNPAD = 0, 1, 2, 3
 
 EXPORTS = (
     "pcb_create", "pcb_destroy", "pcb_last_error", "pcb_sync", "pcb_set_conv_impl", "pcb_launch_count",
-    "pcb_reset_launch_count", "pcb_model_load", "pcb_model_get_tensor", "pcb_resize_area", "pcb_resize_linear", "pcb_resize_factor",
+    "pcb_reset_launch_count", "pcb_set_profile", "pcb_profile_read", "pcb_model_load", "pcb_model_get_tensor", "pcb_resize_area", "pcb_resize_linear", "pcb_resize_factor",
     "pcb_detect", "pcb_letterbox", "pcb_decode_nms", "pcb_align", "pcb_embed", "pcb_set_bank", "pcb_match",
 )
 
@@ -81,6 +81,8 @@ def load():
     lib.pcb_launch_count.argtypes = [vp]
     lib.pcb_reset_launch_count.restype = None
     lib.pcb_reset_launch_count.argtypes = [vp]
+    lib.pcb_set_profile.argtypes = [vp, i32]
+    lib.pcb_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong), i32]
     lib.pcb_model_load.argtypes = [vp, i32, C.POINTER(PcbOp), i32, i32, vp, C.c_size_t, C.POINTER(C.c_int32), i32,
                                    C.POINTER(C.c_float)]
     lib.pcb_model_get_tensor.argtypes = [vp, i32, i32, vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]

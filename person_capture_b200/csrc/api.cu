@@ -85,6 +85,7 @@ extern "C" void pcb_destroy(pcb_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   for (void* p : c->allocs) cudaFree(p);
+  for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
   if (c->h_err) cudaFreeHost(c->h_err);
   for (int i = 0; i < 4; ++i) delete c->models[i];
   if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -119,6 +120,48 @@ extern "C" int pcb_set_conv_impl(pcb_ctx* c, int impl) {
   c->conv_impl = impl;
   return PCB_OK;
 }
+PcbConvTimer::PcbConvTimer(pcb_ctx* ctx, double flops) : c(ctx) {
+  if (!c->profile) return;
+  while (c->ev_pool.size() < c->ev_used + 2) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    c->ev_pool.push_back(e);
+  }
+  cudaEvent_t e0 = c->ev_pool[c->ev_used];
+  e1 = c->ev_pool[c->ev_used + 1];
+  c->ev_used += 2;
+  c->ev_flops.push_back(flops);
+  cudaEventRecord(e0, c->stream);
+}
+PcbConvTimer::~PcbConvTimer() {
+  if (e1) cudaEventRecord(e1, c->stream);
+}
+
+extern "C" int pcb_set_profile(pcb_ctx* c, int on) {
+  c->profile = on != 0;
+  return PCB_OK;
+}
+
+// Folds all recorded conv launches into the running totals and returns them (synchronises).
+extern "C" int pcb_profile_read(pcb_ctx* c, double* conv_ms, double* conv_flops, long long* conv_launches, int reset) {
+  PCB_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (size_t i = 0; i + 1 < c->ev_used; i += 2) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, c->ev_pool[i], c->ev_pool[i + 1]) == cudaSuccess) {
+      c->prof_ms += ms;
+      c->prof_flops += c->ev_flops[i / 2];
+      c->prof_launches++;
+    }
+  }
+  c->ev_used = 0;
+  c->ev_flops.clear();
+  if (conv_ms) *conv_ms = c->prof_ms;
+  if (conv_flops) *conv_flops = c->prof_flops;
+  if (conv_launches) *conv_launches = c->prof_launches;
+  if (reset) { c->prof_ms = 0.0; c->prof_flops = 0.0; c->prof_launches = 0; }
+  return PCB_OK;
+}
+
 extern "C" long long pcb_launch_count(pcb_ctx* c) { return c->launches; }
 extern "C" void pcb_reset_launch_count(pcb_ctx* c) { c->launches = 0; }
 

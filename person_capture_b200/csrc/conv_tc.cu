@@ -266,6 +266,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccStride;
       for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
         uint32_t v[16];
+        __syncwarp();   // lanes diverge on `valid` below; tcgen05.ld is .sync.aligned
         tmem_ld16(t_row + c0, v);
         const int ch = n0 + c0;
         if (!valid) continue;
@@ -420,6 +421,10 @@ int pcb_conv_tc(pcb_ctx* c, const ConvArgs& a) {
   }
   const int total = p.m_tiles * p.n_tiles;
   const int grid = total < c->num_sms ? total : c->num_sms;
+  // algorithmic FLOPs of this layer: 2 * output pixels * cout * cin * taps (real, unpadded extents)
+  double out_px = in.dense ? (double)in.n : (double)in.n * (in.h / p.stride) * (in.w / p.stride);
+  const double k_real = (w.taps == 1 && w.cin == 3) ? 27.0 : (double)w.cin * w.taps;
+  PcbConvTimer timer(c, 2.0 * out_px * (double)w.cout * k_real);
   conv_tc_kernel<<<grid, kThreads, smem, c->stream>>>(tmA, tmB, p);
   PCB_LAUNCH_CHECK(c, "conv_tc_kernel");
   return PCB_OK;

@@ -75,6 +75,21 @@ struct pcb_ctx {
   int bank_rows = 0, bank_cap = 0;
   void* scratch = nullptr;
   size_t scratch_bytes = 0;
+  // profiling (bench.py roofline): CUDA events around every conv launch + algorithmic FLOPs
+  bool profile = false;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+  std::vector<double> ev_flops;      // per recorded launch
+  double prof_ms = 0.0, prof_flops = 0.0;
+  long long prof_launches = 0;
+};
+
+// records an event pair around a conv launch when profiling is on
+struct PcbConvTimer {
+  pcb_ctx* c;
+  cudaEvent_t e1 = nullptr;
+  PcbConvTimer(pcb_ctx* ctx, double flops);
+  ~PcbConvTimer();
 };
 
 int pcb_fail(pcb_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess);

@@ -90,6 +90,15 @@ class Engine:
     def reset_launch_count(self):
         self.lib.pcb_reset_launch_count(self.ctx)
 
+    def set_profile(self, on: bool):
+        self._check(self.lib.pcb_set_profile(self.ctx, 1 if on else 0), "pcb_set_profile")
+
+    def profile_read(self, reset: bool = True):
+        """-> (conv kernel ms, algorithmic conv FLOPs, conv launches) since the last reset."""
+        ms, fl, n = C.c_double(), C.c_double(), C.c_longlong()
+        self._check(self.lib.pcb_profile_read(self.ctx, C.byref(ms), C.byref(fl), C.byref(n), 1 if reset else 0), "pcb_profile_read")
+        return ms.value, fl.value, n.value
+
     def empty(self, shape, dtype):
         # allocate under the engine's stream so the caching allocator orders reuse against our kernels
         with torch.cuda.stream(self.stream):

@@ -272,6 +272,7 @@ class FaceEmbedder:
         emb, emb_flip = eng.embed(al.chips, f, do_flip)
         feat, _sim, _arg = eng.match(emb, emb_flip, None, f)
         eng.sync()
+        self.last_face_count = f
         boxes = al.face_box[:f].cpu().numpy()
         qual = al.quality[:f].cpu().numpy()
         feats = feat[:f].cpu().numpy()
@@ -281,4 +282,7 @@ class FaceEmbedder:
                for i in range(f)]
         self.last_order = sorted(range(f), key=lambda i: (out[i]["quality"], (out[i]["bbox"][2] - out[i]["bbox"][0]) *
                                                            (out[i]["bbox"][3] - out[i]["bbox"][1])), reverse=True)
+        # device-resident features in the returned order (prescan_sequential feeds them to pcb_match)
+        with torch.cuda.stream(eng.stream):
+            self.last_feats_dev = feat[:f].index_select(0, torch.as_tensor(self.last_order, device=feat.device)).contiguous()
         return [out[i] for i in self.last_order]

@@ -359,12 +359,15 @@ def prescan_sequential(clip, fps: int, face: FaceEmbedder, ref_feat, cfg, log: O
     return spans, (out_bank if out_bank is not None else ref_feat)
 
 
-def _post_process(spans, clip, fps, face, bank: RefBank, ref_feat, cfg, trk: SpanTracker, wmax: int):
+def _post_process(spans, clip, fps, face, bank: RefBank, ref_feat, cfg, trk: SpanTracker, wmax: int, batched: int = 0):
     gap = int(round(cfg.prescan_bridge_gap_sec * fps))
     do_bridge = getattr(cfg, "prescan_bridge_gap_sec", 0) > 0
     if spans and do_bridge:
         spans = bridge_spans(spans, gap)
-    spans = _refine_edges(spans, clip, fps, face, bank, ref_feat, cfg, trk, wmax)
+    if batched:
+        spans = _refine_edges_batched(spans, clip, fps, face, bank, ref_feat, cfg, trk, batched)
+    else:
+        spans = _refine_edges(spans, clip, fps, face, bank, ref_feat, cfg, trk, wmax)
     if spans and do_bridge:
         spans = bridge_spans(spans, gap)
     return spans
@@ -417,6 +420,64 @@ def _refine_edges(spans, clip, fps, face, bank: RefBank, ref_feat, cfg, trk: Spa
             out.append((ls, le))
     face.set_prescan_hint(escalate=False)
     face._prescan_rr_mode = rr_old
+    return out
+
+
+def _refine_edges_batched(spans, clip, fps, face, bank: RefBank, ref_feat, cfg, trk: SpanTracker, batch: int):
+    """Same result as _refine_edges, but every candidate probe frame of all spans goes through the
+    batched superset (two GPU rounds: all left windows, then all right windows, whose start depends
+    on the refined left edge).  Probes run in "full"/escalate mode: flip-TTA on, 90 then 270."""
+    if not spans:
+        return spans
+    total = clip.total_frames
+    stride_ref = max(1, min(int(max(1, cfg.prescan_stride) // 4), int(getattr(cfg, "prescan_refine_stride_min", 3))))
+    win = int(round(max(0.0, float(getattr(cfg, "prescan_boundary_refine_sec", 0.75))) * fps))
+    search = max(int(round(max(0.0, float(cfg.prescan_pad_sec)) * fps)), win)
+    trim = bool(getattr(cfg, "prescan_trim_pad", True))
+    skip_trailing = bool(getattr(cfg, "prescan_skip_trailing_refine", True))
+    use_bank = bank if len(bank) else RefBank(cfg, ref_feat)
+
+    def evaluate(frame_ids):
+        """-> {frame: bool hit} for probe frames in escalate mode against the final bank."""
+        ids = sorted(set(frame_ids))
+        if not ids:
+            return {}
+        records, table = compute_superset(clip, ids, face, cfg, batch=batch)
+        fdp, fdf = _LiveDistances(face.engine, table).get(use_bank)
+        res = {}
+        for j in ids:
+            rec = records[j]
+            chosen = rec.up
+            if chosen is None:
+                for deg in (90, 270):
+                    if rec.hits.get(deg, 0) and rec.heavy_raw.get(deg, 0) and deg in rec.heavy:
+                        chosen = rec.heavy[deg]
+                        break
+            res[j] = bool(chosen is not None and (fdf[chosen.rows] <= trk.enter).any())
+        return res
+
+    left_ids = []
+    for s, e in spans:
+        left_ids += list(range(s, min(e, s + search) + 1, stride_ref))
+    lhit = evaluate(left_ids)
+    lefts = []
+    for s, e in spans:
+        first = next((j for j in range(s, min(e, s + search) + 1, stride_ref) if lhit[j]), None)
+        lefts.append(max(s, first) if (first is not None and trim) else s)
+    right_ids = []
+    for (s, e), ls in zip(spans, lefts):
+        if not (skip_trailing and e >= total - 1):
+            right_ids += list(range(max(ls, e - search), e + 1, stride_ref))
+    rhit = evaluate(right_ids)
+    out = []
+    for (s, e), ls in zip(spans, lefts):
+        le = e
+        if not (skip_trailing and e >= total - 1):
+            hits = [j for j in range(max(ls, e - search), e + 1, stride_ref) if rhit[j]]
+            if hits and trim:
+                le = min(e, hits[-1])
+        if le >= ls and (le - ls + 1) >= trk.min_len:
+            out.append((ls, le))
     return out
 
 
@@ -570,11 +631,12 @@ class _LiveDistances:
 
 
 def replay(records: Dict[int, SampleRecord], table: FaceTable, feats_host, idxs: Sequence[int], fps: int, total_frames: int,
-           face: FaceEmbedder, ref_feat, cfg, log: Optional[list] = None):
-    """Host replay of the reference's sequential loop over precomputed superset records."""
+           face: FaceEmbedder, ref_feat, cfg, log: Optional[list] = None, distances=None):
+    """Host replay of the reference's sequential loop over precomputed superset records.
+    `distances` (tests only) replaces the GPU matcher with an object exposing get(bank)."""
     bank = RefBank(cfg, ref_feat)
     trk = SpanTracker(cfg, fps, total_frames)
-    dist = _LiveDistances(face.engine, table)
+    dist = distances if distances is not None else _LiveDistances(face.engine, table)
     fd_add = float(getattr(cfg, "prescan_fd_add", trk.enter))
     cooldown = int(getattr(cfg, "prescan_add_cooldown_samples", 5))
     last_add = -10 ** 9
@@ -654,7 +716,7 @@ def prescan_batched(clip, fps: int, face: FaceEmbedder, ref_feat, cfg, batch: in
         trk, bank = replay(records, table, (plain_h, flip_h), idxs, fps, total, face, ref_feat, cfg, log)
         spans = trk.finish()
         wmax = int(getattr(cfg, "prescan_max_width", 0))
-        spans = _post_process(spans, clip, fps, face, bank, ref_feat, cfg, trk, wmax)
+        spans = _post_process(spans, clip, fps, face, bank, ref_feat, cfg, trk, wmax, batched=batch)
     out_bank = bank.array()
     return spans, (out_bank if out_bank is not None else ref_feat)
 
@@ -668,7 +730,7 @@ def _gather_shards(eng, records, table, plain_h, flip_h, world, group):
     recs = [None] * world
     dist.all_gather_object(recs, records, group=group)
     cap = max(max(counts), 1)
-    dev = table.plain.device if table.count else eng.tdev
+    dev = table.plain.device if table.count else (eng.tdev if eng is not None else torch.device("cpu"))
     backend_cuda = dist.get_backend(group) == "nccl"
     send = torch.zeros((2, cap, L.FEAT_DIM), dtype=torch.float32, device=dev if backend_cuda else "cpu")
     if table.count:

@@ -1,0 +1,138 @@
+"""CPU: pin the oracle's cv2 emulation and the kernels' shared arithmetic header against real cv2."""
+import ctypes
+import os
+import subprocess
+
+import cv2
+import numpy as np
+import pytest
+
+import pcb_test_helpers as H
+from oracle import cv_emul as E
+
+HS_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostsim")
+DST = np.array([[38.2946, 51.6963], [73.5318, 51.5014], [56.0252, 71.7366], [41.5493, 92.3655], [70.7299, 92.2041]], np.float32)
+
+
+@pytest.fixture(scope="module")
+def hs():
+    so = os.path.join(HS_DIR, "_hostsim.so")
+    src = os.path.join(HS_DIR, "hostsim.cpp")
+    hdr = os.path.join(os.path.dirname(HS_DIR), "..", "person_capture_b200", "csrc", "pcb_cvmath.h")
+    if not os.path.isfile(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.run(["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-o", so, src], check=True)
+    return ctypes.CDLL(so)
+
+
+def P(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+SHAPES_LIN = [(540, 960, 288, 512), (360, 640, 234, 416), (100, 80, 320, 256), (77, 53, 112, 112), (200, 256, 100, 128)]
+SHAPES_AREA = [(360, 640, 234, 416), (1080, 1920, 540, 960), (300, 450, 100, 150), (200, 300, 112, 112), (150, 90, 112, 112),
+               (130, 260, 112, 112)]
+
+
+@pytest.mark.parametrize("h,w,dh,dw", SHAPES_LIN)
+def test_linear_resize(hs, h, w, dh, dw):
+    img = H.smooth_image(np.random.default_rng(h + w), h, w)
+    ref = cv2.resize(img, (dw, dh))
+    assert np.array_equal(E.resize_linear_u8(img, dw, dh), ref)
+    out = np.zeros((dh, dw, 3), np.uint8)
+    hs.hs_resize(P(img), h, w, 0, 0, P(out), dh, dw, 0)
+    assert np.array_equal(out, ref)
+
+
+@pytest.mark.parametrize("h,w,dh,dw", SHAPES_AREA)
+def test_area_resize(hs, h, w, dh, dw):
+    img = H.smooth_image(np.random.default_rng(h * 3 + w), h, w)
+    ref = cv2.resize(img, (dw, dh), interpolation=cv2.INTER_AREA)
+    if h * w <= 400 * 700:
+        assert np.array_equal(E.resize_area_u8(img, dw, dh), ref)
+    out = np.zeros((dh, dw, 3), np.uint8)
+    hs.hs_resize(P(img), h, w, 0, 0, P(out), dh, dw, 1)
+    assert np.array_equal(out, ref)
+
+
+@pytest.mark.parametrize("s", [0.75, 0.6, 1.25])
+def test_factor_resize(hs, s):
+    img = H.smooth_image(np.random.default_rng(5), 233, 417)
+    ref = cv2.resize(img, None, fx=s, fy=s, interpolation=cv2.INTER_AREA if s < 1 else cv2.INTER_LINEAR)
+    out = np.zeros_like(ref)
+    hs.hs_resize_factor(P(img), 233, 417, P(out), ctypes.c_double(s), ctypes.c_double(s), int(s < 1))
+    assert np.array_equal(out, ref)
+
+
+@pytest.mark.parametrize("rot,pad", [(90, 0), (90, 24), (180, 24), (270, 0), (270, 24), (0, 25)])
+def test_rotated_padded_view(hs, rot, pad):
+    img = H.smooth_image(np.random.default_rng(rot + pad), 120, 200)
+    ROT = {90: cv2.ROTATE_90_CLOCKWISE, 180: cv2.ROTATE_180, 270: cv2.ROTATE_90_COUNTERCLOCKWISE}
+    ref = cv2.rotate(img, ROT[rot]) if rot else img
+    if pad:
+        ref = cv2.copyMakeBorder(ref, pad, pad, pad, pad, cv2.BORDER_REPLICATE)
+    out = np.zeros_like(ref)
+    hs.hs_view(P(img), 120, 200, rot, pad, P(out))
+    assert np.array_equal(out, ref)
+
+
+def test_lmeds_and_warp(hs):
+    rng = np.random.default_rng(0)
+    bad_mask = 0
+    for t in range(250):
+        s = rng.uniform(16, 300)
+        ang = rng.uniform(-0.4, 0.4)
+        R = np.array([[np.cos(ang), -np.sin(ang)], [np.sin(ang), np.cos(ang)]])
+        src = np.ascontiguousarray(((DST / 112.0 - 0.5) @ R.T * s + s / 2 + rng.normal(0, 0.03 * s, (5, 2))).astype(np.float32))
+        M, inl = cv2.estimateAffinePartial2D(src, DST, method=cv2.LMEDS)
+        Me = np.zeros(6)
+        assert hs.hs_lmeds(P(src), P(DST), 5, P(Me)) == 1 and M is not None
+        assert np.abs(M.ravel() - Me).max() < 1e-9
+        M2, mask = E.estimate_affine_partial_lmeds(src, DST)
+        bad_mask += int(not np.array_equal(mask, inl.ravel().astype(bool)))
+        assert np.abs(M - M2).max() < 1e-9
+        if t < 40:
+            hh, ww = int(s) + 3, int(s * 0.9) + 2
+            big = H.smooth_image(rng, hh + 20, ww + 30)
+            crop = big[5:5 + hh, 7:7 + ww]
+            ref = cv2.warpAffine(crop, M, (112, 112), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_REFLECT)
+            out = np.zeros((112, 112, 3), np.uint8)
+            hs.hs_warp(ctypes.c_void_p(crop.ctypes.data), hh, ww, ctypes.c_longlong(big.strides[0]),
+                       P(np.ascontiguousarray(M.ravel())), P(out), 112, 112)
+            assert np.array_equal(out, ref)
+            if t < 6:
+                assert np.array_equal(E.warp_affine_u8(np.ascontiguousarray(crop), M, 112, 112), ref)
+    assert bad_mask == 0
+
+
+def test_lmeds_three_points(hs):
+    rng = np.random.default_rng(1)
+    d3 = np.ascontiguousarray(DST[:3])
+    for _ in range(40):
+        src = np.ascontiguousarray((d3 * rng.uniform(0.5, 3) + rng.normal(0, 2, (3, 2))).astype(np.float32))
+        M, _ = cv2.estimateAffinePartial2D(src, d3, method=cv2.LMEDS)
+        Me = np.zeros(6)
+        ok = hs.hs_lmeds(P(src), P(d3), 3, P(Me))
+        assert (M is not None) == bool(ok)
+        if ok:
+            assert np.abs(M.ravel() - Me).max() < 1e-8
+
+
+def test_gray_quality_canon(hs):
+    from oracle import face_embedder as OF
+    rng = np.random.default_rng(2)
+    chip = H.smooth_image(rng, 112, 112)
+    g = cv2.cvtColor(chip, cv2.COLOR_BGR2GRAY)
+    assert np.array_equal(E.gray_u8(chip), g)
+    out = np.zeros(112 * 112, np.uint8)
+    hs.hs_gray(P(chip), 112 * 112, P(out))
+    assert np.array_equal(out.reshape(112, 112), g)
+    q = float(cv2.Laplacian(g, cv2.CV_64F).var())
+    assert abs(E.laplacian_var(g) - q) <= 1e-9 * q
+    for _ in range(200):
+        pts = np.ascontiguousarray((DST + rng.normal(0, 12, (5, 2))).astype(np.float32)[rng.permutation(5)])
+        ref = OF.canon_5pts(pts)
+        got = np.zeros((5, 2), np.float32)
+        ok = hs.hs_canon(P(pts), P(got))
+        assert bool(ok) == (ref is not None)
+        if ok:
+            assert np.array_equal(got, ref)

@@ -1,0 +1,76 @@
+"""CPU: the multi-rank exchange with world_size 2 on gloo -- each rank owns a contiguous
+chunk of samples, records are all-gathered, and every rank's replay equals the single-process replay."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, HERE)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from person_capture_b200 import prescan as PS
+    from person_capture_b200.params import PrescanParams
+    import test_cpu_host_logic as T
+    rng = np.random.default_rng(11)
+    n = 120
+    target = T.unit(rng.normal(size=512))
+    sc = T.make_scenario(rng, n, target)
+    cfg = PrescanParams(prescan_stride=1, prescan_max_width=10 ** 6, prescan_fd_add=0.3, prescan_add_cooldown_samples=2,
+                        face_quality_min=50.0, prescan_min_segment_sec=0.25, prescan_pad_sec=0.1)
+    ref = T.unit(target + rng.normal(0, 0.03, 512))[None]
+    idxs = PS.sample_indices(n, 1)
+    per = (len(idxs) + world - 1) // world
+    mine = idxs[rank * per:(rank + 1) * per]
+    records, P, Fl = T.to_records({i: sc[i] for i in mine})
+    table = PS.FaceTable()
+    table.count = len(P)
+    table.plain = torch.from_numpy(P) if len(P) else torch.zeros((1, 512))
+    table.flip = torch.from_numpy(Fl) if len(Fl) else torch.zeros((1, 512))
+    merged, new_table, allp, allf = PS._gather_shards(None, records, table, P, Fl, world, None)
+    log = []
+    trk, bank = PS.replay(merged, None, (allp, allf), idxs, 24, n, T.FakeFace(sc), ref, cfg, log=log,
+                          distances=T.NumpyDistances(allp, allf))
+    q.put((rank, trk.finish(), [(r["idx"], r["skip"], round(r["best"], 6)) for r in log], len(bank)))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gather_and_replay_equal_single_process():
+    sys.path.insert(0, HERE)
+    from person_capture_b200 import prescan as PS
+    from person_capture_b200.params import PrescanParams
+    import test_cpu_host_logic as T
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    outs = sorted([q.get(timeout=180) for _ in procs])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # single-process result
+    rng = np.random.default_rng(11)
+    n = 120
+    target = T.unit(rng.normal(size=512))
+    sc = T.make_scenario(rng, n, target)
+    cfg = PrescanParams(prescan_stride=1, prescan_max_width=10 ** 6, prescan_fd_add=0.3, prescan_add_cooldown_samples=2,
+                        face_quality_min=50.0, prescan_min_segment_sec=0.25, prescan_pad_sec=0.1)
+    ref = T.unit(target + rng.normal(0, 0.03, 512))[None]
+    records, P, Fl = T.to_records(sc)
+    log = []
+    trk, bank = PS.replay(records, None, (P, Fl), PS.sample_indices(n, 1), 24, n, T.FakeFace(sc), ref, cfg, log=log,
+                          distances=T.NumpyDistances(P, Fl))
+    want = (trk.finish(), [(r["idx"], r["skip"], round(r["best"], 6)) for r in log], len(bank))
+    assert outs[0][1:] == want and outs[1][1:] == want
+    assert len(want[0]) >= 1

