@@ -55,14 +55,21 @@ enum { PCB_OP_CONV = 1, PCB_OP_AFFINE = 2, PCB_OP_MAXPOOL3S2 = 3, PCB_OP_AVGPOOL
 enum { PCB_ACT_NONE = 0, PCB_ACT_RELU = 1, PCB_ACT_PRELU = 2 };
 enum { PCB_MODEL_SCRFD = 0, PCB_MODEL_ARCFACE = 1 };
 
+enum { PCB_OPF_OUT_F32 = 1 };   /* pcb_op.flags: primary output kept in fp32 (residual stream) */
+
 typedef struct pcb_op {
   int32_t kind;             /* PCB_OP_* */
   int32_t in0, in1, out;    /* tensor ids; tensor 0 is the graph input; in1 = residual/second addend or -1 */
   int32_t cin, cout, k, stride, act;
+  int32_t out2;             /* CONV only: second fp16 output = scale2 * y + bias2 of the activated value y, or -1
+                               (fuses the BatchNorm that precedes the next block's first conv, iResNet bn1) */
+  int32_t flags;            /* PCB_OPF_* */
   int64_t w_off;            /* byte offset in blob: fp16 [cout][cin][k][k] (FC: [cout][cin]); -1 if none */
   int64_t scale_off;        /* fp32 [cout] */
   int64_t bias_off;         /* fp32 [cout] */
   int64_t slope_off;        /* fp32 [cout] (PReLU) or -1 */
+  int64_t scale2_off;       /* fp32 [cout] for out2, or -1 */
+  int64_t bias2_off;
 } pcb_op;
 
 /* Loads a graph into `slot`.  Tensor 0 is the stem-patch input produced by the pre-processing

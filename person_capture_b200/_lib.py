@@ -19,6 +19,7 @@ OP_CONV, OP_AFFINE, OP_MAXPOOL3S2, OP_AVGPOOL2, OP_UPSAMPLE_ADD, OP_ADD, OP_AFFI
 ACT_NONE, ACT_RELU, ACT_PRELU = 0, 1, 2
 MODEL_SCRFD, MODEL_ARCFACE = 0, 1
 FIX_NONE, FIX_SCALE, FIX_PADPROBE, FIX_UNPAD = 0, 1, 2, 3
+OPF_OUT_F32 = 1
 
 EXPORTS = (
     "pcb_create", "pcb_destroy", "pcb_last_error", "pcb_sync", "pcb_set_conv_impl", "pcb_launch_count",
@@ -30,7 +31,9 @@ EXPORTS = (
 class PcbOp(C.Structure):
     _fields_ = [("kind", C.c_int32), ("in0", C.c_int32), ("in1", C.c_int32), ("out", C.c_int32),
                 ("cin", C.c_int32), ("cout", C.c_int32), ("k", C.c_int32), ("stride", C.c_int32), ("act", C.c_int32),
-                ("w_off", C.c_int64), ("scale_off", C.c_int64), ("bias_off", C.c_int64), ("slope_off", C.c_int64)]
+                ("out2", C.c_int32), ("flags", C.c_int32),
+                ("w_off", C.c_int64), ("scale_off", C.c_int64), ("bias_off", C.c_int64), ("slope_off", C.c_int64),
+                ("scale2_off", C.c_int64), ("bias2_off", C.c_int64)]
 
 
 class DetectArgs(C.Structure):

@@ -2,6 +2,7 @@
 // plan executor, and the detect / embed entry points that chain K1 -> K2 -> K3 and
 // chip-patch -> K2 on the context's stream.
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "pcb_common.cuh"
@@ -10,13 +11,13 @@
 int pcb_letterbox_impl(pcb_ctx* c, const uint8_t* frames, int n, int h, int w, int S, int rot, int pad, __half* out,
                        uint8_t* det_img, double* det_scale_out);
 int pcb_chip_patch_impl(pcb_ctx* c, const uint8_t* chips, int f, int with_flip, __half* out);
-int pcb_decode_nms_impl(pcb_ctx* c, const __half* h8, const __half* h16, const __half* h32, const float* reg_scale3,
+int pcb_decode_nms_impl(pcb_ctx* c, const float* h8, const float* h16, const float* h32, const float* reg_scale3,
                         const pcb_detect_args* a, float det_scale);
 
 struct Model {
   std::vector<pcb_op> ops;
   std::vector<ConvWeights> conv;     // per op (unused entries empty)
-  std::vector<float*> aff_scale, aff_bias;
+  std::vector<float*> aff_scale, aff_bias;   // AFFINE ops, and scale2/bias2 of CONV ops with out2
   int n_tensors = 0;
   std::vector<int> outputs;
   float reg_scale[3] = {1.f, 1.f, 1.f};
@@ -120,8 +121,9 @@ extern "C" int pcb_set_conv_impl(pcb_ctx* c, int impl) {
   c->conv_impl = impl;
   return PCB_OK;
 }
-PcbConvTimer::PcbConvTimer(pcb_ctx* ctx, double flops) : c(ctx) {
+PcbConvTimer::PcbConvTimer(pcb_ctx* ctx, double flops, const char* desc) : c(ctx) {
   if (!c->profile) return;
+  c->ev_desc.push_back(desc ? desc : "");
   while (c->ev_pool.size() < c->ev_used + 2) {
     cudaEvent_t e;
     if (cudaEventCreate(&e) != cudaSuccess) return;
@@ -145,16 +147,21 @@ extern "C" int pcb_set_profile(pcb_ctx* c, int on) {
 // Folds all recorded conv launches into the running totals and returns them (synchronises).
 extern "C" int pcb_profile_read(pcb_ctx* c, double* conv_ms, double* conv_flops, long long* conv_launches, int reset) {
   PCB_CUDA(c, cudaStreamSynchronize(c->stream));
+  FILE* dump = nullptr;
+  if (const char* path = getenv("PCB_PROFILE_DUMP")) dump = fopen(path, "a");
   for (size_t i = 0; i + 1 < c->ev_used; i += 2) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, c->ev_pool[i], c->ev_pool[i + 1]) == cudaSuccess) {
       c->prof_ms += ms;
       c->prof_flops += c->ev_flops[i / 2];
       c->prof_launches++;
+      if (dump) fprintf(dump, "%s,%.6f,%.0f\n", c->ev_desc[i / 2].c_str(), ms, c->ev_flops[i / 2]);
     }
   }
+  if (dump) fclose(dump);
   c->ev_used = 0;
   c->ev_flops.clear();
+  c->ev_desc.clear();
   if (conv_ms) *conv_ms = c->prof_ms;
   if (conv_flops) *conv_flops = c->prof_flops;
   if (conv_launches) *conv_launches = c->prof_launches;
@@ -233,6 +240,12 @@ extern "C" int pcb_model_load(pcb_ctx* c, int slot, const pcb_op* ops, int n_ops
         w.slope = upload_f32_padded(c, (const float*)(blob + op.slope_off), op.cout, w.npad, 0.f);
       }
       if (!w.scale || !w.bias) { delete m; return pcb_fail(c, PCB_ERR_CUDA, "model_load: param upload failed"); }
+      if (op.kind == PCB_OP_CONV && op.out2 >= 0) {
+        if (!need(op.scale2_off, op.cout * 4) || !need(op.bias2_off, op.cout * 4)) { delete m; return pcb_fail(c, PCB_ERR_ARG, "model_load: out2 offsets"); }
+        m->aff_scale[i] = upload_f32_padded(c, (const float*)(blob + op.scale2_off), op.cout, w.npad, 0.f);
+        m->aff_bias[i] = upload_f32_padded(c, (const float*)(blob + op.bias2_off), op.cout, w.npad, 0.f);
+        if (!m->aff_scale[i] || !m->aff_bias[i]) { delete m; return pcb_fail(c, PCB_ERR_CUDA, "model_load: param upload failed"); }
+      }
     } else if (op.kind == PCB_OP_AFFINE || op.kind == PCB_OP_AFFINE_FLATTEN) {
       if (!need(op.scale_off, op.cout * 4) || !need(op.bias_off, op.cout * 4)) { delete m; return pcb_fail(c, PCB_ERR_ARG, "model_load: affine offsets"); }
       const int cp = pcb_round_up(op.cout, 8);
@@ -302,6 +315,16 @@ static int model_prepare(pcb_ctx* c, Model* m, int n, int h, int w, Model::Run**
         const bool stem = op.in0 == 0;
         const int s = stem ? 1 : op.stride;
         o.h = a.h / s; o.w = a.w / s; o.c = op.cout; o.cp = pcb_round_up(op.cout, 8);
+        o.f32 = (op.flags & PCB_OPF_OUT_F32) != 0;
+        if (op.out2 >= 0) {
+          PTensor& o2 = r.t[op.out2];
+          if (o2.data) return pcb_fail(c, PCB_ERR_ARG, "graph writes a tensor twice");
+          o2 = o;
+          o2.f32 = false;
+          o2.data = nullptr;
+          rc = alloc_tensor(c, o2);
+          if (rc) return rc;
+        }
         break;
       }
       case PCB_OP_AFFINE: o.h = a.h; o.w = a.w; o.c = a.c; o.cp = a.cp; break;
@@ -352,6 +375,11 @@ static int model_run(pcb_ctx* c, Model* m, Model::Run* r) {
         } else {
           a.out = &r->t[op.out];
           a.residual = op.in1 >= 0 ? &r->t[op.in1] : nullptr;
+          if (op.out2 >= 0) {
+            a.out2 = &r->t[op.out2];
+            a.scale2 = m->aff_scale[i];
+            a.bias2 = m->aff_bias[i];
+          }
         }
         w.n_tile = pick_n_tile(c, w, a.in->rows());
         rc = c->conv_impl == 0 ? pcb_conv_tc(c, a) : pcb_conv_simple(c, a);
@@ -371,7 +399,8 @@ static int model_run(pcb_ctx* c, Model* m, Model::Run* r) {
   return PCB_OK;
 }
 
-__global__ void gather_nchw_kernel(const __half* __restrict__ in, float* __restrict__ out, int n, int c, int h, int w, int cp, int dense) {
+__global__ void gather_nchw_kernel(const __half* __restrict__ in, float* __restrict__ out, int n, int c, int h, int w, int cp, int dense,
+                                   int is_f32) {
   const long long total = (long long)n * c * h * w;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     const int x = (int)(idx % w);
@@ -379,7 +408,7 @@ __global__ void gather_nchw_kernel(const __half* __restrict__ in, float* __restr
     const int ch = (int)((idx / ((long long)w * h)) % c);
     const int img = (int)(idx / ((long long)w * h * c));
     const long long row = dense ? img : ((long long)img * (h + 2) + y + 1) * (w + 2) + x + 1;
-    out[idx] = __half2float(in[row * cp + ch]);
+    out[idx] = is_f32 ? ((const float*)in)[row * cp + ch] : __half2float(in[row * cp + ch]);
   }
 }
 
@@ -397,7 +426,7 @@ extern "C" int pcb_model_get_tensor(pcb_ctx* c, int slot, int tid, float* out_ho
   const size_t total = (size_t)t.n * C * (t.dense ? 1 : t.h * t.w);
   float* d = nullptr;
   PCB_CUDA(c, cudaMalloc(&d, total * sizeof(float)));
-  gather_nchw_kernel<<<1024, 256, 0, c->stream>>>(t.data, d, t.n, C, t.dense ? 1 : t.h, t.dense ? 1 : t.w, t.cp, t.dense ? 1 : 0);
+  gather_nchw_kernel<<<1024, 256, 0, c->stream>>>(t.data, d, t.n, C, t.dense ? 1 : t.h, t.dense ? 1 : t.w, t.cp, t.dense ? 1 : 0, t.f32 ? 1 : 0);
   cudaError_t e = cudaMemcpyAsync(out_host, d, total * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
   cudaFree(d);
@@ -415,7 +444,7 @@ extern "C" int pcb_letterbox(pcb_ctx* c, const uint8_t* frames_dev, int n, int h
 
 extern "C" int pcb_decode_nms(pcb_ctx* c, const void* h8, const void* h16, const void* h32, const float* reg_scale3_host,
                               const pcb_detect_args* a, float det_scale) {
-  return pcb_decode_nms_impl(c, (const __half*)h8, (const __half*)h16, (const __half*)h32, reg_scale3_host, a, det_scale);
+  return pcb_decode_nms_impl(c, (const float*)h8, (const float*)h16, (const float*)h32, reg_scale3_host, a, det_scale);
 }
 
 extern "C" int pcb_detect(pcb_ctx* c, const pcb_detect_args* a) {
@@ -432,7 +461,10 @@ extern "C" int pcb_detect(pcb_ctx* c, const pcb_detect_args* a) {
   if (rc) return rc;
   rc = model_run(c, m, r);
   if (rc) return rc;
-  return pcb_decode_nms_impl(c, r->t[m->outputs[0]].data, r->t[m->outputs[1]].data, r->t[m->outputs[2]].data,
+  for (int i = 0; i < 3; ++i)
+    if (!r->t[m->outputs[i]].f32) return pcb_fail(c, PCB_ERR_STATE, "detect: SCRFD head outputs must be fp32 (PCB_OPF_OUT_F32)");
+  return pcb_decode_nms_impl(c, (const float*)r->t[m->outputs[0]].data, (const float*)r->t[m->outputs[1]].data,
+                             (const float*)r->t[m->outputs[2]].data,
                              m->has_reg_scale ? m->reg_scale : nullptr, a, (float)det_scale);
 }
 

@@ -12,7 +12,13 @@ struct SimpleParams {
   const float* bias;
   const float* slope;
   const __half* residual;
+  const float* residual_f32;
   __half* out;
+  float* out_s32;
+  __half* out2;
+  const float* scale2;
+  const float* bias2;
+  int cp_out2;
   float* out_f32;
   int n, h, w_, cp_in;       // input logical dims
   int ho, wo, cp_out, res_cp;
@@ -53,10 +59,13 @@ __global__ void conv_simple_kernel(const SimpleParams p) {
       if (co < p.out_f32_cols) p.out_f32[orow * p.out_f32_stride + co] = y;
       continue;
     }
-    if (p.residual) y += __half2float(p.residual[orow * p.res_cp + co]);
+    if (p.residual_f32) y += p.residual_f32[orow * p.res_cp + co];
+    else if (p.residual) y += __half2float(p.residual[orow * p.res_cp + co]);
     if (p.act == PCB_ACT_RELU) y = fmaxf(y, 0.f);
     else if (p.act == PCB_ACT_PRELU) y = y >= 0.f ? y : y * p.slope[co];
-    p.out[orow * p.cp_out + co] = __float2half_rn(y);
+    if (p.out_s32) p.out_s32[orow * p.cp_out + co] = y;
+    else p.out[orow * p.cp_out + co] = __float2half_rn(y);
+    if (p.out2) p.out2[orow * p.cp_out2 + co] = __float2half_rn(fmaf(y, p.scale2[co], p.bias2[co]));
   }
 }
 
@@ -89,14 +98,22 @@ int pcb_conv_simple(pcb_ctx* c, const ConvArgs& a) {
     p.cout_store = w.cout;
     p.ho = p.wo = 1;
   } else {
-    p.out = a.out->data;
+    if (a.out->f32) p.out_s32 = (float*)a.out->data;
+    else p.out = a.out->data;
     p.ho = a.out->h;
     p.wo = a.out->w;
     p.cp_out = a.out->cp;
     p.cout_store = a.out->cp;
     if (a.residual) {
-      p.residual = a.residual->data;
+      if (a.residual->f32) p.residual_f32 = (const float*)a.residual->data;
+      else p.residual = a.residual->data;
       p.res_cp = a.residual->cp;
+    }
+    if (a.out2) {
+      p.out2 = a.out2->data;
+      p.cp_out2 = a.out2->cp;
+      p.scale2 = a.scale2;
+      p.bias2 = a.bias2;
     }
   }
   const long long total = p.dense ? (long long)p.n * p.cout_store : (long long)p.n * p.ho * p.wo * p.cout_store;

@@ -18,6 +18,8 @@
 //
 // Every mbarrier wait is bounded (watchdog): on timeout the kernel raises the context's error
 // word and drains instead of hanging the GPU.
+#include <stdio.h>
+
 #include "pcb_common.cuh"
 
 namespace {
@@ -48,8 +50,14 @@ struct ConvTcParams {
   const float* bias;
   const float* slope;
   const __half* residual;
+  const float* residual_f32;   // residual stream kept in fp32 (same P-layout)
   int res_cp;
   __half* out;
+  float* out_s32;              // primary output as fp32 P-layout (residual stream)
+  __half* out2;                // second output: fp16(scale2 * y + bias2)
+  int out2_cp;
+  const float* scale2;
+  const float* bias2;
   float* out_f32;
   int out_f32_stride;
   int out_f32_cols;
@@ -280,7 +288,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (ch + j < p.out_f32_cols) *(float4*)(o + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
           continue;
         }
-        if (p.residual) {
+        if (p.residual_f32) {
+          const float* r = p.residual_f32 + orow * p.res_cp + ch;
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            if (ch + q4 * 4 < p.out_c_store) {
+              const float4 rv = *(const float4*)(r + q4 * 4);
+              y[q4 * 4] += rv.x; y[q4 * 4 + 1] += rv.y; y[q4 * 4 + 2] += rv.z; y[q4 * 4 + 3] += rv.w;
+            }
+          }
+        } else if (p.residual) {
           const __half* r = p.residual + orow * p.res_cp + ch;
 #pragma unroll
           for (int h8 = 0; h8 < 2; ++h8) {
@@ -303,15 +320,37 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int j = 0; j < 16; ++j) y[j] = y[j] >= 0.f ? y[j] : y[j] * __ldg(p.slope + ch + j);
         }
-        __half* o = p.out + orow * p.out_cp + ch;
+        if (p.out_s32) {
+          float* o = p.out_s32 + orow * p.out_cp + ch;
 #pragma unroll
-        for (int h8 = 0; h8 < 2; ++h8) {
-          if (ch + h8 * 8 < p.out_c_store) {
-            uint4 pk;
-            __half2* ph = (__half2*)&pk;
+          for (int q4 = 0; q4 < 4; ++q4)
+            if (ch + q4 * 4 < p.out_c_store) *(float4*)(o + q4 * 4) = make_float4(y[q4 * 4], y[q4 * 4 + 1], y[q4 * 4 + 2], y[q4 * 4 + 3]);
+        } else {
+          __half* o = p.out + orow * p.out_cp + ch;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) ph[j] = __floats2half2_rn(y[h8 * 8 + 2 * j], y[h8 * 8 + 2 * j + 1]);
-            *(uint4*)(o + h8 * 8) = pk;
+          for (int h8 = 0; h8 < 2; ++h8) {
+            if (ch + h8 * 8 < p.out_c_store) {
+              uint4 pk;
+              __half2* ph = (__half2*)&pk;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) ph[j] = __floats2half2_rn(y[h8 * 8 + 2 * j], y[h8 * 8 + 2 * j + 1]);
+              *(uint4*)(o + h8 * 8) = pk;
+            }
+          }
+        }
+        if (p.out2) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) y[j] = fmaf(y[j], __ldg(p.scale2 + ch + j), __ldg(p.bias2 + ch + j));
+          __half* o2 = p.out2 + orow * p.out2_cp + ch;
+#pragma unroll
+          for (int h8 = 0; h8 < 2; ++h8) {
+            if (ch + h8 * 8 < p.out_c_store) {
+              uint4 pk;
+              __half2* ph = (__half2*)&pk;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) ph[j] = __floats2half2_rn(y[h8 * 8 + 2 * j], y[h8 * 8 + 2 * j + 1]);
+              *(uint4*)(o2 + h8 * 8) = pk;
+            }
           }
         }
       }
@@ -388,15 +427,24 @@ int pcb_conv_tc(pcb_ctx* c, const ConvArgs& a) {
     p.out_f32_cols = w.cout;
   } else {
     const PTensor& out = *a.out;
-    p.out = out.data;
+    if (out.f32) p.out_s32 = (float*)out.data;
+    else p.out = out.data;
     p.out_cp = out.cp;
     p.out_c_store = out.cp;
     p.hp_out = out.h + 2;
     p.wp_out = out.w + 2;
     if (out.cp > w.npad) return pcb_fail(c, PCB_ERR_ARG, "conv_tc: output channels exceed packed weight rows");
     if (a.residual) {
-      p.residual = a.residual->data;
+      if (a.residual->f32) p.residual_f32 = (const float*)a.residual->data;
+      else p.residual = a.residual->data;
       p.res_cp = a.residual->cp;
+    }
+    if (a.out2) {
+      if (a.out2->cp != out.cp || a.out2->f32) return pcb_fail(c, PCB_ERR_ARG, "conv_tc: out2 geometry");
+      p.out2 = a.out2->data;
+      p.out2_cp = a.out2->cp;
+      p.scale2 = a.scale2;
+      p.bias2 = a.bias2;
     }
   }
   if (w.n_tile % 16 || w.n_tile > 256 || w.n_tile < 16) return pcb_fail(c, PCB_ERR_ARG, "conv_tc: bad n_tile");
@@ -424,7 +472,13 @@ int pcb_conv_tc(pcb_ctx* c, const ConvArgs& a) {
   // algorithmic FLOPs of this layer: 2 * output pixels * cout * cin * taps (real, unpadded extents)
   double out_px = in.dense ? (double)in.n : (double)in.n * (in.h / p.stride) * (in.w / p.stride);
   const double k_real = (w.taps == 1 && w.cin == 3) ? 27.0 : (double)w.cin * w.taps;
-  PcbConvTimer timer(c, 2.0 * out_px * (double)w.cout * k_real);
+  char desc[160];
+  desc[0] = 0;
+  if (c->profile)
+    snprintf(desc, sizeof desc, "n=%d,h=%d,w=%d,cin=%d,cout=%d,taps=%d,stride=%d,ntile=%d,tiles=%d,grid=%d,res=%d,f32out=%d,out2=%d", in.n, in.h,
+             in.w, w.cin, w.cout, w.taps, p.stride, p.n_tile, total, grid, a.residual ? (a.residual->f32 ? 2 : 1) : 0,
+             (a.out && a.out->f32) ? 1 : 0, a.out2 ? 1 : 0);
+  PcbConvTimer timer(c, 2.0 * out_px * (double)w.cout * k_real, desc);
   conv_tc_kernel<<<grid, kThreads, smem, c->stream>>>(tmA, tmB, p);
   PCB_LAUNCH_CHECK(c, "conv_tc_kernel");
   return PCB_OK;

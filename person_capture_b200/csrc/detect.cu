@@ -4,7 +4,8 @@
 // FaceEmbedder._extract_with_scrfd_raw::_accumulate + the min-size filter
 // (person_capture/face_embedder.py:2214-2245, 2317-2322).
 //
-// Head maps are the fp16 P-layout outputs of the SCRFD graph, 32 channels per pixel:
+// Head maps are the fp32 P-layout outputs of the SCRFD graph (fp32 so that box / landmark distances of
+// 8..16 stride units are not quantised to 2^-7), 32 channels per pixel:
 //   [cls a0, cls a1 | reg a0 (l,t,r,b), reg a1 | kps a0 (10), kps a1 (10) | 2 pad].
 // All box arithmetic is float32 with explicit non-fused operations in numpy's order, so keep
 // sets are bit-identical to the oracle given identical head maps.  Ties in score are broken by
@@ -23,7 +24,7 @@ struct Cand {
 };
 
 struct DecodeParams {
-  const __half* head[3];
+  const float* head[3];
   int hw[3];              // feature map edge per level (S/8, S/16, S/32)
   int row_off[3];         // first anchor row of each level
   float reg_scale[3];
@@ -46,8 +47,8 @@ __global__ void decode_kernel(const DecodeParams p) {
     const int loc = r >> 1;
     const int w = p.hw[lvl];
     const int y = loc / w, x = loc - y * w;
-    const __half* px = p.head[lvl] + ((((size_t)img * (w + 2)) + y + 1) * (w + 2) + x + 1) * 32;
-    const float logit = __half2float(px[a]);
+    const float* px = p.head[lvl] + ((((size_t)img * (w + 2)) + y + 1) * (w + 2) + x + 1) * 32;
+    const float logit = px[a];
     if (!(logit >= lthr)) continue;
     // torch.sigmoid on float32: evaluate in double and round once
     const float score = (float)(1.0 / (1.0 + exp(-(double)logit)));
@@ -61,14 +62,14 @@ __global__ void decode_kernel(const DecodeParams p) {
     const float cx = __fmul_rn((float)x, stride), cy = __fmul_rn((float)y, stride);
     float d[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) d[j] = __fmul_rn(__fmul_rn(__half2float(px[2 + 4 * a + j]), p.reg_scale[lvl]), stride);
+    for (int j = 0; j < 4; ++j) d[j] = __fmul_rn(__fmul_rn(px[2 + 4 * a + j], p.reg_scale[lvl]), stride);
     c.box[0] = __fdiv_rn(__fsub_rn(cx, d[0]), p.det_scale);
     c.box[1] = __fdiv_rn(__fsub_rn(cy, d[1]), p.det_scale);
     c.box[2] = __fdiv_rn(__fadd_rn(cx, d[2]), p.det_scale);
     c.box[3] = __fdiv_rn(__fadd_rn(cy, d[3]), p.det_scale);
 #pragma unroll
     for (int j = 0; j < 10; ++j) {
-      const float k = __fmul_rn(__half2float(px[10 + 10 * a + j]), stride);
+      const float k = __fmul_rn(px[10 + 10 * a + j], stride);
       c.kps[j] = __fdiv_rn(__fadd_rn((j & 1) ? cy : cx, k), p.det_scale);
     }
     p.cands[(size_t)img * kCandCap + slot] = c;
@@ -264,7 +265,7 @@ static int ensure_scratch(pcb_ctx* c, size_t bytes) {
   return PCB_OK;
 }
 
-int pcb_decode_nms_impl(pcb_ctx* c, const __half* h8, const __half* h16, const __half* h32, const float* reg_scale3,
+int pcb_decode_nms_impl(pcb_ctx* c, const float* h8, const float* h16, const float* h32, const float* reg_scale3,
                         const pcb_detect_args* a, float det_scale) {
   if (!a || a->n <= 0 || a->max_det <= 0 || a->max_det > 1024) return pcb_fail(c, PCB_ERR_ARG, "decode_nms: bad arguments");
   const size_t cand_bytes = (size_t)a->n * kCandCap * sizeof(Cand);

@@ -30,8 +30,9 @@ struct PTensor {
   __half* data = nullptr;
   int n = 0, h = 0, w = 0, c = 0, cp = 0;  // logical dims, cp = padded channel stride
   bool dense = false;                      // dense: [n][cp] rows without spatial ring (FC input)
+  bool f32 = false;                        // elements are float (iResNet residual stream) instead of __half
   size_t rows() const { return dense ? (size_t)n : (size_t)n * (h + 2) * (w + 2); }
-  size_t bytes() const { return rows() * cp * sizeof(__half); }
+  size_t bytes() const { return rows() * cp * (f32 ? sizeof(float) : sizeof(__half)); }
 };
 
 static inline int pcb_round_up(int x, int m) { return (x + m - 1) / m * m; }
@@ -53,7 +54,10 @@ struct ConvArgs {
   const PTensor* out;       // fp16 P-layout output (or nullptr when out_f32 is used)
   float* out_f32;           // dense fp32 output [rows][out_f32_stride] (FC)
   int out_f32_stride;
-  const PTensor* residual;  // optional, same geometry as out
+  const PTensor* residual;  // optional, same geometry as out (fp16 or fp32)
+  const PTensor* out2;      // optional second fp16 output: scale2 * y + bias2 (same geometry as out)
+  const float* scale2;
+  const float* bias2;
   const ConvWeights* w;
   int stride;               // 1 or 2 (spatial); ignored for dense
   int act;                  // 0 none, 1 relu, 2 prelu
@@ -80,6 +84,7 @@ struct pcb_ctx {
   std::vector<cudaEvent_t> ev_pool;
   size_t ev_used = 0;
   std::vector<double> ev_flops;      // per recorded launch
+  std::vector<std::string> ev_desc;  // per recorded launch: layer shape (PCB_PROFILE_DUMP csv)
   double prof_ms = 0.0, prof_flops = 0.0;
   long long prof_launches = 0;
 };
@@ -88,7 +93,7 @@ struct pcb_ctx {
 struct PcbConvTimer {
   pcb_ctx* c;
   cudaEvent_t e1 = nullptr;
-  PcbConvTimer(pcb_ctx* ctx, double flops);
+  PcbConvTimer(pcb_ctx* ctx, double flops, const char* desc = nullptr);
   ~PcbConvTimer();
 };
 

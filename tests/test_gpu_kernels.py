@@ -169,7 +169,7 @@ def test_decode_nms_bit_exact(engine_25g_r50, S, thr, seed, rot, pad, fix):
             logit[y, x, rng.integers(0, 2)] = np.float16(rng.uniform(-1, 6))
         reg = rng.uniform(0.5, 6.0, (h, h, 8)).astype(np.float16)
         kps = rng.uniform(-3.0, 3.0, (h, h, 20)).astype(np.float16)
-        hm = np.zeros((1, h + 2, h + 2, 32), np.float16)
+        hm = np.zeros((1, h + 2, h + 2, 32), np.float32)
         hm[0, 1:-1, 1:-1, 0:2] = logit
         hm[0, 1:-1, 1:-1, 2:10] = reg
         hm[0, 1:-1, 1:-1, 10:30] = kps
