@@ -27,7 +27,13 @@ LEVEL_RANGES = ((0, 56), (56, 200), (200, 10_000))  # face side (px) -> stride 8
 
 
 def make_sample(rng: np.random.Generator, size: int, tex_cache: dict):
-    img = synth.background(rng, size, size, clutter=int(rng.integers(2, 9)))
+    # backgrounds at 1x..4x zoom-out: a 1080p frame letterboxed to 512 shows the background's structure ~4x
+    # smaller than a native-resolution frame does; without these the stride-32 head fires on large smooth blobs
+    zoom = int(rng.choice([1, 1, 2, 3, 4]))
+    img = synth.background(rng, size * zoom, size * zoom, clutter=int(rng.integers(2, 9)))
+    if zoom > 1:
+        import cv2
+        img = cv2.resize(img, (size, size), interpolation=cv2.INTER_AREA)
     n = int(rng.choice([0, 1, 1, 1, 2, 2, 3, 5]))
     boxes, kpss = [], []
     placed = []

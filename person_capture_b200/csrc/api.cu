@@ -117,7 +117,7 @@ extern "C" int pcb_sync(pcb_ctx* c) {
 }
 
 extern "C" int pcb_set_conv_impl(pcb_ctx* c, int impl) {
-  if (impl != 0 && impl != 1) return pcb_fail(c, PCB_ERR_ARG, "conv impl must be 0 or 1");
+  if (impl < 0 || impl > 2) return pcb_fail(c, PCB_ERR_ARG, "conv impl must be 0, 1 or 2");
   c->conv_impl = impl;
   return PCB_OK;
 }
@@ -382,7 +382,7 @@ static int model_run(pcb_ctx* c, Model* m, Model::Run* r) {
           }
         }
         w.n_tile = pick_n_tile(c, w, a.in->rows());
-        rc = c->conv_impl == 0 ? pcb_conv_tc(c, a) : pcb_conv_simple(c, a);
+        rc = c->conv_impl == 0 ? pcb_conv_tc2(c, a) : c->conv_impl == 2 ? pcb_conv_tc(c, a) : pcb_conv_simple(c, a);
         break;
       }
       case PCB_OP_AFFINE: rc = pcb_op_affine(c, r->t[op.in0], r->t[op.out], m->aff_scale[i], m->aff_bias[i]); break;
@@ -472,7 +472,11 @@ extern "C" int pcb_embed(pcb_ctx* c, const uint8_t* chips_dev, int f, float* emb
   if (f < 0 || (f > 0 && (!chips_dev || !emb_dev))) return pcb_fail(c, PCB_ERR_ARG, "embed: bad arguments");
   Model* m = c->models[PCB_MODEL_ARCFACE];
   if (!m) return pcb_fail(c, PCB_ERR_STATE, "embed: no ArcFace graph loaded");
-  const int chunk = 128;   // faces per graph run (x2 images with flip); bounds activation memory
+  // faces per graph run (x2 images with flip).  222 faces = 444 images makes the 14x14 / 28x28 / 7x7 stages
+  // 3.0 / 10.5 / 1.9 waves of 256-row tiles over 148 SMs (>= 95% wave efficiency) and bounds activation memory
+  // at ~11 GB for iResNet-100.
+  static const int chunk_env = getenv("PCB_EMBED_CHUNK") ? atoi(getenv("PCB_EMBED_CHUNK")) : 0;
+  const int chunk = chunk_env > 0 ? chunk_env : (emb_flip_dev ? 222 : 444);
   for (int f0 = 0; f0 < f; f0 += chunk) {
     const int fn = f - f0 < chunk ? f - f0 : chunk;
     const int imgs = emb_flip_dev ? 2 * fn : fn;

@@ -1,0 +1,806 @@
+// K2 (product kernel): implicit-GEMM convolution on the 5th-gen tensor cores with operand reuse in
+// shared memory.  Replaces the ONNX Runtime / TensorRT execution of the SCRFD and ArcFace graphs
+// (reference: person_capture/face_embedder.py:1102-1107, 1341, 1369).
+//
+// Why a second kernel: the first formulation (conv_tc.cu, kept as the A/B baseline, conv impl 2)
+// issues one TMA load of the activation tile per tap, i.e. it reads A nine times and the weight
+// matrix once per 128 output rows.  ncu shows it pinned at the L2->SM bandwidth limit (~12 TB/s) with
+// the tensor pipe half idle.  This kernel cuts L2 traffic ~2.6x:
+//   * A halo tile: for a tile of M = MT*128 consecutive P-layout rows the rows
+//     [m0 - (W+3), m0 + M + (W+3)) of one 64-channel chunk are loaded ONCE; tap (dy,dx) is the same
+//     shared-memory tile at a row offset of (dy+1)*(W+2) + dx + 1, expressed through the UMMA
+//     descriptor start address alone (the swizzle is a function of absolute smem address bits).  For wide
+//     maps (2*(W+3) > 256 rows) three row bands (dy = -1,0,1) are loaded instead (3x, not 9x).
+//   * MT = 2: two 128-row accumulators share every weight stage, halving weight traffic per FLOP.
+//   * small layers (taps*kchunks weight tiles fit in the ring and there is one N tile) keep the whole
+//     weight matrix resident in shared memory for the lifetime of the CTA.
+// Pipelines: A ring (2-3 stages) and B ring (up to 18 stages) with separate producer warps, TMEM
+// accumulators double-buffered when MT*N <= 256 columns.
+//
+// Warp roles (352 threads, 1 CTA/SM, persistent over tiles):
+//   warp 0  A producer (TMA)    warp 1  MMA issuer (+TMEM alloc)    warp 2  B producer (TMA)
+//   warps 3-10  epilogue: TMEM lane quarter = warp % 4, column half = (warp - 3) / 4.
+// Epilogue per 32 columns: tcgen05.ld.x32 -> y = acc*scale+bias (+residual) -> ReLU/PReLU -> fp16
+// (or fp32 head maps) -> 16-byte stores of interior pixels; optional second output scale2*y+bias2
+// (the next block's BatchNorm).  Per-channel vectors live in shared memory; the residual rows of a
+// tile are prefetched into registers before the accumulator is waited for.
+//
+// Every mbarrier wait is bounded (watchdog): on timeout the kernel raises the context's error word
+// and drains instead of hanging the GPU.
+#include <stdio.h>
+#include <stdlib.h>
+
+#include "pcb_common.cuh"
+
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kKC = 64;                       // K elements per weight stage (one 128B swizzle atom)
+constexpr int kSubBytes = kBlockM * kKC * 2;  // 16 KB: one 128-row x 64-channel A sub-tile
+constexpr int kThreads = 352;
+constexpr int kEpiWarp0 = 3;
+constexpr int kEpiWarps = 8;
+constexpr uint32_t kTmemCols = 512;
+constexpr int kMaxA = 3;
+constexpr int kMaxB = 18;
+constexpr int kMaxALoads = 12;
+constexpr int kSmemBudget = 224 * 1024;
+
+struct ALoad {
+  int row_rel;    // first global row of the box relative to m0
+  int smem_off;   // byte offset inside the A stage
+  int map2;       // 0: 128-row box map, 1: small box map
+};
+
+struct Conv2Params {
+  int rows;        // input rows (N*(H+2)*(W+2)) or dense rows
+  int hp, wp;      // input padded dims; 0 for dense
+  int taps;        // 9 or 1
+  int kchunks;     // ceil(cin_eff / 64)
+  int cin_w;       // packed weight K extent per tap
+  int n_tile, n_tiles, m_tiles;   // m_tiles counts tiles of mt*128 rows
+  int mt;          // 128-row sub-tiles per CTA tile
+  int sub_cols;    // TMEM columns between sub-tile accumulators (n_tile rounded up to 32)
+  int acc_bufs;    // 1 | 2
+  int a_stages, a_stage_bytes, a_tx_bytes;
+  int b_stages, b_bytes, b_resident;
+  int n_aloads;
+  ALoad aloads[kMaxALoads];
+  int tap_off[9];  // byte offset of tap t's first row inside the A stage
+  int desc_mode;   // 1 (product): base-offset 0; 0 (experiment): base-offset = (addr >> 7) & 7
+  int stride;      // 1 | 2
+  int hp_out, wp_out;
+  int out_cp;      // channel stride of the P-layout output
+  int out_c_store; // channels to store (<= out_cp, multiple of 8)
+  int act;
+  int dense;
+  int vec_n;       // shared-memory entries of each per-channel vector (npad rounded up to 32)
+  int vec_real;    // entries present in global memory (npad)
+  const float* scale;
+  const float* bias;
+  const float* slope;
+  const __half* residual;
+  int res_cp;
+  __half* out;
+  float* out_s32;              // primary output as fp32 P-layout (SCRFD head maps)
+  __half* out2;                // second output: fp16(scale2 * y + bias2)
+  int out2_cp;
+  const float* scale2;
+  const float* bias2;
+  float* out_f32;              // dense fp32 output (FC)
+  int out_f32_stride;
+  int out_f32_cols;
+  int* err;
+  unsigned long long* dbg;     // optional [16]: block 0 writes clocks / wait cycles (PCB_CONV_DEBUG)
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: false (and *err raised) if the barrier did not flip in ~0.3 s or another role failed.
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* err, int code) {
+  if (mbar_try_wait(bar, parity)) return true;
+  long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 0x3ff) == 0) {
+      if (*(volatile int*)err != 0) return false;
+      if (clock64() - t0 > 600000000LL) {
+        atomicCAS(err, 0, code);
+        return false;
+      }
+    }
+  }
+  return true;
+}
+
+// mbar_wait that also accumulates the cycles spent waiting (debug instrumentation of block 0)
+__device__ __forceinline__ bool mbar_wait_t(uint64_t* bar, uint32_t parity, int* err, int code, long long& acc) {
+  if (mbar_try_wait(bar, parity)) return true;
+  const long long t0 = clock64();
+  const bool ok = mbar_wait(bar, parity, err, code);
+  acc += clock64() - t0;
+  return ok;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, uint32_t dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart.  The start
+// address may sit on any 128-byte row (tap shifts).  Measured on B200 (tools/conv_check.py): the
+// tensor core applies the 128B swizzle to ABSOLUTE shared-memory address bits (the same rule TMA writes
+// with), so a row-shifted start needs base-offset 0; setting base-offset = (addr >> 7) & 7 double-counts
+// the phase and gives wrong sums (desc_mode 0 is kept only to reproduce that experiment).
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr, int desc_mode) {
+  uint64_t lo = (uint64_t)((saddr >> 4) & 0x3fff);             // start address, LBO = 0
+  uint64_t hi = (uint64_t)(1024 >> 4)                           // SBO
+                | (1ull << 14)                                  // descriptor version 1 (sm_100)
+                | (2ull << 29);                                 // layout type: SWIZZLE_128B
+  if (desc_mode == 0) hi |= (uint64_t)((saddr >> 7) & 7) << 17; // base offset, bits 49-51
+  return lo | (hi << 32);
+}
+
+struct RowInfo {
+  bool valid;
+  long long orow;
+};
+
+__device__ __forceinline__ RowInfo row_info(const Conv2Params& p, long long prow) {
+  RowInfo r;
+  r.valid = prow < p.rows;
+  r.orow = prow;
+  if (!p.dense) {
+    const int plane = p.hp * p.wp;
+    const int img = (int)(prow / plane);
+    const int rem = (int)(prow - (long long)img * plane);
+    const int y = rem / p.wp, x = rem - y * p.wp;
+    r.valid = r.valid && y >= 1 && y <= p.hp - 2 && x >= 1 && x <= p.wp - 2;
+    if (p.stride == 2) {
+      r.valid = r.valid && (((y - 1) | (x - 1)) & 1) == 0;
+      r.orow = ((long long)img * p.hp_out + ((y - 1) >> 1) + 1) * p.wp_out + ((x - 1) >> 1) + 1;
+    }
+  }
+  return r;
+}
+
+__device__ __forceinline__ void unpack_h8(const uint4& v, float* f) {
+  const __half2* h = (const __half2*)&v;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 t = __half22float2(h[j]);
+    f[2 * j] = t.x;
+    f[2 * j + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack_h8(const float* f) {
+  uint4 v;
+  __half2* h = (__half2*)&v;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
+  return v;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ Conv2Params p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + (size_t)p.a_stages * p.a_stage_bytes;
+  float* vec = (float*)(smem_b + (size_t)p.b_stages * p.b_bytes);   // scale | bias | slope | scale2 | bias2
+  uint64_t* bars = (uint64_t*)(vec + 5 * p.vec_n);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = a_full + kMaxA;
+  uint64_t* b_full = a_empty + kMaxA;
+  uint64_t* b_empty = b_full + kMaxB;
+  uint64_t* tfull_bar = b_empty + kMaxB;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int tile_rows = p.mt * kBlockM;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.a_stages; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_empty[s], 1);
+    }
+    for (int s = 0; s < p.b_stages; ++s) {
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], kEpiWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // per-channel vectors -> shared memory (epilogue reads them as broadcast float4)
+  for (int i = threadIdx.x; i < p.vec_n; i += kThreads) {
+    const bool in = i < p.vec_real;
+    vec[i] = in ? p.scale[i] : 0.f;
+    vec[p.vec_n + i] = in ? p.bias[i] : 0.f;
+    vec[2 * p.vec_n + i] = (in && p.slope) ? p.slope[i] : 0.f;
+    vec[3 * p.vec_n + i] = (in && p.scale2) ? p.scale2[i] : 0.f;
+    vec[4 * p.vec_n + i] = (in && p.bias2) ? p.bias2[i] : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== A producer =====================
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA2) : "memory");
+      int stage = 0;
+      uint32_t phase = 0;
+      bool ok = true;
+      long long w_empty = 0;
+      const long long c0 = clock64();
+      const unsigned long long n0s = globaltimer_ns();
+      for (int tile = blockIdx.x; ok && tile < total_tiles; tile += gridDim.x) {
+        const int mt_idx = tile / p.n_tiles;
+        const int m0 = mt_idx * tile_rows;
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          if (!mbar_wait_t(&a_empty[stage], phase ^ 1, p.err, 101, w_empty)) { ok = false; break; }
+          const uint32_t sa = smem_u32(smem_a + (size_t)stage * p.a_stage_bytes);
+          mbar_expect_tx(&a_full[stage], (uint32_t)p.a_tx_bytes);
+          for (int l = 0; l < p.n_aloads; ++l) {
+            const ALoad ld = p.aloads[l];
+            tma_load_2d(ld.map2 ? &tmA2 : &tmA, &a_full[stage], sa + ld.smem_off, kc * kKC, m0 + ld.row_rel);
+          }
+          if (++stage == p.a_stages) { stage = 0; phase ^= 1; }
+        }
+      }
+      if (p.dbg && blockIdx.x == 0) {
+        p.dbg[0] = (unsigned long long)c0;
+        p.dbg[1] = n0s;
+        p.dbg[4] = (unsigned long long)w_empty;
+      }
+    }
+  } else if (warp == 2) {
+    // ===================== B producer =====================
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+      const int ksteps = p.taps * p.kchunks;
+      if (p.b_resident) {
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const int kc = ks / p.taps, t = ks - kc * p.taps;
+          mbar_expect_tx(&b_full[ks], (uint32_t)p.b_bytes);
+          tma_load_2d(&tmB, &b_full[ks], smem_u32(smem_b + (size_t)ks * p.b_bytes), t * p.cin_w + kc * kKC, 0);
+        }
+      } else {
+        int stage = 0;
+        uint32_t phase = 0;
+        bool ok = true;
+        long long w_empty = 0;
+        for (int tile = blockIdx.x; ok && tile < total_tiles; tile += gridDim.x) {
+          const int mt_idx = tile / p.n_tiles, nt = tile - mt_idx * p.n_tiles;
+          const int n0 = nt * p.n_tile;
+          for (int ks = 0; ks < ksteps; ++ks) {
+            const int kc = ks / p.taps, t = ks - kc * p.taps;
+            if (!mbar_wait_t(&b_empty[stage], phase ^ 1, p.err, 105, w_empty)) { ok = false; break; }
+            mbar_expect_tx(&b_full[stage], (uint32_t)p.b_bytes);
+            tma_load_2d(&tmB, &b_full[stage], smem_u32(smem_b + (size_t)stage * p.b_bytes), t * p.cin_w + kc * kKC, n0);
+            if (++stage == p.b_stages) { stage = 0; phase ^= 1; }
+          }
+        }
+        if (p.dbg && blockIdx.x == 0) p.dbg[5] = (unsigned long long)w_empty;
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4)                          // D format: F32
+                             | (0u << 7) | (0u << 10)           // A, B format: F16
+                             | ((uint32_t)(p.n_tile >> 3) << 17)
+                             | ((uint32_t)(kBlockM >> 4) << 24);
+      int a_stage = 0, b_stage = 0;
+      uint32_t a_phase = 0, b_phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      bool ok = true;
+      bool b_loaded = false;
+      long long w_a = 0, w_b = 0, w_t = 0;
+      for (int tile = blockIdx.x; ok && tile < total_tiles; tile += gridDim.x) {
+        if (!mbar_wait_t(&tempty_bar[acc], acc_phase ^ 1, p.err, 102, w_t)) { ok = false; break; }
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
+        for (int kc = 0; ok && kc < p.kchunks; ++kc) {
+          if (!mbar_wait_t(&a_full[a_stage], a_phase, p.err, 103, w_a)) { ok = false; break; }
+          const uint32_t sa = smem_u32(smem_a + (size_t)a_stage * p.a_stage_bytes);
+          for (int t = 0; t < p.taps; ++t) {
+            const int slot = p.b_resident ? kc * p.taps + t : b_stage;
+            if (!p.b_resident || !b_loaded) {
+              if (!mbar_wait_t(&b_full[slot], p.b_resident ? 0u : b_phase, p.err, 106, w_b)) { ok = false; break; }
+            }
+            tc_fence_after();
+            const uint32_t sb = smem_u32(smem_b + (size_t)slot * p.b_bytes);
+            const uint64_t db = make_desc_sw128(sb, 1);
+            for (int j = 0; j < p.mt; ++j) {
+              const uint32_t sa_t = sa + (uint32_t)p.tap_off[t] + (uint32_t)(j * kSubBytes);
+              const uint64_t da = make_desc_sw128(sa_t, p.desc_mode);
+#pragma unroll
+              for (int k = 0; k < kKC / 16; ++k) {
+                // advance 16 elements (32 bytes) along K inside the swizzle atom
+                umma_f16(d_tmem + (uint32_t)(j * p.sub_cols), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                         (kc | t | k) != 0 ? 1u : 0u);
+              }
+            }
+            if (!p.b_resident) {
+              umma_commit(&b_empty[b_stage]);
+              if (++b_stage == p.b_stages) { b_stage = 0; b_phase ^= 1; }
+            }
+          }
+          if (!ok) break;
+          umma_commit(&a_empty[a_stage]);
+          if (++a_stage == p.a_stages) { a_stage = 0; a_phase ^= 1; }
+        }
+        if (!ok) break;
+        b_loaded = true;
+        umma_commit(&tfull_bar[acc]);
+        if (p.acc_bufs == 2) {
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1;
+        } else {
+          acc_phase ^= 1;
+        }
+      }
+      if (p.dbg && blockIdx.x == 0) {
+        p.dbg[6] = (unsigned long long)w_a;
+        p.dbg[7] = (unsigned long long)w_b;
+        p.dbg[8] = (unsigned long long)w_t;
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 3..10) =====================
+    const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    const int half = (warp - kEpiWarp0) >> 2;     // column half
+    const int row_in_tile = q * 32 + lane;
+    // column range of this warp inside an n-tile, in 32-column chunks
+    const int split = ((p.n_tile / 2 + 31) / 32) * 32;
+    const int col_lo = half ? split : 0;
+    const int col_hi = half ? p.n_tile : (split < p.n_tile ? split : p.n_tile);
+    const float* v_scale = vec;
+    const float* v_bias = vec + p.vec_n;
+    const float* v_slope = vec + 2 * p.vec_n;
+    const float* v_scale2 = vec + 3 * p.vec_n;
+    const float* v_bias2 = vec + 4 * p.vec_n;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    bool ok = true;
+    long long w_full = 0, t_epi = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int mt_idx = tile / p.n_tiles, nt = tile - mt_idx * p.n_tiles;
+      const int n0 = nt * p.n_tile;
+      const long long row0 = (long long)mt_idx * tile_rows + row_in_tile;
+      RowInfo ri = row_info(p, row0);
+      // residual prefetch for sub-tile 0 (independent of the accumulator): 4 chunks x 32 channels
+      uint4 R[4][4];
+      if (p.residual) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int ch = n0 + col_lo + c * 32;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            R[c][g] = make_uint4(0, 0, 0, 0);
+            if (ri.valid && col_lo + c * 32 < col_hi && ch + g * 8 < p.out_c_store)
+              R[c][g] = *(const uint4*)(p.residual + ri.orow * p.res_cp + ch + g * 8);
+          }
+        }
+      }
+      if (ok) ok = mbar_wait_t(&tfull_bar[acc], acc_phase, p.err, 104, w_full);
+      ok = __all_sync(0xffffffffu, ok);
+      if (!ok) break;
+      tc_fence_after();
+      const long long te0 = clock64();
+      for (int j = 0; j < p.mt; ++j) {
+        RowInfo rn;
+        rn.valid = false;
+        rn.orow = 0;
+        if (j + 1 < p.mt) rn = row_info(p, row0 + (long long)(j + 1) * kBlockM);
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256 + j * p.sub_cols);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int col = col_lo + c * 32;
+          if (col >= col_hi) break;
+          uint32_t v[32];
+          __syncwarp();   // lanes diverge on `valid` below; tcgen05.ld is .sync.aligned
+          tmem_ld32(t_row + col, v);
+          const int ch = n0 + col;
+          if (ri.valid) {
+            float y[32];
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              const float4 s4 = *(const float4*)(v_scale + ch + g * 4);
+              const float4 b4 = *(const float4*)(v_bias + ch + g * 4);
+              y[g * 4 + 0] = fmaf(__uint_as_float(v[g * 4 + 0]), s4.x, b4.x);
+              y[g * 4 + 1] = fmaf(__uint_as_float(v[g * 4 + 1]), s4.y, b4.y);
+              y[g * 4 + 2] = fmaf(__uint_as_float(v[g * 4 + 2]), s4.z, b4.z);
+              y[g * 4 + 3] = fmaf(__uint_as_float(v[g * 4 + 3]), s4.w, b4.w);
+            }
+            if (p.out_f32) {
+              float* o = p.out_f32 + ri.orow * p.out_f32_stride + ch;
+#pragma unroll
+              for (int g = 0; g < 8; ++g)
+                if (ch + g * 4 < p.out_f32_cols) *(float4*)(o + g * 4) = make_float4(y[g * 4], y[g * 4 + 1], y[g * 4 + 2], y[g * 4 + 3]);
+            } else {
+              if (p.residual) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                  float f[8];
+                  unpack_h8(R[c][g], f);
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) y[g * 8 + e] += f[e];
+                }
+              }
+              if (p.act == PCB_ACT_RELU) {
+#pragma unroll
+                for (int e = 0; e < 32; ++e) y[e] = fmaxf(y[e], 0.f);
+              } else if (p.act == PCB_ACT_PRELU) {
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                  const float4 a4 = *(const float4*)(v_slope + ch + g * 4);
+                  y[g * 4 + 0] = y[g * 4 + 0] >= 0.f ? y[g * 4 + 0] : y[g * 4 + 0] * a4.x;
+                  y[g * 4 + 1] = y[g * 4 + 1] >= 0.f ? y[g * 4 + 1] : y[g * 4 + 1] * a4.y;
+                  y[g * 4 + 2] = y[g * 4 + 2] >= 0.f ? y[g * 4 + 2] : y[g * 4 + 2] * a4.z;
+                  y[g * 4 + 3] = y[g * 4 + 3] >= 0.f ? y[g * 4 + 3] : y[g * 4 + 3] * a4.w;
+                }
+              }
+              if (p.out_s32) {
+                float* o = p.out_s32 + ri.orow * p.out_cp + ch;
+#pragma unroll
+                for (int g = 0; g < 8; ++g)
+                  if (ch + g * 4 < p.out_c_store) *(float4*)(o + g * 4) = make_float4(y[g * 4], y[g * 4 + 1], y[g * 4 + 2], y[g * 4 + 3]);
+              } else {
+                __half* o = p.out + ri.orow * p.out_cp + ch;
+#pragma unroll
+                for (int g = 0; g < 4; ++g)
+                  if (ch + g * 8 < p.out_c_store) *(uint4*)(o + g * 8) = pack_h8(y + g * 8);
+              }
+              if (p.out2) {
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                  const float4 s4 = *(const float4*)(v_scale2 + ch + g * 4);
+                  const float4 b4 = *(const float4*)(v_bias2 + ch + g * 4);
+                  y[g * 4 + 0] = fmaf(y[g * 4 + 0], s4.x, b4.x);
+                  y[g * 4 + 1] = fmaf(y[g * 4 + 1], s4.y, b4.y);
+                  y[g * 4 + 2] = fmaf(y[g * 4 + 2], s4.z, b4.z);
+                  y[g * 4 + 3] = fmaf(y[g * 4 + 3], s4.w, b4.w);
+                }
+                __half* o2 = p.out2 + ri.orow * p.out2_cp + ch;
+#pragma unroll
+                for (int g = 0; g < 4; ++g)
+                  if (ch + g * 8 < p.out_c_store) *(uint4*)(o2 + g * 8) = pack_h8(y + g * 8);
+              }
+            }
+          }
+          // refill this chunk's residual registers with the next sub-tile's row
+          if (p.residual && j + 1 < p.mt) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              R[c][g] = make_uint4(0, 0, 0, 0);
+              if (rn.valid && ch + g * 8 < p.out_c_store)
+                R[c][g] = *(const uint4*)(p.residual + rn.orow * p.res_cp + ch + g * 8);
+            }
+          }
+        }
+        ri = rn;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      t_epi += clock64() - te0;
+      if (p.acc_bufs == 2) {
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      } else {
+        acc_phase ^= 1;
+      }
+    }
+    if (p.dbg && blockIdx.x == 0 && warp == kEpiWarp0 && lane == 0) {
+      p.dbg[9] = (unsigned long long)w_full;
+      p.dbg[10] = (unsigned long long)t_epi;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+  if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) {
+    p.dbg[2] = (unsigned long long)clock64();
+    p.dbg[3] = globaltimer_ns();
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 2-D fp16 map over a row-major [rows][cols] matrix with a {64, box_rows} box, 128B swizzle.
+bool make_map_2d(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_elems, uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {row_stride_elems * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kKC, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+int env_int(const char* name, int dflt) {
+  const char* s = getenv(name);
+  return s && *s ? atoi(s) : dflt;
+}
+
+// Fills the A-stage plan (loads, tap offsets, stage bytes) for `mt` sub-tiles.  Returns false if no
+// plan exists (box limits).
+bool plan_a(Conv2Params& p, int mt, int* a2_rows) {
+  p.mt = mt;
+  p.n_aloads = 0;
+  *a2_rows = 8;
+  auto add = [&](int row_rel, int off, int map2) {
+    if (p.n_aloads >= kMaxALoads) return false;
+    p.aloads[p.n_aloads++] = ALoad{row_rel, off, map2};
+    return true;
+  };
+  if (p.taps == 1) {
+    for (int j = 0; j < mt; ++j) add(j * kBlockM, j * kSubBytes, 0);
+    p.tap_off[0] = 0;
+    p.a_stage_bytes = mt * kSubBytes;
+    p.a_tx_bytes = mt * kSubBytes;
+    return true;
+  }
+  const int halo = p.wp + 1;
+  const int merged_extra = pcb_round_up(2 * halo, 8);
+  const long long merged_rows = (long long)mt * kBlockM + merged_extra;
+  const long long banded_rows = 3LL * (mt * kBlockM + 8);
+  if (merged_extra <= 256 && merged_rows <= banded_rows) {
+    for (int j = 0; j < mt; ++j) add(-halo + j * kBlockM, j * kSubBytes, 0);
+    add(-halo + mt * kBlockM, mt * kSubBytes, 1);
+    *a2_rows = merged_extra;
+    for (int t = 0; t < 9; ++t) p.tap_off[t] = (halo + (t / 3 - 1) * p.wp + (t % 3 - 1)) * 128;
+    p.a_tx_bytes = (int)merged_rows * 128;
+    p.a_stage_bytes = pcb_round_up(p.a_tx_bytes, 1024);
+    return true;
+  }
+  const int band_bytes = pcb_round_up((mt * kBlockM + 8) * 128, 1024);
+  for (int b = 0; b < 3; ++b) {
+    for (int j = 0; j < mt; ++j)
+      if (!add((b - 1) * p.wp - 1 + j * kBlockM, b * band_bytes + j * kSubBytes, 0)) return false;
+    if (!add((b - 1) * p.wp - 1 + mt * kBlockM, b * band_bytes + mt * kSubBytes, 1)) return false;
+  }
+  for (int t = 0; t < 9; ++t) p.tap_off[t] = (t / 3) * band_bytes + (t % 3) * 128;
+  p.a_tx_bytes = (int)banded_rows * 128;
+  p.a_stage_bytes = 3 * band_bytes;
+  return true;
+}
+
+}  // namespace
+
+int pcb_conv_tc2(pcb_ctx* c, const ConvArgs& a) {
+  const PTensor& in = *a.in;
+  const ConvWeights& w = *a.w;
+  if (a.residual && a.residual->f32) return pcb_conv_tc(c, a);   // fp32 residual stream: baseline kernel only
+  Conv2Params p{};
+  p.rows = (int)in.rows();
+  p.dense = in.dense ? 1 : 0;
+  p.hp = in.dense ? 0 : in.h + 2;
+  p.wp = in.dense ? 0 : in.w + 2;
+  p.taps = w.taps;
+  p.cin_w = w.cin_w;
+  p.kchunks = w.cin_w / kKC;
+  p.n_tile = w.n_tile;
+  p.n_tiles = w.npad / w.n_tile;
+  p.vec_n = pcb_round_up(w.npad, 32);
+  p.vec_real = w.npad;
+  p.stride = in.dense ? 1 : a.stride;
+  p.act = a.act;
+  p.scale = w.scale;
+  p.bias = w.bias;
+  p.slope = w.slope;
+  p.err = c->d_err;
+  p.desc_mode = env_int("PCB_DESC_MODE", 1);
+  if (a.out_f32) {
+    p.out_f32 = a.out_f32;
+    p.out_f32_stride = a.out_f32_stride;
+    p.out_f32_cols = w.cout;
+  } else {
+    const PTensor& out = *a.out;
+    if (out.f32) p.out_s32 = (float*)out.data;
+    else p.out = out.data;
+    p.out_cp = out.cp;
+    p.out_c_store = out.cp;
+    p.hp_out = out.h + 2;
+    p.wp_out = out.w + 2;
+    if (out.cp > w.npad) return pcb_fail(c, PCB_ERR_ARG, "conv_tc2: output channels exceed packed weight rows");
+    if (a.residual) {
+      p.residual = a.residual->data;
+      p.res_cp = a.residual->cp;
+    }
+    if (a.out2) {
+      if (a.out2->cp != out.cp || a.out2->f32) return pcb_fail(c, PCB_ERR_ARG, "conv_tc2: out2 geometry");
+      p.out2 = a.out2->data;
+      p.out2_cp = a.out2->cp;
+      p.scale2 = a.scale2;
+      p.bias2 = a.bias2;
+    }
+  }
+  if (w.n_tile % 16 || w.n_tile > 256 || w.n_tile < 16) return pcb_fail(c, PCB_ERR_ARG, "conv_tc2: bad n_tile");
+  p.sub_cols = pcb_round_up(w.n_tile, 32);
+  p.b_bytes = w.n_tile * kKC * 2;
+  const int ksteps = p.taps * p.kchunks;
+  const int fixed = 5 * p.vec_n * 4 + (2 * kMaxA + 2 * kMaxB + 4) * 8 + 16 + 1024;
+
+  // choose MT (1 or 2): fewer L2 bytes per FLOP at MT=2, but half as many tiles to spread over the SMs
+  const int force_mt = env_int("PCB_CONV_MT", 0);
+  int best_mt = 0;
+  double best_cost = 0.0;
+  int a2_rows = 8;
+  for (int mt = 1; mt <= 2; ++mt) {
+    if (force_mt && mt != force_mt) continue;
+    if (mt * p.sub_cols > (int)kTmemCols) continue;
+    Conv2Params q = p;
+    int a2 = 8;
+    if (!plan_a(q, mt, &a2)) continue;
+    const int min_b = ksteps < 3 ? ksteps : 3;
+    if (2 * q.a_stage_bytes + min_b * q.b_bytes + fixed > kSmemBudget) continue;
+    const long long m_tiles = ((long long)p.rows + mt * kBlockM - 1) / (mt * kBlockM);
+    const long long tiles = m_tiles * p.n_tiles;
+    const long long waves = (tiles + c->num_sms - 1) / c->num_sms;
+    // relative time per tile: rows * (1 + L2 penalty); MT=2 moves ~0.6x the bytes per row
+    const double cost = (double)waves * mt * (mt == 1 ? 1.0 : 0.72);
+    if (!best_mt || cost < best_cost) { best_mt = mt; best_cost = cost; }
+  }
+  if (!best_mt) return pcb_conv_tc(c, a);   // no shared-memory plan (very wide maps): baseline kernel
+  plan_a(p, best_mt, &a2_rows);
+  p.m_tiles = (int)(((long long)p.rows + p.mt * kBlockM - 1) / (p.mt * kBlockM));
+  p.acc_bufs = (p.mt * p.sub_cols <= 256) ? 2 : 1;
+  const int room = kSmemBudget - fixed;
+  p.b_resident = 0;
+  if (p.n_tiles == 1 && ksteps <= kMaxB && 2 * p.a_stage_bytes + ksteps * p.b_bytes <= room && !env_int("PCB_CONV_NO_RESIDENT", 0)) {
+    p.b_resident = 1;
+    p.b_stages = ksteps;
+    p.a_stages = (room - ksteps * p.b_bytes) / p.a_stage_bytes;
+  } else {
+    // two A stages, the rest to B; a third A stage when B already has >= 6
+    p.a_stages = 2;
+    p.b_stages = (room - 2 * p.a_stage_bytes) / p.b_bytes;
+    if (p.b_stages > 8 && (room - 3 * p.a_stage_bytes) / p.b_bytes >= 6) {
+      p.a_stages = 3;
+      p.b_stages = (room - 3 * p.a_stage_bytes) / p.b_bytes;
+    }
+    if (p.b_stages > kMaxB) p.b_stages = kMaxB;
+  }
+  if (p.a_stages > kMaxA) p.a_stages = kMaxA;
+  if (p.a_stages > p.kchunks * 2 && p.a_stages > 2) p.a_stages = 2;
+  const size_t smem = (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * p.b_bytes + fixed;
+
+  CUtensorMap tmA, tmA2, tmB;
+  if (!make_map_2d(&tmA, in.data, (uint64_t)p.rows, (uint64_t)in.cp, (uint64_t)in.cp, kBlockM))
+    return pcb_fail(c, PCB_ERR_CUDA, "cuTensorMapEncodeTiled(A) failed");
+  if (!make_map_2d(&tmA2, in.data, (uint64_t)p.rows, (uint64_t)in.cp, (uint64_t)in.cp, (uint32_t)a2_rows))
+    return pcb_fail(c, PCB_ERR_CUDA, "cuTensorMapEncodeTiled(A2) failed");
+  if (!make_map_2d(&tmB, w.w, (uint64_t)w.npad, (uint64_t)w.taps * w.cin_w, (uint64_t)w.taps * w.cin_w, (uint32_t)w.n_tile))
+    return pcb_fail(c, PCB_ERR_CUDA, "cuTensorMapEncodeTiled(B) failed");
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    PCB_CUDA(c, cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  const int total = p.m_tiles * p.n_tiles;
+  const int grid = total < c->num_sms ? total : c->num_sms;
+  // algorithmic FLOPs of this layer: 2 * output pixels * cout * cin * taps (real, unpadded extents)
+  double out_px = in.dense ? (double)in.n : (double)in.n * (in.h / p.stride) * (in.w / p.stride);
+  const double k_real = (w.taps == 1 && w.cin == 3) ? 27.0 : (double)w.cin * w.taps;
+  char desc[200];
+  desc[0] = 0;
+  if (c->profile)
+    snprintf(desc, sizeof desc, "n=%d,h=%d,w=%d,cin=%d,cout=%d,taps=%d,stride=%d,ntile=%d,mt=%d,tiles=%d,grid=%d,res=%d,f32out=%d,out2=%d,ast=%d,bst=%d,bres=%d",
+             in.n, in.h, in.w, w.cin, w.cout, w.taps, p.stride, p.n_tile, p.mt, total, grid, a.residual ? 1 : 0,
+             (a.out && a.out->f32) ? 1 : 0, a.out2 ? 1 : 0, p.a_stages, p.b_stages, p.b_resident);
+  static const int debug = env_int("PCB_CONV_DEBUG", 0);
+  static unsigned long long* dbg_dev = nullptr;
+  if (debug && c->profile) {
+    if (!dbg_dev) dbg_dev = (unsigned long long*)pcb_dev_alloc(c, 16 * sizeof(unsigned long long), true);
+    p.dbg = dbg_dev;
+  }
+  {
+    PcbConvTimer timer(c, 2.0 * out_px * (double)w.cout * k_real, desc);
+    conv_tc2_kernel<<<grid, kThreads, smem, c->stream>>>(tmA, tmA2, tmB, p);
+  }
+  PCB_LAUNCH_CHECK(c, "conv_tc2_kernel");
+  if (p.dbg) {
+    // debug only: serialises the stream.  Columns: SM MHz seen by block 0, its cycles, and the cycles each role
+    // of block 0 spent blocked (A/B producer on empty slots, MMA on A/B full and on TMEM empty, epilogue on TMEM full)
+    unsigned long long h[16];
+    cudaMemcpyAsync(h, dbg_dev, sizeof h, cudaMemcpyDeviceToHost, c->stream);
+    cudaStreamSynchronize(c->stream);
+    const double cyc = (double)(h[2] - h[0]), ns = (double)(h[3] - h[1]);
+    fprintf(stderr, "CONVDBG %s | mhz=%.0f cyc=%.0f prodA_wait=%.2f prodB_wait=%.2f mma_waitA=%.2f mma_waitB=%.2f mma_waitT=%.2f epi_wait=%.2f epi_busy=%.2f\n",
+            desc, ns > 0 ? cyc / ns * 1e3 : 0.0, cyc, h[4] / cyc, h[5] / cyc, h[6] / cyc, h[7] / cyc, h[8] / cyc, h[9] / cyc, h[10] / cyc);
+  }
+  return PCB_OK;
+}

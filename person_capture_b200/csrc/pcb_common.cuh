@@ -71,7 +71,7 @@ struct pcb_ctx {
   std::string last_error;
   int* d_err = nullptr;       // device error word (watchdog / overflow)
   int* h_err = nullptr;       // pinned mirror
-  int conv_impl = 0;          // 0 = tcgen05 (product), 1 = CUDA-core validation kernel
+  int conv_impl = 0;          // 0 = tcgen05 (product), 1 = CUDA-core validation kernel, 2 = tcgen05 baseline (one TMA load per tap)
   long long launches = 0;     // kernels launched since the last pcb_reset_counters
   std::vector<void*> allocs;  // everything cudaMalloc'ed through the context
   struct Model* models[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -113,7 +113,8 @@ int pcb_fail(pcb_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess
 void* pcb_dev_alloc(pcb_ctx* c, size_t bytes, bool zero);
 
 // conv_tc.cu / conv_simple.cu
-int pcb_conv_tc(pcb_ctx* c, const ConvArgs& a);
+int pcb_conv_tc2(pcb_ctx* c, const ConvArgs& a);   // product kernel (operand reuse in shared memory)
+int pcb_conv_tc(pcb_ctx* c, const ConvArgs& a);    // first formulation, kept as the A/B baseline (impl 2)
 int pcb_conv_simple(pcb_ctx* c, const ConvArgs& a);
 // ops.cu
 int pcb_op_affine(pcb_ctx* c, const PTensor& in, const PTensor& out, const float* scale, const float* bias);

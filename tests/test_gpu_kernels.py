@@ -90,10 +90,11 @@ def _scrfd_heads(eng, name, blob_img, S, impl):
 
 
 @pytest.mark.parametrize("name,fix,S", [("scrfd_2.5g_bnkps", "engine_25g_r50", 320), ("scrfd_10g_bnkps", "engine_10g_r50", 512)])
-@pytest.mark.parametrize("impl", [1, 0])
+@pytest.mark.parametrize("impl", [1, 2, 0])
 def test_scrfd_heads_match_oracle(request, name, fix, S, impl):
     """fp16 conv path vs fp32 oracle on identical weights: head maps agree to 2e-2 absolute on logits
-    / distances (values are O(1..10)); impl 1 = CUDA-core validation kernel, 0 = tcgen05."""
+    / distances (values are O(1..10)); impl 1 = CUDA-core validation kernel, 2 = first tcgen05 formulation,
+    0 = product tcgen05 kernel (operand reuse in shared memory)."""
     eng = request.getfixturevalue(fix)
     from person_capture_b200 import synth, _lib as L
     clip = synth.ClipSpec(S, S, 10, seed=3, target_segments=[(0, 9)])
@@ -110,7 +111,7 @@ def test_scrfd_heads_match_oracle(request, name, fix, S, impl):
         assert err.max() < 0.06 and err.mean() < 4e-3, (lvl, float(err.max()), float(err.mean()))
 
 
-@pytest.mark.parametrize("impl", [1, 0])
+@pytest.mark.parametrize("impl", [1, 2, 0])
 def test_arcface_embeddings_match_oracle(engine_25g_r50, impl):
     """cosine(e_gpu, e_oracle) >= 0.999 (north_star tolerance) on R50, with and without flip."""
     eng = engine_25g_r50

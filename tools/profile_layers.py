@@ -11,6 +11,8 @@ ap.add_argument("--S", type=int, default=512)
 ap.add_argument("--n", type=int, default=64)
 ap.add_argument("--faces", type=int, default=128)
 ap.add_argument("--out", default="gpurun_out/layers.csv")
+ap.add_argument("--impl", type=int, default=0)
+ap.add_argument("--sustain", type=int, default=0, help="run the ArcFace pass this many times back to back and report TF/s + clocks")
 args = ap.parse_args()
 if os.path.exists(args.out):
     os.remove(args.out)
@@ -18,6 +20,7 @@ os.environ["PCB_PROFILE_DUMP"] = args.out
 import torch
 from person_capture_b200.engine import Engine
 eng = Engine(0, scrfd=args.scrfd, arcface=args.arcface)
+eng.set_conv_impl(args.impl)
 rng = np.random.default_rng(0)
 frames = eng.to_device(rng.integers(0, 256, (args.n, 540, 960, 3), dtype=np.uint8))
 chips = eng.to_device(rng.integers(0, 256, (args.faces, 112, 112, 3), dtype=np.uint8))
@@ -46,3 +49,28 @@ for line in open(args.out):
 print(f"{'layer shape':110s} {'cnt':>4s} {'ms':>9s} {'TF/s':>8s} {'%time':>6s}")
 for k, (c, t, f) in sorted(rows.items(), key=lambda kv: -kv[1][1]):
     print(f"{k:110s} {c:4d} {t:9.3f} {f/t/1e9:8.1f} {100*t/ms:6.1f}")
+
+if args.sustain:
+    import subprocess, threading, time
+    from person_capture_b200 import graphs
+    eng.set_profile(False)
+    rows = []
+    pr = subprocess.Popen(["nvidia-smi", "--query-gpu=clocks.sm,power.draw,clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits", "-lms", "50"],
+                          stdout=subprocess.PIPE, text=True)
+    threading.Thread(target=lambda: [rows.append(l.strip()) for l in pr.stdout], daemon=True).start()
+    time.sleep(0.3)
+    n0 = len(rows)
+    a0 = torch.cuda.Event(enable_timing=True); a1 = torch.cuda.Event(enable_timing=True)
+    a0.record(eng.stream)
+    for _ in range(args.sustain):
+        eng.embed(chips, args.faces, True)
+    a1.record(eng.stream)
+    eng.sync()
+    n1 = len(rows)
+    pr.terminate()
+    ms = a0.elapsed_time(a1)
+    fl = 2.0 * graphs.graph_macs(graphs.build_graph(args.arcface), 112, 112) * 2 * args.faces * args.sustain
+    clk = [float(r.split(",")[0]) for r in rows[n0:n1] if r]
+    pw = [float(r.split(",")[1]) for r in rows[n0:n1] if r]
+    print(f"sustained ArcFace: {args.sustain} passes of {2*args.faces} images in {ms:.1f} ms -> {fl/ms/1e9:.1f} TFLOP/s (whole pass incl. non-conv kernels); "
+          f"sm clock median {np.median(clk) if clk else -1:.0f} MHz min {min(clk) if clk else -1:.0f}, power median {np.median(pw) if pw else -1:.0f} W, samples {len(clk)}")
