@@ -38,7 +38,8 @@ const char* pcb_last_error(pcb_ctx* ctx);
 /* Waits for the stream and checks the device-side error word (watchdogs, capacity overflow). */
 int pcb_sync(pcb_ctx* ctx);
 /* 0 = tcgen05/TMEM implicit GEMM (default), 1 = CUDA-core validation kernel (tests only),
- * 2 = first tcgen05 formulation (one TMA load per tap; A/B baseline for profiles). */
+ * 2 = first tcgen05 formulation (one TMA load per tap; A/B baseline for profiles),
+ * 3 = transposed tcgen05 experiment (couts on the UMMA M dimension). */
 int pcb_set_conv_impl(pcb_ctx* ctx, int impl);
 /* Number of kernels this library launched on the context since the last reset. */
 long long pcb_launch_count(pcb_ctx* ctx);

@@ -117,7 +117,7 @@ extern "C" int pcb_sync(pcb_ctx* c) {
 }
 
 extern "C" int pcb_set_conv_impl(pcb_ctx* c, int impl) {
-  if (impl < 0 || impl > 2) return pcb_fail(c, PCB_ERR_ARG, "conv impl must be 0, 1 or 2");
+  if (impl < 0 || impl > 3) return pcb_fail(c, PCB_ERR_ARG, "conv impl must be 0..3");
   c->conv_impl = impl;
   return PCB_OK;
 }
@@ -213,13 +213,14 @@ extern "C" int pcb_model_load(pcb_ctx* c, int slot, const pcb_op* ops, int n_ops
       w.cin_w = pcb_round_up(cin_eff, 64);
       w.npad = op.cout <= 256 ? pcb_round_up(op.cout, 16) : pcb_round_up(op.cout, 256);
       w.n_tile = w.npad <= 256 ? w.npad : 256;
+      w.rows_alloc = pcb_round_up(w.npad, 128);   // zero rows up to a multiple of 128: conv_tc3 uses couts as the UMMA M dimension
       const size_t wbytes = (size_t)op.cout * op.cin * kk * sizeof(__half);
       if (!need(op.w_off, wbytes) || !need(op.scale_off, op.cout * 4) || !need(op.bias_off, op.cout * 4)) {
         delete m;
         return pcb_fail(c, PCB_ERR_ARG, "model_load: blob offsets out of range");
       }
       const __half* src = (const __half*)(blob + op.w_off);
-      std::vector<__half> packed((size_t)w.npad * w.taps * w.cin_w, __float2half(0.f));
+      std::vector<__half> packed((size_t)w.rows_alloc * w.taps * w.cin_w, __float2half(0.f));
       for (int co = 0; co < op.cout; ++co)
         for (int ci = 0; ci < op.cin; ++ci)
           for (int t = 0; t < kk; ++t) {
@@ -233,17 +234,17 @@ extern "C" int pcb_model_load(pcb_ctx* c, int slot, const pcb_op* ops, int n_ops
       if (!w.w) { delete m; return pcb_fail(c, PCB_ERR_CUDA, "model_load: weight alloc failed"); }
       PCB_CUDA(c, cudaMemcpyAsync(w.w, packed.data(), packed.size() * sizeof(__half), cudaMemcpyHostToDevice, c->stream));
       PCB_CUDA(c, cudaStreamSynchronize(c->stream));
-      w.scale = upload_f32_padded(c, (const float*)(blob + op.scale_off), op.cout, w.npad, 0.f);
-      w.bias = upload_f32_padded(c, (const float*)(blob + op.bias_off), op.cout, w.npad, 0.f);
+      w.scale = upload_f32_padded(c, (const float*)(blob + op.scale_off), op.cout, w.rows_alloc, 0.f);
+      w.bias = upload_f32_padded(c, (const float*)(blob + op.bias_off), op.cout, w.rows_alloc, 0.f);
       if (op.act == PCB_ACT_PRELU) {
         if (!need(op.slope_off, op.cout * 4)) { delete m; return pcb_fail(c, PCB_ERR_ARG, "model_load: slope offset"); }
-        w.slope = upload_f32_padded(c, (const float*)(blob + op.slope_off), op.cout, w.npad, 0.f);
+        w.slope = upload_f32_padded(c, (const float*)(blob + op.slope_off), op.cout, w.rows_alloc, 0.f);
       }
       if (!w.scale || !w.bias) { delete m; return pcb_fail(c, PCB_ERR_CUDA, "model_load: param upload failed"); }
       if (op.kind == PCB_OP_CONV && op.out2 >= 0) {
         if (!need(op.scale2_off, op.cout * 4) || !need(op.bias2_off, op.cout * 4)) { delete m; return pcb_fail(c, PCB_ERR_ARG, "model_load: out2 offsets"); }
-        m->aff_scale[i] = upload_f32_padded(c, (const float*)(blob + op.scale2_off), op.cout, w.npad, 0.f);
-        m->aff_bias[i] = upload_f32_padded(c, (const float*)(blob + op.bias2_off), op.cout, w.npad, 0.f);
+        m->aff_scale[i] = upload_f32_padded(c, (const float*)(blob + op.scale2_off), op.cout, w.rows_alloc, 0.f);
+        m->aff_bias[i] = upload_f32_padded(c, (const float*)(blob + op.bias2_off), op.cout, w.rows_alloc, 0.f);
         if (!m->aff_scale[i] || !m->aff_bias[i]) { delete m; return pcb_fail(c, PCB_ERR_CUDA, "model_load: param upload failed"); }
       }
     } else if (op.kind == PCB_OP_AFFINE || op.kind == PCB_OP_AFFINE_FLATTEN) {
@@ -382,7 +383,7 @@ static int model_run(pcb_ctx* c, Model* m, Model::Run* r) {
           }
         }
         w.n_tile = pick_n_tile(c, w, a.in->rows());
-        rc = c->conv_impl == 0 ? pcb_conv_tc2(c, a) : c->conv_impl == 2 ? pcb_conv_tc(c, a) : pcb_conv_simple(c, a);
+        rc = c->conv_impl == 0 ? pcb_conv_tc2(c, a) : c->conv_impl == 3 ? pcb_conv_tc3(c, a) : c->conv_impl == 2 ? pcb_conv_tc(c, a) : pcb_conv_simple(c, a);
         break;
       }
       case PCB_OP_AFFINE: rc = pcb_op_affine(c, r->t[op.in0], r->t[op.out], m->aff_scale[i], m->aff_bias[i]); break;

@@ -57,6 +57,7 @@ struct Conv2Params {
   int hp, wp;      // input padded dims; 0 for dense
   int taps;        // 9 or 1
   int kchunks;     // ceil(cin_eff / 64)
+  int kinstr_last; // 16-channel MMA steps in the last chunk (1..4)
   int cin_w;       // packed weight K extent per tap
   int n_tile, n_tiles, m_tiles;   // m_tiles counts tiles of mt*128 rows
   int mt;          // 128-row sub-tiles per CTA tile
@@ -141,6 +142,19 @@ __device__ __forceinline__ bool mbar_wait_t(uint64_t* bar, uint32_t parity, int*
   acc += clock64() - t0;
   return ok;
 }
+// One lane of a converged warp (the canonical single-issuer idiom: control flow stays warp-uniform, so the
+// operands of UTCHMMA / UTMALDG / SYNCS live in uniform registers instead of being broadcast lane by lane --
+// with `if (lane == 0)` around the loop every tcgen05.mma was wrapped in an ELECT/R2UR/BRA.U.ANY loop and
+// issue, not the tensor pipe, set the pace at ~150 cycles per instruction).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -195,6 +209,15 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr, int desc_mod
   return lo | (hi << 32);
 }
 
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
 struct RowInfo {
   bool valid;
   long long orow;
@@ -235,6 +258,8 @@ __device__ __forceinline__ uint4 pack_h8(const float* f) {
   return v;
 }
 
+// kAct: PCB_ACT_*; kRes: residual add; kOut2: second (affine) output; kOutMode: 0 fp16 P-layout, 1 fp32 P-layout, 2 dense fp32
+template <int kAct, bool kRes, bool kOut2, int kOutMode>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                 const __grid_constant__ CUtensorMap tmB, const __grid_constant__ Conv2Params p) {
@@ -243,7 +268,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + (size_t)p.a_stages * p.a_stage_bytes;
   float* vec = (float*)(smem_b + (size_t)p.b_stages * p.b_bytes);   // scale | bias | slope | scale2 | bias2
-  uint64_t* bars = (uint64_t*)(vec + 5 * p.vec_n);
+  uint8_t* stage_buf = (uint8_t*)(vec + 5 * p.vec_n);                  // [8 warps][2 KB] epilogue transpose buffers
+  uint64_t* bars = (uint64_t*)(stage_buf + kEpiWarps * 2048);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + kMaxA;
   uint64_t* b_full = a_empty + kMaxA;
@@ -252,7 +278,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform by construction
   const int lane = threadIdx.x & 31;
   const int total_tiles = p.m_tiles * p.n_tiles;
   const int tile_rows = p.mt * kBlockM;
@@ -292,10 +318,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================== A producer =====================
-    if (lane == 0) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA2) : "memory");
+    // ===================== A producer (whole warp loops, one elected lane issues) =====================
+    {
+      if (elect_one()) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA2) : "memory");
+      }
       int stage = 0;
       uint32_t phase = 0;
       bool ok = true;
@@ -306,17 +334,21 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int mt_idx = tile / p.n_tiles;
         const int m0 = mt_idx * tile_rows;
         for (int kc = 0; kc < p.kchunks; ++kc) {
-          if (!mbar_wait_t(&a_empty[stage], phase ^ 1, p.err, 101, w_empty)) { ok = false; break; }
-          const uint32_t sa = smem_u32(smem_a + (size_t)stage * p.a_stage_bytes);
-          mbar_expect_tx(&a_full[stage], (uint32_t)p.a_tx_bytes);
-          for (int l = 0; l < p.n_aloads; ++l) {
-            const ALoad ld = p.aloads[l];
-            tma_load_2d(ld.map2 ? &tmA2 : &tmA, &a_full[stage], sa + ld.smem_off, kc * kKC, m0 + ld.row_rel);
+          ok = __all_sync(0xffffffffu, mbar_wait_t(&a_empty[stage], phase ^ 1, p.err, 101, w_empty));
+          if (!ok) break;
+          if (elect_one()) {
+            const uint32_t sa = smem_u32(smem_a + (size_t)stage * p.a_stage_bytes);
+            mbar_expect_tx(&a_full[stage], (uint32_t)p.a_tx_bytes);
+            for (int l = 0; l < p.n_aloads; ++l) {
+              const ALoad ld = p.aloads[l];
+              tma_load_2d(ld.map2 ? &tmA2 : &tmA, &a_full[stage], sa + ld.smem_off, kc * kKC, m0 + ld.row_rel);
+            }
           }
+          __syncwarp();
           if (++stage == p.a_stages) { stage = 0; phase ^= 1; }
         }
       }
-      if (p.dbg && blockIdx.x == 0) {
+      if (p.dbg && blockIdx.x == 0 && lane == 0) {
         p.dbg[0] = (unsigned long long)c0;
         p.dbg[1] = n0s;
         p.dbg[4] = (unsigned long long)w_empty;
@@ -324,37 +356,44 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
   } else if (warp == 2) {
     // ===================== B producer =====================
-    if (lane == 0) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    {
+      if (elect_one()) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
       const int ksteps = p.taps * p.kchunks;
+      long long w_empty = 0;
       if (p.b_resident) {
-        for (int ks = 0; ks < ksteps; ++ks) {
-          const int kc = ks / p.taps, t = ks - kc * p.taps;
-          mbar_expect_tx(&b_full[ks], (uint32_t)p.b_bytes);
-          tma_load_2d(&tmB, &b_full[ks], smem_u32(smem_b + (size_t)ks * p.b_bytes), t * p.cin_w + kc * kKC, 0);
+        if (elect_one()) {
+          for (int ks = 0; ks < ksteps; ++ks) {
+            const int kc = ks / p.taps, t = ks - kc * p.taps;
+            mbar_expect_tx(&b_full[ks], (uint32_t)p.b_bytes);
+            tma_load_2d(&tmB, &b_full[ks], smem_u32(smem_b + (size_t)ks * p.b_bytes), t * p.cin_w + kc * kKC, 0);
+          }
         }
+        __syncwarp();
       } else {
         int stage = 0;
         uint32_t phase = 0;
         bool ok = true;
-        long long w_empty = 0;
         for (int tile = blockIdx.x; ok && tile < total_tiles; tile += gridDim.x) {
           const int mt_idx = tile / p.n_tiles, nt = tile - mt_idx * p.n_tiles;
           const int n0 = nt * p.n_tile;
           for (int ks = 0; ks < ksteps; ++ks) {
             const int kc = ks / p.taps, t = ks - kc * p.taps;
-            if (!mbar_wait_t(&b_empty[stage], phase ^ 1, p.err, 105, w_empty)) { ok = false; break; }
-            mbar_expect_tx(&b_full[stage], (uint32_t)p.b_bytes);
-            tma_load_2d(&tmB, &b_full[stage], smem_u32(smem_b + (size_t)stage * p.b_bytes), t * p.cin_w + kc * kKC, n0);
+            ok = __all_sync(0xffffffffu, mbar_wait_t(&b_empty[stage], phase ^ 1, p.err, 105, w_empty));
+            if (!ok) break;
+            if (elect_one()) {
+              mbar_expect_tx(&b_full[stage], (uint32_t)p.b_bytes);
+              tma_load_2d(&tmB, &b_full[stage], smem_u32(smem_b + (size_t)stage * p.b_bytes), t * p.cin_w + kc * kKC, n0);
+            }
+            __syncwarp();
             if (++stage == p.b_stages) { stage = 0; phase ^= 1; }
           }
         }
-        if (p.dbg && blockIdx.x == 0) p.dbg[5] = (unsigned long long)w_empty;
       }
+      if (p.dbg && blockIdx.x == 0 && lane == 0) p.dbg[5] = (unsigned long long)w_empty;
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (whole warp loops, one elected lane issues) =====================
+    {
       const uint32_t idesc = (1u << 4)                          // D format: F32
                              | (0u << 7) | (0u << 10)           // A, B format: F16
                              | ((uint32_t)(p.n_tile >> 3) << 17)
@@ -367,42 +406,50 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       bool b_loaded = false;
       long long w_a = 0, w_b = 0, w_t = 0;
       for (int tile = blockIdx.x; ok && tile < total_tiles; tile += gridDim.x) {
-        if (!mbar_wait_t(&tempty_bar[acc], acc_phase ^ 1, p.err, 102, w_t)) { ok = false; break; }
+        ok = __all_sync(0xffffffffu, mbar_wait_t(&tempty_bar[acc], acc_phase ^ 1, p.err, 102, w_t));
+        if (!ok) break;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
         for (int kc = 0; ok && kc < p.kchunks; ++kc) {
-          if (!mbar_wait_t(&a_full[a_stage], a_phase, p.err, 103, w_a)) { ok = false; break; }
+          ok = __all_sync(0xffffffffu, mbar_wait_t(&a_full[a_stage], a_phase, p.err, 103, w_a));
+          if (!ok) break;
           const uint32_t sa = smem_u32(smem_a + (size_t)a_stage * p.a_stage_bytes);
+          const int kinstr = (kc == p.kchunks - 1) ? p.kinstr_last : kKC / 16;
           for (int t = 0; t < p.taps; ++t) {
             const int slot = p.b_resident ? kc * p.taps + t : b_stage;
             if (!p.b_resident || !b_loaded) {
-              if (!mbar_wait_t(&b_full[slot], p.b_resident ? 0u : b_phase, p.err, 106, w_b)) { ok = false; break; }
+              ok = __all_sync(0xffffffffu, mbar_wait_t(&b_full[slot], p.b_resident ? 0u : b_phase, p.err, 106, w_b));
+              if (!ok) break;
             }
             tc_fence_after();
-            const uint32_t sb = smem_u32(smem_b + (size_t)slot * p.b_bytes);
-            const uint64_t db = make_desc_sw128(sb, 1);
-            for (int j = 0; j < p.mt; ++j) {
-              const uint32_t sa_t = sa + (uint32_t)p.tap_off[t] + (uint32_t)(j * kSubBytes);
-              const uint64_t da = make_desc_sw128(sa_t, p.desc_mode);
-#pragma unroll
-              for (int k = 0; k < kKC / 16; ++k) {
-                // advance 16 elements (32 bytes) along K inside the swizzle atom
-                umma_f16(d_tmem + (uint32_t)(j * p.sub_cols), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
-                         (kc | t | k) != 0 ? 1u : 0u);
+            if (elect_one()) {
+              const uint64_t db = make_desc_sw128(smem_u32(smem_b + (size_t)slot * p.b_bytes), 1);
+              const uint32_t first = (kc | t) != 0 ? 1u : 0u;
+              for (int j = 0; j < p.mt; ++j) {
+                const uint64_t da = make_desc_sw128(sa + (uint32_t)p.tap_off[t] + (uint32_t)(j * kSubBytes), p.desc_mode);
+                const uint32_t d = d_tmem + (uint32_t)(j * p.sub_cols);
+                // advance 16 elements (32 bytes) along K inside the swizzle atom; all-zero K slices are skipped
+                umma_f16(d, da, db, idesc, first);
+                if (kinstr > 1) umma_f16(d, da + 2, db + 2, idesc, 1u);
+                if (kinstr > 2) umma_f16(d, da + 4, db + 4, idesc, 1u);
+                if (kinstr > 3) umma_f16(d, da + 6, db + 6, idesc, 1u);
               }
+              if (!p.b_resident) umma_commit(&b_empty[b_stage]);
             }
+            __syncwarp();
             if (!p.b_resident) {
-              umma_commit(&b_empty[b_stage]);
               if (++b_stage == p.b_stages) { b_stage = 0; b_phase ^= 1; }
             }
           }
           if (!ok) break;
-          umma_commit(&a_empty[a_stage]);
+          if (elect_one()) umma_commit(&a_empty[a_stage]);
+          __syncwarp();
           if (++a_stage == p.a_stages) { a_stage = 0; a_phase ^= 1; }
         }
         if (!ok) break;
         b_loaded = true;
-        umma_commit(&tfull_bar[acc]);
+        if (elect_one()) umma_commit(&tfull_bar[acc]);
+        __syncwarp();
         if (p.acc_bufs == 2) {
           acc ^= 1;
           if (acc == 0) acc_phase ^= 1;
@@ -410,7 +457,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           acc_phase ^= 1;
         }
       }
-      if (p.dbg && blockIdx.x == 0) {
+      if (p.dbg && blockIdx.x == 0 && lane == 0) {
         p.dbg[6] = (unsigned long long)w_a;
         p.dbg[7] = (unsigned long long)w_b;
         p.dbg[8] = (unsigned long long)w_t;
@@ -430,10 +477,16 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const float* v_slope = vec + 2 * p.vec_n;
     const float* v_scale2 = vec + 3 * p.vec_n;
     const float* v_bias2 = vec + 4 * p.vec_n;
+    // this warp's 2 KB transpose buffer: 32 rows x 64 B (32 fp16 channels), 16-byte pieces XOR-swizzled by
+    // (row >> 1) & 3 so that both the row-wise writes and the 4-lanes-per-row read-back are conflict-free
+    uint8_t* stg = stage_buf + (warp - kEpiWarp0) * 2048;
+    const uint32_t stg_w = smem_u32(stg) + (uint32_t)(lane * 64);          // my row, as writer
+    const int w_sw = (lane >> 1) & 3;
+    const int rb_piece = lane & 3;                                          // as reader: piece rb_piece of row i*8 + lane/4
     int acc = 0;
     uint32_t acc_phase = 0;
     bool ok = true;
-    long long w_full = 0, t_epi = 0;
+    long long w_full = 0, t_epi = 0, t_ld = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int mt_idx = tile / p.n_tiles, nt = tile - mt_idx * p.n_tiles;
       const int n0 = nt * p.n_tile;
@@ -441,7 +494,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       RowInfo ri = row_info(p, row0);
       // residual prefetch for sub-tile 0 (independent of the accumulator): 4 chunks x 32 channels
       uint4 R[4][4];
-      if (p.residual) {
+      if (kRes) {
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const int ch = n0 + col_lo + c * 32;
@@ -463,66 +516,87 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         rn.valid = false;
         rn.orow = 0;
         if (j + 1 < p.mt) rn = row_info(p, row0 + (long long)(j + 1) * kBlockM);
+        // rows this lane writes back after the transpose: i*8 + lane/4, i = 0..3
+        long long wrow[4];
+        bool wvalid[4];
+        if (kOutMode == 0) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int src = i * 8 + (lane >> 2);
+            wrow[i] = __shfl_sync(0xffffffffu, ri.orow, src);
+            wvalid[i] = __shfl_sync(0xffffffffu, ri.valid ? 1 : 0, src) != 0;
+          }
+        }
         const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256 + j * p.sub_cols);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const int col = col_lo + c * 32;
           if (col >= col_hi) break;
           uint32_t v[32];
-          __syncwarp();   // lanes diverge on `valid` below; tcgen05.ld is .sync.aligned
+          __syncwarp();   // tcgen05.ld is .sync.aligned; also orders the previous read-back before this chunk's staging writes
+          const long long tl0 = clock64();
           tmem_ld32(t_row + col, v);
+          t_ld += clock64() - tl0;
           const int ch = n0 + col;
-          if (ri.valid) {
-            float y[32];
+          float y[32];
 #pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              const float4 s4 = *(const float4*)(v_scale + ch + g * 4);
-              const float4 b4 = *(const float4*)(v_bias + ch + g * 4);
-              y[g * 4 + 0] = fmaf(__uint_as_float(v[g * 4 + 0]), s4.x, b4.x);
-              y[g * 4 + 1] = fmaf(__uint_as_float(v[g * 4 + 1]), s4.y, b4.y);
-              y[g * 4 + 2] = fmaf(__uint_as_float(v[g * 4 + 2]), s4.z, b4.z);
-              y[g * 4 + 3] = fmaf(__uint_as_float(v[g * 4 + 3]), s4.w, b4.w);
-            }
-            if (p.out_f32) {
+          for (int g = 0; g < 8; ++g) {
+            const float4 s4 = *(const float4*)(v_scale + ch + g * 4);
+            const float4 b4 = *(const float4*)(v_bias + ch + g * 4);
+            y[g * 4 + 0] = fmaf(__uint_as_float(v[g * 4 + 0]), s4.x, b4.x);
+            y[g * 4 + 1] = fmaf(__uint_as_float(v[g * 4 + 1]), s4.y, b4.y);
+            y[g * 4 + 2] = fmaf(__uint_as_float(v[g * 4 + 2]), s4.z, b4.z);
+            y[g * 4 + 3] = fmaf(__uint_as_float(v[g * 4 + 3]), s4.w, b4.w);
+          }
+          if (kOutMode == 2) {
+            if (ri.valid) {
               float* o = p.out_f32 + ri.orow * p.out_f32_stride + ch;
 #pragma unroll
               for (int g = 0; g < 8; ++g)
                 if (ch + g * 4 < p.out_f32_cols) *(float4*)(o + g * 4) = make_float4(y[g * 4], y[g * 4 + 1], y[g * 4 + 2], y[g * 4 + 3]);
-            } else {
-              if (p.residual) {
+            }
+          } else {
+            if (kRes) {
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                  float f[8];
-                  unpack_h8(R[c][g], f);
+              for (int g = 0; g < 4; ++g) {
+                float f[8];
+                unpack_h8(R[c][g], f);
 #pragma unroll
-                  for (int e = 0; e < 8; ++e) y[g * 8 + e] += f[e];
-                }
+                for (int e = 0; e < 8; ++e) y[g * 8 + e] += f[e];
               }
-              if (p.act == PCB_ACT_RELU) {
+            }
+            if (kAct == PCB_ACT_RELU) {
 #pragma unroll
-                for (int e = 0; e < 32; ++e) y[e] = fmaxf(y[e], 0.f);
-              } else if (p.act == PCB_ACT_PRELU) {
+              for (int e = 0; e < 32; ++e) y[e] = fmaxf(y[e], 0.f);
+            } else if (kAct == PCB_ACT_PRELU) {
 #pragma unroll
-                for (int g = 0; g < 8; ++g) {
-                  const float4 a4 = *(const float4*)(v_slope + ch + g * 4);
-                  y[g * 4 + 0] = y[g * 4 + 0] >= 0.f ? y[g * 4 + 0] : y[g * 4 + 0] * a4.x;
-                  y[g * 4 + 1] = y[g * 4 + 1] >= 0.f ? y[g * 4 + 1] : y[g * 4 + 1] * a4.y;
-                  y[g * 4 + 2] = y[g * 4 + 2] >= 0.f ? y[g * 4 + 2] : y[g * 4 + 2] * a4.z;
-                  y[g * 4 + 3] = y[g * 4 + 3] >= 0.f ? y[g * 4 + 3] : y[g * 4 + 3] * a4.w;
-                }
+              for (int g = 0; g < 8; ++g) {
+                const float4 a4 = *(const float4*)(v_slope + ch + g * 4);
+                y[g * 4 + 0] = y[g * 4 + 0] >= 0.f ? y[g * 4 + 0] : y[g * 4 + 0] * a4.x;
+                y[g * 4 + 1] = y[g * 4 + 1] >= 0.f ? y[g * 4 + 1] : y[g * 4 + 1] * a4.y;
+                y[g * 4 + 2] = y[g * 4 + 2] >= 0.f ? y[g * 4 + 2] : y[g * 4 + 2] * a4.z;
+                y[g * 4 + 3] = y[g * 4 + 3] >= 0.f ? y[g * 4 + 3] : y[g * 4 + 3] * a4.w;
               }
-              if (p.out_s32) {
+            }
+            if (kOutMode == 1) {
+              if (ri.valid) {
                 float* o = p.out_s32 + ri.orow * p.out_cp + ch;
 #pragma unroll
                 for (int g = 0; g < 8; ++g)
                   if (ch + g * 4 < p.out_c_store) *(float4*)(o + g * 4) = make_float4(y[g * 4], y[g * 4 + 1], y[g * 4 + 2], y[g * 4 + 3]);
-              } else {
-                __half* o = p.out + ri.orow * p.out_cp + ch;
-#pragma unroll
-                for (int g = 0; g < 4; ++g)
-                  if (ch + g * 8 < p.out_c_store) *(uint4*)(o + g * 8) = pack_h8(y + g * 8);
               }
-              if (p.out2) {
+            } else {
+              // transpose through shared memory so that 4 lanes write one row's 64 contiguous bytes (full sectors)
+#pragma unroll
+              for (int g = 0; g < 4; ++g) st_shared_v4(stg_w + (uint32_t)(((g ^ w_sw) & 3) * 16), pack_h8(y + g * 8));
+              __syncwarp();
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int r = i * 8 + (lane >> 2);
+                const uint4 o4 = ld_shared_v4(smem_u32(stg) + (uint32_t)(r * 64 + ((rb_piece ^ (r >> 1)) & 3) * 16));
+                if (wvalid[i] && ch + rb_piece * 8 < p.out_c_store) *(uint4*)(p.out + wrow[i] * p.out_cp + ch + rb_piece * 8) = o4;
+              }
+              if (kOut2) {
 #pragma unroll
                 for (int g = 0; g < 8; ++g) {
                   const float4 s4 = *(const float4*)(v_scale2 + ch + g * 4);
@@ -532,15 +606,21 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                   y[g * 4 + 2] = fmaf(y[g * 4 + 2], s4.z, b4.z);
                   y[g * 4 + 3] = fmaf(y[g * 4 + 3], s4.w, b4.w);
                 }
-                __half* o2 = p.out2 + ri.orow * p.out2_cp + ch;
+                __syncwarp();
 #pragma unroll
-                for (int g = 0; g < 4; ++g)
-                  if (ch + g * 8 < p.out_c_store) *(uint4*)(o2 + g * 8) = pack_h8(y + g * 8);
+                for (int g = 0; g < 4; ++g) st_shared_v4(stg_w + (uint32_t)(((g ^ w_sw) & 3) * 16), pack_h8(y + g * 8));
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const int r = i * 8 + (lane >> 2);
+                  const uint4 o4 = ld_shared_v4(smem_u32(stg) + (uint32_t)(r * 64 + ((rb_piece ^ (r >> 1)) & 3) * 16));
+                  if (wvalid[i] && ch + rb_piece * 8 < p.out_c_store) *(uint4*)(p.out2 + wrow[i] * p.out2_cp + ch + rb_piece * 8) = o4;
+                }
               }
             }
           }
           // refill this chunk's residual registers with the next sub-tile's row
-          if (p.residual && j + 1 < p.mt) {
+          if (kRes && j + 1 < p.mt) {
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               R[c][g] = make_uint4(0, 0, 0, 0);
@@ -565,6 +645,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (p.dbg && blockIdx.x == 0 && warp == kEpiWarp0 && lane == 0) {
       p.dbg[9] = (unsigned long long)w_full;
       p.dbg[10] = (unsigned long long)t_epi;
+      p.dbg[11] = (unsigned long long)t_ld;
     }
   }
 
@@ -670,7 +751,11 @@ int pcb_conv_tc2(pcb_ctx* c, const ConvArgs& a) {
   p.wp = in.dense ? 0 : in.w + 2;
   p.taps = w.taps;
   p.cin_w = w.cin_w;
-  p.kchunks = w.cin_w / kKC;
+  {
+    const int cin_eff = in.dense ? w.cin : (w.taps == 1 && w.cin == 3) ? 27 : w.cin;   // stem: 27 patch channels
+    p.kchunks = (cin_eff + kKC - 1) / kKC;
+    p.kinstr_last = (cin_eff - (p.kchunks - 1) * kKC + 15) / 16;
+  }
   p.n_tile = w.n_tile;
   p.n_tiles = w.npad / w.n_tile;
   p.vec_n = pcb_round_up(w.npad, 32);
@@ -711,7 +796,7 @@ int pcb_conv_tc2(pcb_ctx* c, const ConvArgs& a) {
   p.sub_cols = pcb_round_up(w.n_tile, 32);
   p.b_bytes = w.n_tile * kKC * 2;
   const int ksteps = p.taps * p.kchunks;
-  const int fixed = 5 * p.vec_n * 4 + (2 * kMaxA + 2 * kMaxB + 4) * 8 + 16 + 1024;
+  const int fixed = 5 * p.vec_n * 4 + kEpiWarps * 2048 + (2 * kMaxA + 2 * kMaxB + 4) * 8 + 16 + 1024;
 
   // choose MT (1 or 2): fewer L2 bytes per FLOP at MT=2, but half as many tiles to spread over the SMs
   const int force_mt = env_int("PCB_CONV_MT", 0);
@@ -735,6 +820,7 @@ int pcb_conv_tc2(pcb_ctx* c, const ConvArgs& a) {
   }
   if (!best_mt) return pcb_conv_tc(c, a);   // no shared-memory plan (very wide maps): baseline kernel
   plan_a(p, best_mt, &a2_rows);
+  if (env_int("PCB_TAP_ALIGN", 0)) for (int t = 0; t < 9; ++t) p.tap_off[t] &= ~1023;   // timing experiment only (wrong sums)
   p.m_tiles = (int)(((long long)p.rows + p.mt * kBlockM - 1) / (p.mt * kBlockM));
   p.acc_bufs = (p.mt * p.sub_cols <= 256) ? 2 : 1;
   const int room = kSmemBudget - fixed;
@@ -765,11 +851,6 @@ int pcb_conv_tc2(pcb_ctx* c, const ConvArgs& a) {
   if (!make_map_2d(&tmB, w.w, (uint64_t)w.npad, (uint64_t)w.taps * w.cin_w, (uint64_t)w.taps * w.cin_w, (uint32_t)w.n_tile))
     return pcb_fail(c, PCB_ERR_CUDA, "cuTensorMapEncodeTiled(B) failed");
 
-  static bool attr_set = false;
-  if (!attr_set) {
-    PCB_CUDA(c, cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
   const int total = p.m_tiles * p.n_tiles;
   const int grid = total < c->num_sms ? total : c->num_sms;
   // algorithmic FLOPs of this layer: 2 * output pixels * cout * cin * taps (real, unpadded extents)
@@ -789,7 +870,42 @@ int pcb_conv_tc2(pcb_ctx* c, const ConvArgs& a) {
   }
   {
     PcbConvTimer timer(c, 2.0 * out_px * (double)w.cout * k_real, desc);
-    conv_tc2_kernel<<<grid, kThreads, smem, c->stream>>>(tmA, tmA2, tmB, p);
+    const int mode = p.out_f32 ? 2 : (p.out_s32 ? 1 : 0);
+    if (mode != 0 && (p.residual || p.out2)) return pcb_fail(c, PCB_ERR_ARG, "conv_tc2: fp32 outputs take no residual / second output");
+    const int key = mode == 0 ? (p.act * 4 + (p.residual ? 2 : 0) + (p.out2 ? 1 : 0)) : (100 + mode * 4 + p.act);
+    cudaError_t le = cudaErrorInvalidValue;
+#define PCB_TC2_CASE(KEY, ACT, RES, OUT2, MODE)                                                                         \
+  case KEY: {                                                                                                          \
+    static bool attr = false;                                                                                          \
+    if (!attr) {                                                                                                       \
+      cudaFuncSetAttribute(conv_tc2_kernel<ACT, RES, OUT2, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
+      attr = true;                                                                                                     \
+    }                                                                                                                  \
+    conv_tc2_kernel<ACT, RES, OUT2, MODE><<<grid, kThreads, smem, c->stream>>>(tmA, tmA2, tmB, p);                     \
+    le = cudaSuccess;                                                                                                  \
+    break;                                                                                                             \
+  }
+    switch (key) {
+      PCB_TC2_CASE(0, 0, false, false, 0)
+      PCB_TC2_CASE(1, 0, false, true, 0)
+      PCB_TC2_CASE(2, 0, true, false, 0)
+      PCB_TC2_CASE(3, 0, true, true, 0)
+      PCB_TC2_CASE(4, 1, false, false, 0)
+      PCB_TC2_CASE(5, 1, false, true, 0)
+      PCB_TC2_CASE(6, 1, true, false, 0)
+      PCB_TC2_CASE(7, 1, true, true, 0)
+      PCB_TC2_CASE(8, 2, false, false, 0)
+      PCB_TC2_CASE(9, 2, false, true, 0)
+      PCB_TC2_CASE(10, 2, true, false, 0)
+      PCB_TC2_CASE(11, 2, true, true, 0)
+      PCB_TC2_CASE(104, 0, false, false, 1)
+      PCB_TC2_CASE(105, 1, false, false, 1)
+      PCB_TC2_CASE(106, 2, false, false, 1)
+      PCB_TC2_CASE(108, 0, false, false, 2)
+      default: break;
+    }
+#undef PCB_TC2_CASE
+    if (le != cudaSuccess) return pcb_fail(c, PCB_ERR_ARG, "conv_tc2: unsupported epilogue combination");
   }
   PCB_LAUNCH_CHECK(c, "conv_tc2_kernel");
   if (p.dbg) {
@@ -799,8 +915,8 @@ int pcb_conv_tc2(pcb_ctx* c, const ConvArgs& a) {
     cudaMemcpyAsync(h, dbg_dev, sizeof h, cudaMemcpyDeviceToHost, c->stream);
     cudaStreamSynchronize(c->stream);
     const double cyc = (double)(h[2] - h[0]), ns = (double)(h[3] - h[1]);
-    fprintf(stderr, "CONVDBG %s | mhz=%.0f cyc=%.0f prodA_wait=%.2f prodB_wait=%.2f mma_waitA=%.2f mma_waitB=%.2f mma_waitT=%.2f epi_wait=%.2f epi_busy=%.2f\n",
-            desc, ns > 0 ? cyc / ns * 1e3 : 0.0, cyc, h[4] / cyc, h[5] / cyc, h[6] / cyc, h[7] / cyc, h[8] / cyc, h[9] / cyc, h[10] / cyc);
+    fprintf(stderr, "CONVDBG %s | mhz=%.0f cyc=%.0f prodA_wait=%.2f prodB_wait=%.2f mma_waitA=%.2f mma_waitB=%.2f mma_waitT=%.2f epi_wait=%.2f epi_busy=%.2f epi_ldtm=%.2f\n",
+            desc, ns > 0 ? cyc / ns * 1e3 : 0.0, cyc, h[4] / cyc, h[5] / cyc, h[6] / cyc, h[7] / cyc, h[8] / cyc, h[9] / cyc, h[10] / cyc, h[11] / cyc);
   }
   return PCB_OK;
 }

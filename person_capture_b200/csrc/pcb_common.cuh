@@ -46,6 +46,7 @@ struct ConvWeights {
   int cin = 0, cout = 0, k = 0, taps = 0;
   int cin_w = 0;   // per-tap K extent in the packed weight (multiple of 64)
   int npad = 0;    // rows in the packed weight (multiple of n_tile)
+  int rows_alloc = 0;  // rows actually allocated (npad rounded up to 128, zero filled)
   int n_tile = 0;  // UMMA N used for this layer
 };
 
@@ -71,7 +72,7 @@ struct pcb_ctx {
   std::string last_error;
   int* d_err = nullptr;       // device error word (watchdog / overflow)
   int* h_err = nullptr;       // pinned mirror
-  int conv_impl = 0;          // 0 = tcgen05 (product), 1 = CUDA-core validation kernel, 2 = tcgen05 baseline (one TMA load per tap)
+  int conv_impl = 0;          // 0 = tcgen05 product (tc2), 1 = CUDA-core validation, 2 = tcgen05 baseline (tc), 3 = transposed experiment (tc3)
   long long launches = 0;     // kernels launched since the last pcb_reset_counters
   std::vector<void*> allocs;  // everything cudaMalloc'ed through the context
   struct Model* models[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -113,7 +114,8 @@ int pcb_fail(pcb_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess
 void* pcb_dev_alloc(pcb_ctx* c, size_t bytes, bool zero);
 
 // conv_tc.cu / conv_simple.cu
-int pcb_conv_tc2(pcb_ctx* c, const ConvArgs& a);   // product kernel (operand reuse in shared memory)
+int pcb_conv_tc2(pcb_ctx* c, const ConvArgs& a);   // product kernel: pixels on UMMA M, couts on N, operand reuse in shared memory
+int pcb_conv_tc3(pcb_ctx* c, const ConvArgs& a);   // experiment (impl 3): couts on M, 256 pixels on N; faster MMA phase, slower epilogue
 int pcb_conv_tc(pcb_ctx* c, const ConvArgs& a);    // first formulation, kept as the A/B baseline (impl 2)
 int pcb_conv_simple(pcb_ctx* c, const ConvArgs& a);
 // ops.cu
