@@ -34,14 +34,22 @@ def make_sample(rng: np.random.Generator, size: int, tex_cache: dict):
     if zoom > 1:
         import cv2
         img = cv2.resize(img, (size, size), interpolation=cv2.INTER_AREA)
+    # top-left anchored letterbox (InsightFace SCRFD.detect): a 16:9 frame fills only the top 56% of the square and
+    # the rest is zero pad; half of the samples get such a pad so the heads learn that the content/pad edge is not a face
+    hc, wc = size, size
+    if rng.random() < 0.5:
+        if rng.random() < 0.8:
+            hc = int(size * rng.uniform(0.4, 0.95))
+        else:
+            wc = int(size * rng.uniform(0.4, 0.95))
     n = int(rng.choice([0, 1, 1, 1, 2, 2, 3, 5]))
     boxes, kpss = [], []
     placed = []
     for _ in range(n):
-        side = float(np.exp(rng.uniform(np.log(12.0), np.log(size * 0.95))))
+        side = float(np.exp(rng.uniform(np.log(12.0), np.log(min(hc, wc) * 0.95))))
         for _try in range(6):
-            cx = float(rng.uniform(side * 0.35, size - side * 0.35))
-            cy = float(rng.uniform(side * 0.35, size - side * 0.35))
+            cx = float(rng.uniform(side * 0.35, wc - side * 0.35))
+            cy = float(rng.uniform(side * 0.35, hc - side * 0.35))
             if all(abs(cx - x) > (side + s) * 0.55 or abs(cy - y) > (side + s) * 0.55 for x, y, s in placed):
                 break
         else:
@@ -57,6 +65,8 @@ def make_sample(rng: np.random.Generator, size: int, tex_cache: dict):
     if rng.random() < 0.5:
         noise = rng.normal(0, rng.uniform(1, 6), img.shape)
         img = np.clip(img.astype(np.float32) + noise, 0, 255).astype(np.uint8)
+    img[hc:] = 0
+    img[:, wc:] = 0
     return img, np.array(boxes, np.float32).reshape(-1, 4), np.array(kpss, np.float32).reshape(-1, 5, 2)
 
 
