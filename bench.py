@@ -36,14 +36,19 @@ METRIC = "prescan_frames_per_sec"
 
 def make_cfg():
     from person_capture_b200.params import PrescanParams
+    # thresholds calibrated on the synthetic identities (seeded-random ArcFace weights put same-identity distances
+    # around 0.3-0.6, tests/test_gpu_e2e.py uses the same values): the clip then has active stretches, bank growth,
+    # flip-TTA while active and edge refinement, as a real pre-scan does
     return PrescanParams(face_model="scrfd_10g_bnkps", prescan_stride=1, prescan_max_width=960, prescan_decode_max_w=0,
-                         prescan_cache_mode="off")
+                         prescan_cache_mode="off", prescan_fd_enter=0.62, prescan_fd_exit=0.72, prescan_fd_add=0.50,
+                         face_quality_min=40.0)
 
 
 def make_pool(n: int, seed: int = 1002):
-    """`n` distinct synthetic 1080p frames (target identity visible in two stretches) + reference image."""
+    """`n` distinct synthetic 1080p frames + reference image.  SURVEY.md 8(d) C2: about one face per frame -- a distractor
+    identity in every frame, the target identity on top of it in two stretches (48 % of the frames)."""
     from person_capture_b200 import synth
-    clip = synth.ClipSpec(1920, 1080, n, seed=seed, target=1, others=(2, 3, 4))
+    clip = synth.ClipSpec(1920, 1080, n, seed=seed, target=1, others=(2, 3, 4), distractor_prob=1.0)
     frames = np.stack([clip.frame(i) for i in range(n)])
     return frames, synth.reference_image(1, 512, seed=seed)
 
@@ -58,7 +63,7 @@ class PooledDeviceClip:
     def host(self, i):
         return self.pool[i % self.pool.shape[0]].cpu().numpy()
 
-    def device_batch(self, eng, idxs):
+    def device_batch(self, eng, idxs, stream=None):
         import torch
         P = self.pool.shape[0]
         lo = idxs[0] % P
@@ -80,7 +85,9 @@ class PooledHostClip:
     def host(self, i):
         return self.pool[i % self.pool.shape[0]].numpy()
 
-    def device_batch(self, eng, idxs):
+    host_resident = True
+
+    def device_batch(self, eng, idxs, stream=None):
         import torch
         P = self.pool.shape[0]
         lo = idxs[0] % P
@@ -89,7 +96,7 @@ class PooledHostClip:
         else:
             src = self.pool[torch.as_tensor([i % P for i in idxs])].pin_memory()
         self.h2d_bytes += src.numel()
-        with torch.cuda.stream(eng.stream):
+        with torch.cuda.stream(stream if stream is not None else eng.stream):
             return src.to(eng.tdev, non_blocking=True)
 
 
@@ -223,12 +230,14 @@ def main():
     clip_dev = PooledDeviceClip(pool_dev, total)
     clip_host = PooledHostClip(pool_pin, total)
 
-    faces_seen = {"n": 0}
+    faces_seen = {"n": 0, "passes": 0}
 
     def step(clip):
-        log = []
-        spans, _ = PS.prescan_batched(clip, 24, face, bank, cfg, batch=args.batch, log=log)
-        faces_seen["n"] = sum(r["nfaces"] for r in log)
+        stats = {}
+        spans, _ = PS.prescan_batched(clip, 24, face, bank, cfg, batch=args.batch, stats=stats)
+        faces_seen["n"] = stats.get("faces", 0)               # faces aligned + embedded by THIS rank in the step
+        faces_seen["passes"] = stats.get("arcface_passes", 0)  # ArcFace image passes (e(x), plus e(flip x) where the span logic needs it)
+        faces_seen["spans"] = [list(map(int, sp)) for sp in spans]
         return spans
 
     def timed(clip, steps, profile=False):
@@ -301,16 +310,18 @@ def main():
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": args.frames_per_step, "batch": args.batch,
                    "pool_frames": args.pool, "l2_policy": "inputs larger than L2 (pool 398 MB of 1080p frames, cycled)",
-                   "detector_input": 512, "faces_per_step": faces_seen["n"],
+                   "detector_input": 512, "kept_spans": faces_seen.get("spans"), "faces_per_step_per_gpu": faces_seen["n"], "arcface_passes_per_step_per_gpu": faces_seen["passes"],
+                   "flip_tta": "e(flip x) only for faces evaluated while a span is active (as the reference); N>1 ranks embed both variants before the all-gather",
                    "weights": "SCRFD trained on synthetic faces; ArcFace seeded random + calibrated affine (no checkpoints offline)",
                    "scrfd_gflop_per_frame": 2e-9 * graphs.graph_macs(g_s, 256, 256),
                    "arcface_gflop_per_face_pass": 2e-9 * graphs.graph_macs(g_a, 112, 112)},
-        "faces_embedded_per_sec": faces_seen["n"] * 2 * args.steps / (ms / 1000.0) / max(1, world) * world,
+        "faces_embedded_per_sec": faces_seen["n"] * world * args.steps / (ms / 1000.0),
+        "arcface_image_passes_per_sec": faces_seen["passes"] * world * args.steps / (ms / 1000.0),
         "gpu_launches": launches,
         "wall_ms_per_step": 1000.0 * wall / args.steps,
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(h2d),
-                "d2h_bytes_per_step": int(faces_seen["n"] * 2 * 2 * 2048 + args.frames_per_step * 64)},
+                "d2h_bytes_per_step": int(faces_seen["passes"] * 2048 + faces_seen["n"] * 64 + args.frames_per_step * 64)},
         "roofline": {"kernel": "conv_tc_kernel", "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": achieved / peak_tf if peak_tf else None, "traffic": None, "peak_source": peak_src,
                      "conv_launches": conv_n, "conv_ms_per_step": conv_ms / args.steps,

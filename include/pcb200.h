@@ -160,7 +160,8 @@ int pcb_align(pcb_ctx* ctx, const pcb_align_args* a);
 
 /* ---- ArcFace (replaces _arcface_preprocess + arc_sess.run, face_embedder.py:1281-1288, 1369) -- */
 /* chips uint8 [f][112][112][3] BGR -> raw embeddings e(x) [f][512] and, if emb_flip_dev != NULL,
- * e(flip x) [f][512] (cv2.flip(chip, 1), face_embedder.py:1297-1298). */
+ * e(flip x) [f][512] (cv2.flip(chip, 1), face_embedder.py:1297-1298).  emb_dev may be NULL when only
+ * e(flip x) is wanted (the reference computes the flip pass only while a span is active, :1295). */
 int pcb_embed(pcb_ctx* ctx, const uint8_t* chips_dev, int f, float* emb_dev, float* emb_flip_dev);
 
 /* ---- K5: bank distance (replaces face_embedder.py:1383-1389 + Processor._fd_min,

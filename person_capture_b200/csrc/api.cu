@@ -470,27 +470,29 @@ extern "C" int pcb_detect(pcb_ctx* c, const pcb_detect_args* a) {
 }
 
 extern "C" int pcb_embed(pcb_ctx* c, const uint8_t* chips_dev, int f, float* emb_dev, float* emb_flip_dev) {
-  if (f < 0 || (f > 0 && (!chips_dev || !emb_dev))) return pcb_fail(c, PCB_ERR_ARG, "embed: bad arguments");
+  if (f < 0 || (f > 0 && (!chips_dev || (!emb_dev && !emb_flip_dev)))) return pcb_fail(c, PCB_ERR_ARG, "embed: bad arguments");
   Model* m = c->models[PCB_MODEL_ARCFACE];
   if (!m) return pcb_fail(c, PCB_ERR_STATE, "embed: no ArcFace graph loaded");
-  // faces per graph run (x2 images with flip).  222 faces = 444 images makes the 14x14 / 28x28 / 7x7 stages
-  // 3.0 / 10.5 / 1.9 waves of 256-row tiles over 148 SMs (>= 95% wave efficiency) and bounds activation memory
-  // at ~11 GB for iResNet-100.
+  // 0: e(x) only, 1: e(x) and e(flip x), 2: e(flip x) only
+  const int mode = emb_dev ? (emb_flip_dev ? 1 : 0) : 2;
+  // faces per graph run.  444 images make the 14x14 / 28x28 / 7x7 stages 3.0 / 10.5 / 1.9 waves of 256-row tiles over
+  // 148 SMs (>= 95% wave efficiency) and bound activation memory at ~11 GB for iResNet-100.
   static const int chunk_env = getenv("PCB_EMBED_CHUNK") ? atoi(getenv("PCB_EMBED_CHUNK")) : 0;
-  const int chunk = chunk_env > 0 ? chunk_env : (emb_flip_dev ? 222 : 444);
+  const int chunk = chunk_env > 0 ? chunk_env : (mode == 1 ? 222 : 444);
   for (int f0 = 0; f0 < f; f0 += chunk) {
     const int fn = f - f0 < chunk ? f - f0 : chunk;
-    const int imgs = emb_flip_dev ? 2 * fn : fn;
+    const int imgs = mode == 1 ? 2 * fn : fn;
     Model::Run* r = nullptr;
     int rc = model_prepare(c, m, imgs, PCB_CHIP, PCB_CHIP, &r);
     if (rc) return rc;
-    rc = pcb_chip_patch_impl(c, chips_dev + (size_t)f0 * PCB_CHIP * PCB_CHIP * 3, fn, emb_flip_dev ? 1 : 0, r->t[0].data);
+    rc = pcb_chip_patch_impl(c, chips_dev + (size_t)f0 * PCB_CHIP * PCB_CHIP * 3, fn, mode, r->t[0].data);
     if (rc) return rc;
     rc = model_run(c, m, r);
     if (rc) return rc;
-    PCB_CUDA(c, cudaMemcpyAsync(emb_dev + (size_t)f0 * PCB_FEAT_DIM, r->fc_out, (size_t)fn * PCB_FEAT_DIM * sizeof(float),
+    float* first = mode == 2 ? emb_flip_dev : emb_dev;
+    PCB_CUDA(c, cudaMemcpyAsync(first + (size_t)f0 * PCB_FEAT_DIM, r->fc_out, (size_t)fn * PCB_FEAT_DIM * sizeof(float),
                                 cudaMemcpyDeviceToDevice, c->stream));
-    if (emb_flip_dev)
+    if (mode == 1)
       PCB_CUDA(c, cudaMemcpyAsync(emb_flip_dev + (size_t)f0 * PCB_FEAT_DIM, r->fc_out + (size_t)fn * PCB_FEAT_DIM,
                                   (size_t)fn * PCB_FEAT_DIM * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
   }

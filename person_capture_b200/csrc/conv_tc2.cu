@@ -814,8 +814,10 @@ int pcb_conv_tc2(pcb_ctx* c, const ConvArgs& a) {
     const long long m_tiles = ((long long)p.rows + mt * kBlockM - 1) / (mt * kBlockM);
     const long long tiles = m_tiles * p.n_tiles;
     const long long waves = (tiles + c->num_sms - 1) / c->num_sms;
-    // relative time per tile: rows * (1 + L2 penalty); MT=2 moves ~0.6x the bytes per row
-    const double cost = (double)waves * mt * (mt == 1 ? 1.0 : 0.72);
+    // relative time per tile, measured on B200 (tools/profile_layers.py, PCB_CONV_MT): MT=2 shares each weight stage
+    // between two accumulators and is ~1.4x faster per row while TMEM can still be double-buffered (2*N <= 256);
+    // for N > 128 it would be single-buffered and the exposed epilogue costs more than the saved weight traffic
+    const double cost = (double)waves * mt * (mt == 1 ? 1.0 : (2 * p.sub_cols > 256 ? 1.05 : 0.72));
     if (!best_mt || cost < best_cost) { best_mt = mt; best_cost = cost; }
   }
   if (!best_mt) return pcb_conv_tc(c, a);   // no shared-memory plan (very wide maps): baseline kernel

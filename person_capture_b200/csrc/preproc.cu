@@ -149,16 +149,17 @@ __global__ void __launch_bounds__(256) letterbox_kernel(const LetterboxParams p)
 }
 
 // ------------------------------------------------------------------ ArcFace input
-// chips [f][112][112][3] BGR -> patch tensor [f(*2)][114][114][32]; images f..2f-1 are the flipped chips.
+// chips [f][112][112][3] BGR -> patch tensor [f(*2)][114][114][32].  with_flip: 0 = chips only, 1 = chips then (images
+// f..2f-1) their mirror images, 2 = mirror images only (flip-TTA computed lazily for faces that turn out to need it).
 __global__ void __launch_bounds__(256) chip_patch_kernel(const uint8_t* __restrict__ chips, __half* __restrict__ out, int f, int with_flip) {
-  const int total_imgs = with_flip ? 2 * f : f;
+  const int total_imgs = with_flip == 1 ? 2 * f : f;
   const long long total = (long long)total_imgs * PCB_CHIP * PCB_CHIP;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     const int x = (int)(idx % PCB_CHIP);
     const int y = (int)((idx / PCB_CHIP) % PCB_CHIP);
     const int img = (int)(idx / (PCB_CHIP * PCB_CHIP));
-    const bool flip = img >= f;
-    const uint8_t* chip = chips + (size_t)(flip ? img - f : img) * PCB_CHIP * PCB_CHIP * 3;
+    const bool flip = with_flip == 2 || img >= f;
+    const uint8_t* chip = chips + (size_t)(img >= f ? img - f : img) * PCB_CHIP * PCB_CHIP * 3;
     __align__(16) __half vals[32];
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky)
@@ -282,7 +283,7 @@ int pcb_letterbox_impl(pcb_ctx* c, const uint8_t* frames, int n, int h, int w, i
 }
 
 int pcb_chip_patch_impl(pcb_ctx* c, const uint8_t* chips, int f, int with_flip, __half* out) {
-  const long long total = (long long)(with_flip ? 2 * f : f) * PCB_CHIP * PCB_CHIP;
+  const long long total = (long long)(with_flip == 1 ? 2 * f : f) * PCB_CHIP * PCB_CHIP;
   chip_patch_kernel<<<grid_for(total, c), 256, 0, c->stream>>>(chips, out, f, with_flip);
   PCB_LAUNCH_CHECK(c, "chip_patch_kernel");
   return PCB_OK;

@@ -51,6 +51,7 @@ class Engine:
         self.tdev = torch.device("cuda", self.device)
         torch.cuda.set_device(self.device)
         self.stream = torch.cuda.Stream(device=self.tdev)
+        self.copy_stream = torch.cuda.Stream(device=self.tdev)   # H2D prefetch of the next frame batch (prescan.compute_superset)
         self.ctx = self.lib.pcb_create(self.device, C.c_void_p(self.stream.cuda_stream))
         if not self.ctx:
             raise L.PcbError("pcb_create failed (needs an sm_100 device)")
@@ -108,10 +109,10 @@ class Engine:
         with torch.cuda.stream(self.stream):
             return torch.zeros(shape, dtype=dtype, device=self.tdev)
 
-    def to_device(self, arr: np.ndarray) -> torch.Tensor:
-        """Host -> device on the engine's stream (pinned staging)."""
+    def to_device(self, arr: np.ndarray, stream=None) -> torch.Tensor:
+        """Host -> device on the engine's stream (or `stream`) through pinned staging."""
         t = torch.from_numpy(np.ascontiguousarray(arr))
-        with torch.cuda.stream(self.stream):
+        with torch.cuda.stream(stream if stream is not None else self.stream):
             return t.pin_memory().to(self.tdev, non_blocking=True)
 
     # ------------------------------------------------------------------ graphs
@@ -225,12 +226,14 @@ class Engine:
         return res
 
     # ------------------------------------------------------------------ ArcFace + K5
-    def embed(self, chips: torch.Tensor, f: int, flip: bool):
-        emb = self.empty((max(f, 1), L.FEAT_DIM), torch.float32)
+    def embed(self, chips: torch.Tensor, f: int, flip):
+        """flip False: e(x); True: e(x) and e(flip x); "only": e(flip x) alone (returned as the second element)."""
+        only = flip == "only"
+        emb = None if only else self.empty((max(f, 1), L.FEAT_DIM), torch.float32)
         emb_flip = self.empty((max(f, 1), L.FEAT_DIM), torch.float32) if flip else None
         if f > 0:
-            self._check(self.lib.pcb_embed(self.ctx, chips.data_ptr(), f, emb.data_ptr(),
-                                           emb_flip.data_ptr() if flip else None), "pcb_embed")
+            self._check(self.lib.pcb_embed(self.ctx, chips.data_ptr(), f, emb.data_ptr() if emb is not None else None,
+                                           emb_flip.data_ptr() if emb_flip is not None else None), "pcb_embed")
         return emb, emb_flip
 
     def set_bank(self, bank: Optional[np.ndarray]):

@@ -170,15 +170,19 @@ class FaceEmbedder:
 
     # ---- extract -----------------------------------------------------------------------
     def extract(self, bgr_img, *, imgsz: Optional[int] = None):
-        if bgr_img is None or bgr_img.size == 0:
+        if bgr_img is None:
             return []
-        if bgr_img.ndim != 3 or bgr_img.shape[2] != 3 or bgr_img.dtype != np.uint8:
+        on_device = isinstance(bgr_img, torch.Tensor)
+        if (bgr_img.numel() if on_device else bgr_img.size) == 0:
+            return []
+        if bgr_img.ndim != 3 or bgr_img.shape[2] != 3 or bgr_img.dtype != (torch.uint8 if on_device else np.uint8):
             raise ValueError("extract expects a uint8 BGR image [H, W, 3]")
         self._frame_idx += 1
         self.last_passes = []
         eng = self.engine
-        H0, W0 = bgr_img.shape[:2]
-        frame = eng.to_device(bgr_img[None])
+        H0, W0 = int(bgr_img.shape[0]), int(bgr_img.shape[1])
+        # frames already resident in HBM (north_star) are used in place; host arrays go through pinned staging
+        frame = bgr_img.contiguous()[None] if on_device else eng.to_device(bgr_img[None])
         dyn = self.upright_size(H0, W0, imgsz)
         heavy90, heavy180 = self.heavy_sizes(H0, W0, dyn)
         fast = self._fast_prescan

@@ -24,6 +24,15 @@ class PrescanParams:
     clip_face_backbone: str = "ViT-L-14"
     clip_face_pretrained: str = "laion2b_s32b_b82k"
     use_arcface: bool = True
+    # main-pass identity sites (gui_app.py:308, 419-421, 468, 471, 477, 522)
+    frame_stride: int = 2
+    lock_face_roi_enable: bool = True
+    lock_face_roi_pad: float = 1.25
+    lock_face_roi_max_misses: int = 8
+    face_fullframe_cadence: int = 12
+    face_visible_uses_quality: bool = True
+    learn_bank_runtime: bool = False
+    face_fullframe_when_missed: bool = True
     # rotation strategy of the main pass
     rot_adaptive: bool = True
     rot_every_n: int = 12

@@ -42,6 +42,7 @@ FD_NONE = 9.0
 # --------------------------------------------------------------------------------------------
 class HostClip:
     """Frames produced on the host (decode stand-in): get(i) -> uint8 BGR [H,W,3]."""
+    host_resident = True     # batches cross PCIe: compute_superset prefetches the next one on the engine's copy stream
 
     def __init__(self, get: Callable[[int], np.ndarray], total_frames: int):
         self._get = get
@@ -50,8 +51,8 @@ class HostClip:
     def host(self, i: int) -> np.ndarray:
         return self._get(i)
 
-    def device_batch(self, eng, idxs: Sequence[int]) -> torch.Tensor:
-        return eng.to_device(np.stack([self._get(i) for i in idxs]))
+    def device_batch(self, eng, idxs: Sequence[int], stream=None) -> torch.Tensor:
+        return eng.to_device(np.stack([self._get(i) for i in idxs]), stream=stream)
 
 
 class DeviceClip:
@@ -66,7 +67,7 @@ class DeviceClip:
     def host(self, i: int) -> np.ndarray:
         return self.frames[i - self.first].cpu().numpy()
 
-    def device_batch(self, eng, idxs: Sequence[int]) -> torch.Tensor:
+    def device_batch(self, eng, idxs: Sequence[int], stream=None) -> torch.Tensor:
         lo = idxs[0] - self.first
         if list(idxs) == list(range(idxs[0], idxs[0] + len(idxs))):
             return self.frames[lo:lo + len(idxs)]
@@ -359,13 +360,13 @@ def prescan_sequential(clip, fps: int, face: FaceEmbedder, ref_feat, cfg, log: O
     return spans, (out_bank if out_bank is not None else ref_feat)
 
 
-def _post_process(spans, clip, fps, face, bank: RefBank, ref_feat, cfg, trk: SpanTracker, wmax: int, batched: int = 0):
+def _post_process(spans, clip, fps, face, bank: RefBank, ref_feat, cfg, trk: SpanTracker, wmax: int, batched: int = 0, stats=None):
     gap = int(round(cfg.prescan_bridge_gap_sec * fps))
     do_bridge = getattr(cfg, "prescan_bridge_gap_sec", 0) > 0
     if spans and do_bridge:
         spans = bridge_spans(spans, gap)
     if batched:
-        spans = _refine_edges_batched(spans, clip, fps, face, bank, ref_feat, cfg, trk, batched)
+        spans = _refine_edges_batched(spans, clip, fps, face, bank, ref_feat, cfg, trk, batched, stats=stats)
     else:
         spans = _refine_edges(spans, clip, fps, face, bank, ref_feat, cfg, trk, wmax)
     if spans and do_bridge:
@@ -423,7 +424,7 @@ def _refine_edges(spans, clip, fps, face, bank: RefBank, ref_feat, cfg, trk: Spa
     return out
 
 
-def _refine_edges_batched(spans, clip, fps, face, bank: RefBank, ref_feat, cfg, trk: SpanTracker, batch: int):
+def _refine_edges_batched(spans, clip, fps, face, bank: RefBank, ref_feat, cfg, trk: SpanTracker, batch: int, stats=None):
     """Same result as _refine_edges, but every candidate probe frame of all spans goes through the
     batched superset (two GPU rounds: all left windows, then all right windows, whose start depends
     on the refined left edge).  Probes run in "full"/escalate mode: flip-TTA on, 90 then 270."""
@@ -443,6 +444,7 @@ def _refine_edges_batched(spans, clip, fps, face, bank: RefBank, ref_feat, cfg, 
         if not ids:
             return {}
         records, table = compute_superset(clip, ids, face, cfg, batch=batch)
+        _count_passes(stats, table)
         fdp, fdf = _LiveDistances(face.engine, table).get(use_bank)
         res = {}
         for j in ids:
@@ -502,43 +504,117 @@ class SampleRecord:
 
 
 class FaceTable:
-    """All faces of the superset: normalised features without / with flip-TTA (device + host)."""
+    """All faces of the superset: normalised features without / with flip-TTA (device + host).
 
-    def __init__(self):
+    Chips are queued as the frame batches are aligned and embedded in runs of EMBED_RUN images, so the ArcFace batch
+    (which sets the wave efficiency of the convolution tiles) does not depend on how many faces a frame batch holds.
+    Lazy mode (single process): only e(x) is computed up front, as the reference does while no span is active
+    (face_embedder.py:1295); chips and raw embeddings stay resident and `ensure_flip` computes e(flip x) for the rows the
+    replay actually evaluates in the active state (plus a look-ahead window, so the GPU sees large batches)."""
+    EMBED_RUN = 444       # images per ArcFace graph run (pcb_embed chunk; 222 faces when both variants are computed)
+
+    def __init__(self, lazy: bool = False):
+        self.lazy = lazy
         self.feat_plain: List[torch.Tensor] = []
         self.feat_flip: List[torch.Tensor] = []
+        self.raw: List[torch.Tensor] = []
+        self.chip_list: List[torch.Tensor] = []
+        self.pending: List[torch.Tensor] = []
+        self.pending_n = 0
         self.count = 0
+        self.flip_passes = 0          # faces that went through the flip pass (bench: ArcFace image passes / s)
 
-    def append(self, fp: torch.Tensor, ff: torch.Tensor, k: int) -> np.ndarray:
+    def queue(self, eng, chips: torch.Tensor, k: int) -> np.ndarray:
+        """Register k aligned chips; -> their row numbers.  Embedding happens in `flush`."""
         rows = np.arange(self.count, self.count + k)
-        self.feat_plain.append(fp[:k])
-        self.feat_flip.append(ff[:k])
+        with torch.cuda.stream(eng.stream):
+            self.pending.append(chips[:k].clone())
+        self.pending_n += k
         self.count += k
+        per_run = self.EMBED_RUN if self.lazy else self.EMBED_RUN // 2
+        if self.pending_n >= per_run:
+            self.flush(eng, keep_remainder=True)
         return rows
 
+    def flush(self, eng, keep_remainder: bool = False):
+        if not self.pending_n:
+            return
+        per_run = self.EMBED_RUN if self.lazy else self.EMBED_RUN // 2
+        with torch.cuda.stream(eng.stream):
+            chips = torch.cat(self.pending, 0) if len(self.pending) > 1 else self.pending[0]
+        n = chips.shape[0]
+        take = (n // per_run) * per_run if keep_remainder else n
+        if take == 0:
+            return
+        use = chips[:take].contiguous()
+        if self.lazy:
+            emb, _ = eng.embed(use, take, False)
+            fp, _, _ = eng.match(emb, None, None, take)           # normalise(e(x))
+            self.raw.append(emb[:take])
+            self.chip_list.append(use)
+        else:
+            emb, emb_flip = eng.embed(use, take, True)
+            fp, _, _ = eng.match(emb, None, None, take)           # normalise(e(x))
+            ff, _, _ = eng.match(emb, emb_flip, None, take)       # normalise(e(x) + e(flip x))
+            self.feat_flip.append(ff[:take])
+            self.flip_passes += take
+        self.feat_plain.append(fp[:take])
+        if take < n:
+            with torch.cuda.stream(eng.stream):
+                self.pending = [chips[take:].clone()]
+            self.pending_n = n - take
+        else:
+            self.pending, self.pending_n = [], 0
+
     def finalize(self, eng):
+        self.flush(eng)
         with torch.cuda.stream(eng.stream):
             if self.count:
                 self.plain = torch.cat(self.feat_plain, 0).contiguous()
-                self.flip = torch.cat(self.feat_flip, 0).contiguous()
+                if self.lazy:
+                    self.raw_all = torch.cat(self.raw, 0).contiguous()
+                    self.chips = torch.cat(self.chip_list, 0).contiguous()
+                    self.flip = torch.zeros_like(self.plain)
+                else:
+                    self.flip = torch.cat(self.feat_flip, 0).contiguous()
             else:
                 self.plain = eng.empty((1, L.FEAT_DIM), torch.float32)
                 self.flip = eng.empty((1, L.FEAT_DIM), torch.float32)
-        self.feat_plain, self.feat_flip = [], []
+        self.flip_ready = np.zeros(self.count, bool) if self.lazy else np.ones(self.count, bool)
+        self.flip_host = np.zeros((self.count, L.FEAT_DIM), np.float32) if self.lazy else None
+        self.feat_plain, self.feat_flip, self.raw, self.chip_list = [], [], [], []
+
+    def ensure_flip(self, eng, rows: np.ndarray) -> bool:
+        """Compute normalise(e(x) + e(flip x)) for the rows that do not have it yet.  -> True if anything was computed."""
+        if not self.lazy or not len(rows):
+            return False
+        need = np.unique(np.asarray(rows)[~self.flip_ready[rows]])
+        if not len(need):
+            return False
+        with torch.cuda.stream(eng.stream):
+            sel = torch.as_tensor(need, device=self.plain.device)
+            chips = self.chips.index_select(0, sel).contiguous()
+            raw = self.raw_all.index_select(0, sel).contiguous()
+        _, emb_flip = eng.embed(chips, len(need), "only")
+        ff, _, _ = eng.match(raw, emb_flip, None, len(need))
+        with torch.cuda.stream(eng.stream):
+            self.flip.index_copy_(0, sel, ff[:len(need)])
+        eng.sync()
+        self.flip_host[need] = ff[:len(need)].cpu().numpy()
+        self.flip_ready[need] = True
+        self.flip_passes += len(need)
+        return True
 
 
 def _collect_variant(eng, frames, det, idx_list, records, key, table: FaceTable, max_faces: int):
-    """Align + embed (+flip) every accumulated face of `det` (batch over idx_list)."""
+    """Align every accumulated face of `det` (batch over idx_list) and queue its chip for embedding."""
     al = eng.align(frames, det, max_faces=max_faces)
     eng.sync()
     total = int(al.face_total.cpu()[0])
     counts = al.face_count.cpu().numpy()
     if total == 0:
         return
-    emb, emb_flip = eng.embed(al.chips, total, True)
-    fp, _, _ = eng.match(emb, None, None, total)          # normalise(e(x))
-    ff, _, _ = eng.match(emb, emb_flip, None, total)      # normalise(e(x) + e(flip x))
-    rows = table.append(fp, ff, total)
+    rows = table.queue(eng, al.chips, total)
     boxes = al.face_box[:total].cpu().numpy()
     qual = al.quality[:total].cpu().numpy()
     off = 0
@@ -553,15 +629,35 @@ def _collect_variant(eng, frames, det, idx_list, records, key, table: FaceTable,
         off += k
 
 
-def compute_superset(clip, idxs: Sequence[int], face: FaceEmbedder, cfg, batch: int = 32, max_faces: int = 4096):
-    """GPU stage of the batched pre-scan for the samples `idxs` (fast pre-scan settings must be active)."""
+def compute_superset(clip, idxs: Sequence[int], face: FaceEmbedder, cfg, batch: int = 32, max_faces: int = 4096,
+                     lazy_flip: bool = False):
+    """GPU stage of the batched pre-scan for the samples `idxs` (fast pre-scan settings must be active).
+    lazy_flip: compute e(flip x) later, only for the faces the replay evaluates while a span is active."""
     eng = face.engine
     wmax = int(getattr(cfg, "prescan_max_width", 0))
     records: Dict[int, SampleRecord] = {}
-    table = FaceTable()
-    for b0 in range(0, len(idxs), batch):
-        chunk = list(idxs[b0:b0 + batch])
-        frames = clip.device_batch(eng, chunk)
+    table = FaceTable(lazy=lazy_flip)
+    chunks = [list(idxs[b0:b0 + batch]) for b0 in range(0, len(idxs), batch)]
+    prefetch = bool(getattr(clip, "host_resident", False))
+
+    def fetch(chunk):
+        """Issue the H2D copy of a batch on the copy stream; -> (frames, event that marks its completion)."""
+        with torch.cuda.stream(eng.copy_stream):
+            fr = clip.device_batch(eng, chunk, stream=eng.copy_stream)
+            ev = torch.cuda.Event()
+            ev.record(eng.copy_stream)
+        return fr, ev
+
+    pending = fetch(chunks[0]) if (prefetch and chunks) else None
+    for ci, chunk in enumerate(chunks):
+        if prefetch:
+            frames, ev = pending
+            eng.stream.wait_event(ev)
+            frames.record_stream(eng.stream)
+            # the next batch crosses PCIe while this one is on the SMs
+            pending = fetch(chunks[ci + 1]) if ci + 1 < len(chunks) else None
+        else:
+            frames = clip.device_batch(eng, chunk)
         n, h, w, _ = frames.shape
         if w > wmax:
             nh, nw = _downscaled_dims(h, w, wmax)
@@ -607,12 +703,15 @@ def compute_superset(clip, idxs: Sequence[int], face: FaceEmbedder, cfg, batch: 
 
 class _LiveDistances:
     """fd of every table row against the live bank, for both flip variants; recomputed on the GPU
-    (pcb_match) whenever the bank version changes."""
+    (pcb_match) whenever the bank version changes or new flip rows became available."""
 
     def __init__(self, eng, table: FaceTable):
         self.eng, self.table = eng, table
         self.version = None
         self.fd_plain = self.fd_flip = None
+
+    def invalidate(self):
+        self.version = None
 
     def get(self, bank: RefBank):
         if self.version != bank.version or self.fd_plain is None:
@@ -622,12 +721,23 @@ class _LiveDistances:
             else:
                 eng.set_bank(bank.array())
                 _, s0, _ = eng.match(t.plain, None, None, t.count)
-                _, s1, _ = eng.match(t.flip, None, None, t.count)
+                _, s1, _ = eng.match(t.flip, None, None, t.count)     # rows without a flip yet are zero vectors: never read
                 eng.sync()
                 self.fd_plain = 1.0 - s0[:t.count].cpu().numpy().astype(np.float64)
                 self.fd_flip = 1.0 - s1[:t.count].cpu().numpy().astype(np.float64)
             self.version = bank.version
         return self.fd_plain, self.fd_flip
+
+
+def _count_passes(stats, table: FaceTable):
+    if stats is not None:
+        stats["faces"] = stats.get("faces", 0) + table.count
+        stats["arcface_passes"] = stats.get("arcface_passes", 0) + table.count + table.flip_passes
+
+
+def _rows_of(rec: "SampleRecord") -> List[np.ndarray]:
+    out = [] if rec.up is None else [rec.up.rows]
+    return out + [v.rows for v in rec.heavy.values()]
 
 
 def replay(records: Dict[int, SampleRecord], table: FaceTable, feats_host, idxs: Sequence[int], fps: int, total_frames: int,
@@ -641,12 +751,22 @@ def replay(records: Dict[int, SampleRecord], table: FaceTable, feats_host, idxs:
     cooldown = int(getattr(cfg, "prescan_add_cooldown_samples", 5))
     last_add = -10 ** 9
     plain_h, flip_h = feats_host
+    lazy = table is not None and getattr(table, "lazy", False)
+    if lazy:
+        flip_h = table.flip_host
+    lookahead = 96      # samples whose faces get their flip pass together once the replay needs one of them
     for sample_idx, idx in enumerate(idxs):
         rec = records[idx]
         active = trk.active
         best = FD_NONE
         skipped = trk.gate_skips()
         nfaces = 0
+        if lazy and active and not skipped and (rec.up is not None or rec.heavy):
+            mine = _rows_of(rec)
+            if not table.flip_ready[np.concatenate(mine)].all():
+                rows = [r for j in idxs[sample_idx:sample_idx + lookahead] for r in _rows_of(records[j])]
+                if table.ensure_flip(getattr(face, "engine", None), np.concatenate(rows)):
+                    dist.invalidate()
         if not skipped:
             face._frame_idx += 1
             chosen = rec.up
@@ -689,11 +809,75 @@ def replay(records: Dict[int, SampleRecord], table: FaceTable, feats_host, idxs:
     return trk, bank
 
 
+def _predict_flip_rows(records: Dict[int, SampleRecord], idxs: Sequence[int], fd_plain: np.ndarray, cfg, fps: int,
+                       carry_in: bool, margin: float = 0.12) -> np.ndarray:
+    """Rows whose flip-TTA feature the replay will most likely read: samples that follow, within the exit cooldown, a
+    sample with a face at plain distance <= enter + margin from the *initial* bank (the bank only grows, so live
+    distances are not larger), plus the head of a chunk that starts inside another rank's possible active stretch.
+    A prediction only: the replay computes whatever is missing on demand, so spans never depend on it."""
+    enter = float(cfg.prescan_fd_enter)
+    stride = max(1, int(cfg.prescan_stride))
+    exit_cool = int(round(max(0.0, float(getattr(cfg, "prescan_exit_cooldown_sec", 0.5))) * fps))
+    tail = (exit_cool + stride - 1) // stride + 1
+    remaining = tail if carry_in else 0
+    rows: List[np.ndarray] = []
+    for idx in idxs:
+        rws = _rows_of(records[idx])
+        if remaining > 0:
+            rows += rws
+            remaining -= 1
+        if rws and min(float(fd_plain[r].min()) for r in rws) <= enter + margin:
+            remaining = tail
+    return np.concatenate(rows) if rows else np.zeros((0,), np.int64)
+
+
+class _ShardedTable:
+    """The all-gathered face table of a multi-rank pre-scan.  Flip features that no rank predicted are computed by the rank
+    that owns the face (it holds the chip) and exchanged; every rank replays identically, so all ranks reach `ensure_flip`
+    with the same rows and the exchange is a matched collective."""
+    lazy = True
+
+    def __init__(self, local: FaceTable, counts: List[int], rank: int, group, plain, flip, ready, flip_host):
+        self.local, self.counts, self.rank, self.group = local, counts, rank, group
+        self.base = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+        self.count = int(self.base[-1])
+        self.plain, self.flip, self.flip_ready, self.flip_host = plain, flip, ready, flip_host
+        self.flip_passes = 0
+
+    def ensure_flip(self, eng, rows: np.ndarray) -> bool:
+        import torch.distributed as dist
+        if not len(rows):
+            return False
+        need = np.unique(np.asarray(rows)[~self.flip_ready[rows]])
+        if not len(need):
+            return False
+        lo, hi = self.base[self.rank], self.base[self.rank + 1]
+        mine = need[(need >= lo) & (need < hi)] - lo
+        self.local.ensure_flip(eng, mine)
+        parts = [None] * len(self.counts)
+        dist.all_gather_object(parts, (mine + lo, self.local.flip_host[mine] if len(mine) else np.zeros((0, L.FEAT_DIM), np.float32)),
+                               group=self.group)
+        for rows_g, feats in parts:
+            if len(rows_g):
+                self.flip_host[rows_g] = feats
+                self.flip_ready[rows_g] = True
+                if self.flip.is_cuda:
+                    with torch.cuda.stream(eng.stream):
+                        self.flip.index_copy_(0, torch.as_tensor(rows_g, device=self.flip.device), torch.from_numpy(feats).to(self.flip.device))
+                else:
+                    self.flip[torch.as_tensor(rows_g)] = torch.from_numpy(feats)
+        return True
+
+
 def prescan_batched(clip, fps: int, face: FaceEmbedder, ref_feat, cfg, batch: int = 32, log: Optional[list] = None,
-                    dist_group=None):
+                    dist_group=None, stats: Optional[dict] = None):
     """Throughput pre-scan.  With torch.distributed initialised (dist_group or the default group), the
     sample list is split into contiguous chunks per rank, per-face records are all-gathered and every
-    rank replays the same sequence."""
+    rank replays the same sequence.
+
+    ArcFace work matches the reference's: e(x) for every face; e(flip x) only for faces evaluated while a span is active
+    (face_embedder.py:1295).  Which faces those are is a property of the sequential replay, so each rank first embeds the
+    flips its own chunk is *predicted* to need (in parallel, large batches) and the replay fills any gap on demand."""
     import torch.distributed as dist
     total = clip.total_frames
     stride = max(1, int(cfg.prescan_stride))
@@ -704,38 +888,59 @@ def prescan_batched(clip, fps: int, face: FaceEmbedder, ref_feat, cfg, batch: in
     if int(getattr(cfg, "prescan_probe_imgsz", 512)) > int(face.fast_no_face_imgsz):
         raise RuntimeError("prescan_batched requires prescan_probe_imgsz <= fast_no_face_imgsz (the upright size would "
                            "depend on the no-face streak, SURVEY.md H1); use prescan_sequential")
+    eng = face.engine
     with _PrescanFaceMode(face, cfg):
         per = (len(idxs) + world - 1) // world
         mine = idxs[rank * per:(rank + 1) * per]
-        records, table = compute_superset(clip, mine, face, cfg, batch=batch)
-        face.engine.sync()
+        lazy = os.environ.get("PCB_EAGER_FLIP", "0") != "1"
+        records, table = compute_superset(clip, mine, face, cfg, batch=batch, lazy_flip=lazy)
+        eng.sync()
+        if lazy and table.count:
+            bank0 = RefBank(cfg, ref_feat)
+            if len(bank0):
+                eng.set_bank(bank0.array())
+                _, s0, _ = eng.match(table.plain, None, None, table.count)
+                eng.sync()
+                fd0 = 1.0 - s0[:table.count].cpu().numpy().astype(np.float64)
+                table.ensure_flip(eng, _predict_flip_rows(records, mine, fd0, cfg, fps, carry_in=rank > 0))
         plain_h = table.plain[:table.count].cpu().numpy() if table.count else np.zeros((0, L.FEAT_DIM), np.float32)
-        flip_h = table.flip[:table.count].cpu().numpy() if table.count else np.zeros((0, L.FEAT_DIM), np.float32)
+        flip_h = (table.flip[:table.count].cpu().numpy() if (table.count and not lazy) else np.zeros((0, L.FEAT_DIM), np.float32))
+        local_table = table
         if world > 1:
-            records, table, plain_h, flip_h = _gather_shards(face.engine, records, table, plain_h, flip_h, world, dist_group)
+            records, table, plain_h, flip_h = _gather_shards(eng, records, table, plain_h, flip_h, world, dist_group)
         trk, bank = replay(records, table, (plain_h, flip_h), idxs, fps, total, face, ref_feat, cfg, log)
+        _count_passes(stats, local_table)      # this rank's faces / ArcFace image passes
         spans = trk.finish()
         wmax = int(getattr(cfg, "prescan_max_width", 0))
-        spans = _post_process(spans, clip, fps, face, bank, ref_feat, cfg, trk, wmax, batched=batch)
+        spans = _post_process(spans, clip, fps, face, bank, ref_feat, cfg, trk, wmax, batched=batch, stats=stats)
     out_bank = bank.array()
     return spans, (out_bank if out_bank is not None else ref_feat)
 
 
 def _gather_shards(eng, records, table, plain_h, flip_h, world, group):
     """All-gather per-face records: features through NCCL (device tensors), the small per-sample
-    metadata through all_gather_object."""
+    metadata through all_gather_object.  -> (records of all ranks, merged table, plain_h, flip_h)."""
     import torch.distributed as dist
+    rank = dist.get_rank(group)
+    lazy = bool(getattr(table, "lazy", False))
     counts = [None] * world
     dist.all_gather_object(counts, table.count, group=group)
     recs = [None] * world
     dist.all_gather_object(recs, records, group=group)
+    readies = [None] * world
+    dist.all_gather_object(readies, getattr(table, "flip_ready", np.ones(table.count, bool)) if table.count else np.zeros((0,), bool),
+                           group=group)
     cap = max(max(counts), 1)
-    dev = table.plain.device if table.count else (eng.tdev if eng is not None else torch.device("cpu"))
     backend_cuda = dist.get_backend(group) == "nccl"
-    send = torch.zeros((2, cap, L.FEAT_DIM), dtype=torch.float32, device=dev if backend_cuda else "cpu")
+    dev = eng.tdev if (backend_cuda and eng is not None) else torch.device("cpu")
+    send = torch.zeros((2, cap, L.FEAT_DIM), dtype=torch.float32, device=dev)
     if table.count:
+        if lazy:
+            flip_src = table.flip[:table.count] if backend_cuda else torch.from_numpy(table.flip_host)
+        else:
+            flip_src = table.flip[:table.count] if backend_cuda else torch.from_numpy(flip_h)
         send[0, :table.count] = table.plain[:table.count] if backend_cuda else torch.from_numpy(plain_h)
-        send[1, :table.count] = table.flip[:table.count] if backend_cuda else torch.from_numpy(flip_h)
+        send[1, :table.count] = flip_src
     recv = [torch.empty_like(send) for _ in range(world)]
     if backend_cuda:
         torch.cuda.current_stream().wait_stream(eng.stream)
@@ -752,15 +957,22 @@ def _gather_shards(eng, records, table, plain_h, flip_h, world, group):
         plains.append(recv[r][0, :counts[r]])
         flips.append(recv[r][1, :counts[r]])
         base += counts[r]
-    new = FaceTable()
-    new.count = base
     allp = torch.cat(plains, 0) if base else torch.zeros((1, L.FEAT_DIM))
     allf = torch.cat(flips, 0) if base else torch.zeros((1, L.FEAT_DIM))
     if backend_cuda:
         torch.cuda.current_stream().synchronize()
-    new.plain = allp.to(eng.tdev).contiguous() if eng is not None else allp
-    new.flip = allf.to(eng.tdev).contiguous() if eng is not None else allf
-    return merged, new, allp[:base].cpu().numpy(), allf[:base].cpu().numpy()
+    plain_all = allp.to(eng.tdev).contiguous() if eng is not None else allp
+    flip_all = allf.to(eng.tdev).contiguous() if eng is not None else allf.clone()
+    plain_host = allp[:base].cpu().numpy()
+    flip_host = allf[:base].cpu().numpy().copy()
+    if lazy:
+        ready = np.concatenate([np.asarray(x, bool) for x in readies]) if base else np.zeros((0,), bool)
+        new = _ShardedTable(table, counts, rank, group, plain_all, flip_all, ready, flip_host)
+    else:
+        new = FaceTable()
+        new.count = base
+        new.plain, new.flip = plain_all, flip_all
+    return merged, new, plain_host, flip_host
 
 
 # --------------------------------------------------------------------------------------------

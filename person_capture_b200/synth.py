@@ -128,13 +128,14 @@ class ClipSpec:
 
     def __init__(self, width: int, height: int, n_frames: int, seed: int, target: int = 1,
                  others: tuple = (2, 3, 4), faces_per_frame: int = 1, face_px=(48, 120),
-                 target_segments=None, fps: float = 24.0, crowd: int = 0):
+                 target_segments=None, fps: float = 24.0, crowd: int = 0, distractor_prob: float = 0.4):
         self.width, self.height, self.n_frames, self.seed = width, height, n_frames, seed
         self.target, self.others = target, tuple(others)
         self.faces_per_frame = faces_per_frame
         self.face_px = face_px
         self.fps = fps
         self.crowd = crowd
+        self.distractor_prob = float(distractor_prob)
         if target_segments is None:
             # target visible in two stretches, absent elsewhere
             a, b = int(0.15 * n_frames), int(0.40 * n_frames)
@@ -184,7 +185,7 @@ class ClipSpec:
             idents.append(self.target)
         # a distractor identity in roughly 40% of frames (blocks of 24 frames)
         drng = np.random.default_rng(self.seed * 13 + (i // 24))
-        if self.others and drng.random() < 0.4:
+        if self.others and drng.random() < self.distractor_prob:
             idents.append(int(self.others[int(drng.integers(0, len(self.others)))]))
         slots = []
         for ident in idents[: max(1, self.faces_per_frame + 1)]:
