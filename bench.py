@@ -238,6 +238,7 @@ def main():
         faces_seen["n"] = stats.get("faces", 0)               # faces aligned + embedded by THIS rank in the step
         faces_seen["passes"] = stats.get("arcface_passes", 0)  # ArcFace image passes (e(x), plus e(flip x) where the span logic needs it)
         faces_seen["spans"] = [list(map(int, sp)) for sp in spans]
+        faces_seen["phase_ms"] = stats.get("phase_ms")
         return spans
 
     def timed(clip, steps, profile=False):
@@ -318,6 +319,7 @@ def main():
         "faces_embedded_per_sec": faces_seen["n"] * world * args.steps / (ms / 1000.0),
         "arcface_image_passes_per_sec": faces_seen["passes"] * world * args.steps / (ms / 1000.0),
         "gpu_launches": launches,
+        "phase_ms_last_step": faces_seen.get("phase_ms"),
         "wall_ms_per_step": 1000.0 * wall / args.steps,
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(h2d),

@@ -191,15 +191,15 @@ class SpanTracker:
         self.start = 0
         self.neg_run = 0
         self.fd9_streak = 0
+        self._fd9_skip = bool(getattr(cfg, "prescan_fd9_skip", True))
+        self._fd9_grace = max(0, int(getattr(cfg, "prescan_fd9_grace", 1)))
+        self._fd9_period = max(1, int(getattr(cfg, "prescan_fd9_probe_period", 2)))
 
     def gate_skips(self) -> bool:
         """fd9 skip gate evaluated before a sample (gui_app.py:1479-1492)."""
-        cfg = self.cfg
-        if self.active or not bool(getattr(cfg, "prescan_fd9_skip", True)):
+        if self.active or not self._fd9_skip:
             return False
-        grace = max(0, int(getattr(cfg, "prescan_fd9_grace", 1)))
-        period = max(1, int(getattr(cfg, "prescan_fd9_probe_period", 2)))
-        return self.fd9_streak >= grace and (self.fd9_streak % period) != 0
+        return self.fd9_streak >= self._fd9_grace and (self.fd9_streak % self._fd9_period) != 0
 
     def _close(self, s: int, e: int):
         if e - s + 1 >= self.min_len:
@@ -360,13 +360,14 @@ def prescan_sequential(clip, fps: int, face: FaceEmbedder, ref_feat, cfg, log: O
     return spans, (out_bank if out_bank is not None else ref_feat)
 
 
-def _post_process(spans, clip, fps, face, bank: RefBank, ref_feat, cfg, trk: SpanTracker, wmax: int, batched: int = 0, stats=None):
+def _post_process(spans, clip, fps, face, bank: RefBank, ref_feat, cfg, trk: SpanTracker, wmax: int, batched: int = 0, stats=None,
+                  shard=None):
     gap = int(round(cfg.prescan_bridge_gap_sec * fps))
     do_bridge = getattr(cfg, "prescan_bridge_gap_sec", 0) > 0
     if spans and do_bridge:
         spans = bridge_spans(spans, gap)
     if batched:
-        spans = _refine_edges_batched(spans, clip, fps, face, bank, ref_feat, cfg, trk, batched, stats=stats)
+        spans = _refine_edges_batched(spans, clip, fps, face, bank, ref_feat, cfg, trk, batched, stats=stats, shard=shard)
     else:
         spans = _refine_edges(spans, clip, fps, face, bank, ref_feat, cfg, trk, wmax)
     if spans and do_bridge:
@@ -424,7 +425,7 @@ def _refine_edges(spans, clip, fps, face, bank: RefBank, ref_feat, cfg, trk: Spa
     return out
 
 
-def _refine_edges_batched(spans, clip, fps, face, bank: RefBank, ref_feat, cfg, trk: SpanTracker, batch: int, stats=None):
+def _refine_edges_batched(spans, clip, fps, face, bank: RefBank, ref_feat, cfg, trk: SpanTracker, batch: int, stats=None, shard=None):
     """Same result as _refine_edges, but every candidate probe frame of all spans goes through the
     batched superset (two GPU rounds: all left windows, then all right windows, whose start depends
     on the refined left edge).  Probes run in "full"/escalate mode: flip-TTA on, 90 then 270."""
@@ -440,13 +441,16 @@ def _refine_edges_batched(spans, clip, fps, face, bank: RefBank, ref_feat, cfg, 
 
     def evaluate(frame_ids):
         """-> {frame: bool hit} for probe frames in escalate mode against the final bank."""
-        ids = sorted(set(frame_ids))
-        if not ids:
+        all_ids = sorted(set(frame_ids))
+        if not all_ids:
             return {}
-        records, table = compute_superset(clip, ids, face, cfg, batch=batch)
-        _count_passes(stats, table)
-        fdp, fdf = _LiveDistances(face.engine, table).get(use_bank)
+        # several ranks: each probe frame is evaluated by the rank that owns its time chunk, results are all-gathered
+        ids = all_ids if shard is None else [j for j in all_ids if shard["owner"](j) == shard["rank"]]
         res = {}
+        if ids:
+            records, table = compute_superset(clip, ids, face, cfg, batch=batch)
+            _count_passes(stats, table)
+            fdp, fdf = _LiveDistances(face.engine, table).get(use_bank)
         for j in ids:
             rec = records[j]
             chosen = rec.up
@@ -456,6 +460,13 @@ def _refine_edges_batched(spans, clip, fps, face, bank: RefBank, ref_feat, cfg, 
                         chosen = rec.heavy[deg]
                         break
             res[j] = bool(chosen is not None and (fdf[chosen.rows] <= trk.enter).any())
+        if shard is not None:
+            import torch.distributed as dist
+            parts = [None] * shard["world"]
+            dist.all_gather_object(parts, res, group=shard["group"])
+            res = {}
+            for part in parts:
+                res.update(part)
         return res
 
     left_ids = []
@@ -743,12 +754,17 @@ def _rows_of(rec: "SampleRecord") -> List[np.ndarray]:
 def replay(records: Dict[int, SampleRecord], table: FaceTable, feats_host, idxs: Sequence[int], fps: int, total_frames: int,
            face: FaceEmbedder, ref_feat, cfg, log: Optional[list] = None, distances=None):
     """Host replay of the reference's sequential loop over precomputed superset records.
-    `distances` (tests only) replaces the GPU matcher with an object exposing get(bank)."""
+    `distances` (tests only) replaces the GPU matcher with an object exposing get(bank).
+
+    Every rank of a multi-GPU pre-scan runs this over ALL samples, so its cost per sample bounds the scaling: the common
+    case (no face of the sample can be offered to the bank) is a vectorised min over the chosen variant's rows; the
+    reference's face-by-face loop only runs for samples where a bank update is possible."""
     bank = RefBank(cfg, ref_feat)
     trk = SpanTracker(cfg, fps, total_frames)
     dist = distances if distances is not None else _LiveDistances(face.engine, table)
     fd_add = float(getattr(cfg, "prescan_fd_add", trk.enter))
     cooldown = int(getattr(cfg, "prescan_add_cooldown_samples", 5))
+    qmin = float(cfg.face_quality_min)
     last_add = -10 ** 9
     plain_h, flip_h = feats_host
     lazy = table is not None and getattr(table, "lazy", False)
@@ -761,12 +777,6 @@ def replay(records: Dict[int, SampleRecord], table: FaceTable, feats_host, idxs:
         best = FD_NONE
         skipped = trk.gate_skips()
         nfaces = 0
-        if lazy and active and not skipped and (rec.up is not None or rec.heavy):
-            mine = _rows_of(rec)
-            if not table.flip_ready[np.concatenate(mine)].all():
-                rows = [r for j in idxs[sample_idx:sample_idx + lookahead] for r in _rows_of(records[j])]
-                if table.ensure_flip(getattr(face, "engine", None), np.concatenate(rows)):
-                    dist.invalidate()
         if not skipped:
             face._frame_idx += 1
             chosen = rec.up
@@ -789,20 +799,32 @@ def replay(records: Dict[int, SampleRecord], table: FaceTable, feats_host, idxs:
                 face._last_face_idx = face._frame_idx
                 face._rot_cycle = 0
             if chosen is not None:
-                k = len(chosen.rows)
-                nfaces = k
-                area = (chosen.box[:, 2] - chosen.box[:, 0]) * (chosen.box[:, 3] - chosen.box[:, 1])
-                order = sorted(range(k), key=lambda i: (chosen.quality[i], area[i]), reverse=True)
-                for i in order:
-                    row = int(chosen.rows[i])
-                    fdp, fdf = dist.get(bank)
-                    fd = float(fdf[row] if active else fdp[row])
-                    best = min(best, fd)
-                    q = float(chosen.quality[i])
-                    if fd <= fd_add and (sample_idx - last_add) >= cooldown and q >= cfg.face_quality_min:
-                        vec = (flip_h if active else plain_h)[row]
-                        if bank.offer(vec, q) in ("added", "replaced"):
-                            last_add = sample_idx
+                rows = chosen.rows
+                nfaces = len(rows)
+                if lazy and active and not table.flip_ready[rows].all():
+                    want = [rows]
+                    for j in idxs[sample_idx + 1:sample_idx + lookahead]:
+                        rj = records[j]
+                        want += [rj.up.rows] if rj.up is not None else [v.rows for v in rj.heavy.values()]
+                    if table.ensure_flip(getattr(face, "engine", None), np.concatenate(want)):
+                        dist.invalidate()
+                fdp, fdf = dist.get(bank)
+                fds = (fdf if active else fdp)[rows]
+                if (sample_idx - last_add) >= cooldown and bool(((fds <= fd_add) & (chosen.quality >= qmin)).any()):
+                    # a bank update is possible: the reference's face-by-face order matters (later faces see the new bank)
+                    area = (chosen.box[:, 2] - chosen.box[:, 0]) * (chosen.box[:, 3] - chosen.box[:, 1])
+                    for i in sorted(range(nfaces), key=lambda i: (chosen.quality[i], area[i]), reverse=True):
+                        row = int(rows[i])
+                        fdp, fdf = dist.get(bank)
+                        fd = float(fdf[row] if active else fdp[row])
+                        best = min(best, fd)
+                        q = float(chosen.quality[i])
+                        if fd <= fd_add and (sample_idx - last_add) >= cooldown and q >= qmin:
+                            vec = (flip_h if active else plain_h)[row]
+                            if bank.offer(vec, q) in ("added", "replaced"):
+                                last_add = sample_idx
+                else:
+                    best = min(best, float(fds.min()))
         if log is not None:
             log.append(dict(idx=idx, skip=skipped, best=best, active_before=active, nfaces=nfaces))
         trk.observe(idx, best)
@@ -889,12 +911,21 @@ def prescan_batched(clip, fps: int, face: FaceEmbedder, ref_feat, cfg, batch: in
         raise RuntimeError("prescan_batched requires prescan_probe_imgsz <= fast_no_face_imgsz (the upright size would "
                            "depend on the no-face streak, SURVEY.md H1); use prescan_sequential")
     eng = face.engine
+    import time as _time
+    tmark = [("start", _time.perf_counter())]
+
+    def mark(name):
+        if stats is not None:
+            eng.sync()
+            tmark.append((name, _time.perf_counter()))
+
     with _PrescanFaceMode(face, cfg):
         per = (len(idxs) + world - 1) // world
         mine = idxs[rank * per:(rank + 1) * per]
         lazy = os.environ.get("PCB_EAGER_FLIP", "0") != "1"
         records, table = compute_superset(clip, mine, face, cfg, batch=batch, lazy_flip=lazy)
         eng.sync()
+        mark("superset")
         if lazy and table.count:
             bank0 = RefBank(cfg, ref_feat)
             if len(bank0):
@@ -903,16 +934,27 @@ def prescan_batched(clip, fps: int, face: FaceEmbedder, ref_feat, cfg, batch: in
                 eng.sync()
                 fd0 = 1.0 - s0[:table.count].cpu().numpy().astype(np.float64)
                 table.ensure_flip(eng, _predict_flip_rows(records, mine, fd0, cfg, fps, carry_in=rank > 0))
+        mark("predicted_flips")
         plain_h = table.plain[:table.count].cpu().numpy() if table.count else np.zeros((0, L.FEAT_DIM), np.float32)
         flip_h = (table.flip[:table.count].cpu().numpy() if (table.count and not lazy) else np.zeros((0, L.FEAT_DIM), np.float32))
         local_table = table
         if world > 1:
             records, table, plain_h, flip_h = _gather_shards(eng, records, table, plain_h, flip_h, world, dist_group)
+        mark("gather")
         trk, bank = replay(records, table, (plain_h, flip_h), idxs, fps, total, face, ref_feat, cfg, log)
+        mark("replay")
         _count_passes(stats, local_table)      # this rank's faces / ArcFace image passes
         spans = trk.finish()
         wmax = int(getattr(cfg, "prescan_max_width", 0))
-        spans = _post_process(spans, clip, fps, face, bank, ref_feat, cfg, trk, wmax, batched=batch, stats=stats)
+        shard = None
+        if world > 1:
+            first_of = [idxs[min(r * per, len(idxs) - 1)] for r in range(world)]
+            shard = dict(world=world, rank=rank, group=dist_group,
+                         owner=lambda j: max(r for r in range(world) if first_of[r] <= j or r == 0))
+        spans = _post_process(spans, clip, fps, face, bank, ref_feat, cfg, trk, wmax, batched=batch, stats=stats, shard=shard)
+        mark("refine")
+    if stats is not None:
+        stats["phase_ms"] = {b[0]: round(1000.0 * (b[1] - a[1]), 2) for a, b in zip(tmark, tmark[1:])}
     out_bank = bank.array()
     return spans, (out_bank if out_bank is not None else ref_feat)
 
