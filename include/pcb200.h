@@ -174,6 +174,30 @@ int pcb_set_bank(pcb_ctx* ctx, const float* bank_host /* [rows][512] */, int row
 int pcb_match(pcb_ctx* ctx, const float* emb_dev, const float* emb_flip_dev, const uint8_t* use_flip_dev,
               int f, float* feat_dev, float* sim_dev, int32_t* argmax_dev);
 
+/* ---- host replay of the pre-scan state machine (replaces the per-sample body of Processor._prescan,
+ *      gui_app.py:1468-1655, for samples whose detections / features were precomputed in batches) -------- */
+#define PCB_REPLAY_META 10
+/* meta[s] = { up_start (-1: no upright face), up_count, hits90, hits270, heavy_raw90, heavy_raw270,
+ *             heavy90_start (-1: none), heavy90_count, heavy270_start, heavy270_count }; rows index the face table */
+typedef struct pcb_replay_cfg {
+  double enter, exit_thr, fd_add, quality_min;
+  int64_t total_frames, pad, min_len, exit_cool;
+  int32_t stride, cooldown, fd9_skip, fd9_grace, fd9_period;
+} pcb_replay_cfg;
+typedef struct pcb_replay_state {      /* FaceEmbedder counters the reference advances per extract() call */
+  int64_t frame_idx, last_face_idx;
+  int32_t no_face_streak, rot_cycle, prescan_rr, trk_active;
+} pcb_replay_state;
+/* offer: a face qualifies for the bank (gui_app.py:1519-1549); returns 1 if the bank changed (the callee has then
+ * rewritten fd_plain / fd_flip in place).  need_flip: flip-TTA features of sample s are missing (callee fills them). */
+typedef int (*pcb_replay_offer_cb)(void* user, int sample, int row, double quality, int active);
+typedef int (*pcb_replay_flip_cb)(void* user, int sample);
+int pcb_replay(const pcb_replay_cfg* cfg, const int32_t* meta, const int64_t* frame_idx, int n_samples,
+               const double* quality, const int64_t* area, const uint8_t* flip_ready /* NULL: all present */,
+               const double* fd_plain, const double* fd_flip, pcb_replay_state* st, pcb_replay_offer_cb offer,
+               pcb_replay_flip_cb need_flip, void* user, double* best_out, uint8_t* skip_out, uint8_t* active_out,
+               int32_t* nfaces_out, int64_t* spans_out /* [max_spans][2] */, int max_spans, int32_t* n_spans_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -24,7 +24,7 @@ OPF_OUT_F32 = 1
 EXPORTS = (
     "pcb_create", "pcb_destroy", "pcb_last_error", "pcb_sync", "pcb_set_conv_impl", "pcb_launch_count",
     "pcb_reset_launch_count", "pcb_set_profile", "pcb_profile_read", "pcb_model_load", "pcb_model_get_tensor", "pcb_resize_area", "pcb_resize_linear", "pcb_resize_factor",
-    "pcb_detect", "pcb_letterbox", "pcb_decode_nms", "pcb_align", "pcb_embed", "pcb_set_bank", "pcb_match",
+    "pcb_detect", "pcb_letterbox", "pcb_decode_nms", "pcb_align", "pcb_embed", "pcb_set_bank", "pcb_match", "pcb_replay",
 )
 
 
@@ -53,6 +53,25 @@ class AlignArgs(C.Structure):
                 ("face_count_dev", C.c_void_p), ("face_total_dev", C.c_void_p), ("face_frame_dev", C.c_void_p),
                 ("face_box_dev", C.c_void_p), ("face_kind_dev", C.c_void_p), ("chips_dev", C.c_void_p),
                 ("quality_dev", C.c_void_p)]
+
+
+REPLAY_META = 10
+
+
+class ReplayCfg(C.Structure):
+    _fields_ = [("enter", C.c_double), ("exit_thr", C.c_double), ("fd_add", C.c_double), ("quality_min", C.c_double),
+                ("total_frames", C.c_int64), ("pad", C.c_int64), ("min_len", C.c_int64), ("exit_cool", C.c_int64),
+                ("stride", C.c_int32), ("cooldown", C.c_int32), ("fd9_skip", C.c_int32), ("fd9_grace", C.c_int32),
+                ("fd9_period", C.c_int32)]
+
+
+class ReplayState(C.Structure):
+    _fields_ = [("frame_idx", C.c_int64), ("last_face_idx", C.c_int64), ("no_face_streak", C.c_int32),
+                ("rot_cycle", C.c_int32), ("prescan_rr", C.c_int32), ("trk_active", C.c_int32)]
+
+
+REPLAY_OFFER_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_int)
+REPLAY_FLIP_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int)
 
 
 class PcbError(RuntimeError):
@@ -99,6 +118,8 @@ def load():
     lib.pcb_embed.argtypes = [vp, vp, i32, vp, vp]
     lib.pcb_set_bank.argtypes = [vp, vp, i32]
     lib.pcb_match.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp]
+    lib.pcb_replay.argtypes = [C.POINTER(ReplayCfg), vp, vp, i32, vp, vp, vp, vp, vp, C.POINTER(ReplayState), REPLAY_OFFER_CB,
+                               REPLAY_FLIP_CB, vp, vp, vp, vp, vp, vp, i32, C.POINTER(C.c_int32)]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int:

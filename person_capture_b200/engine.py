@@ -245,13 +245,14 @@ class Engine:
         self._check(self.lib.pcb_set_bank(self.ctx, b.ctypes.data_as(C.c_void_p), b.shape[0]), "pcb_set_bank")
         self.bank_rows = b.shape[0]
 
-    def match(self, emb: torch.Tensor, emb_flip: Optional[torch.Tensor], use_flip: Optional[torch.Tensor], f: int):
-        """-> (feat [f,512], sim [f], argmax [f]) device tensors; fd = 1 - sim."""
-        feat = self.empty((max(f, 1), L.FEAT_DIM), torch.float32)
+    def match(self, emb: torch.Tensor, emb_flip: Optional[torch.Tensor], use_flip: Optional[torch.Tensor], f: int,
+              want_feat: bool = True):
+        """-> (feat [f,512] or None, sim [f], argmax [f]) device tensors; fd = 1 - sim."""
+        feat = self.empty((max(f, 1), L.FEAT_DIM), torch.float32) if want_feat else None
         sim = self.empty((max(f, 1),), torch.float32)
         arg = self.empty((max(f, 1),), torch.int32)
         if f > 0:
             self._check(self.lib.pcb_match(self.ctx, emb.data_ptr(), emb_flip.data_ptr() if emb_flip is not None else None,
-                                           use_flip.data_ptr() if use_flip is not None else None, f, feat.data_ptr(),
-                                           sim.data_ptr(), arg.data_ptr()), "pcb_match")
+                                           use_flip.data_ptr() if use_flip is not None else None, f,
+                                           feat.data_ptr() if feat is not None else None, sim.data_ptr(), arg.data_ptr()), "pcb_match")
         return feat, sim, arg

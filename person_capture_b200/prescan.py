@@ -714,15 +714,18 @@ def compute_superset(clip, idxs: Sequence[int], face: FaceEmbedder, cfg, batch: 
 
 class _LiveDistances:
     """fd of every table row against the live bank, for both flip variants; recomputed on the GPU
-    (pcb_match) whenever the bank version changes or new flip rows became available."""
+    (pcb_match) whenever the bank version changes or new flip rows became available.  Both variants go through
+    ONE match launch over the stacked [plain; flip] table and one device->host copy."""
 
     def __init__(self, eng, table: FaceTable):
         self.eng, self.table = eng, table
         self.version = None
         self.fd_plain = self.fd_flip = None
+        self.both = None
 
     def invalidate(self):
         self.version = None
+        self.both = None
 
     def get(self, bank: RefBank):
         if self.version != bank.version or self.fd_plain is None:
@@ -730,12 +733,15 @@ class _LiveDistances:
             if t.count == 0:
                 self.fd_plain = self.fd_flip = np.zeros((0,), np.float64)
             else:
+                if self.both is None:
+                    with torch.cuda.stream(eng.stream):
+                        # rows without a flip feature yet are zero vectors: their distances are never read
+                        self.both = torch.cat([t.plain[:t.count], t.flip[:t.count]], 0).contiguous()
                 eng.set_bank(bank.array())
-                _, s0, _ = eng.match(t.plain, None, None, t.count)
-                _, s1, _ = eng.match(t.flip, None, None, t.count)     # rows without a flip yet are zero vectors: never read
+                _, sim, _ = eng.match(self.both, None, None, 2 * t.count, want_feat=False)
                 eng.sync()
-                self.fd_plain = 1.0 - s0[:t.count].cpu().numpy().astype(np.float64)
-                self.fd_flip = 1.0 - s1[:t.count].cpu().numpy().astype(np.float64)
+                fd = 1.0 - sim[:2 * t.count].cpu().numpy().astype(np.float64)
+                self.fd_plain, self.fd_flip = fd[:t.count], fd[t.count:]
             self.version = bank.version
         return self.fd_plain, self.fd_flip
 
@@ -751,8 +757,8 @@ def _rows_of(rec: "SampleRecord") -> List[np.ndarray]:
     return out + [v.rows for v in rec.heavy.values()]
 
 
-def replay(records: Dict[int, SampleRecord], table: FaceTable, feats_host, idxs: Sequence[int], fps: int, total_frames: int,
-           face: FaceEmbedder, ref_feat, cfg, log: Optional[list] = None, distances=None):
+def _replay_python(records: Dict[int, SampleRecord], table: FaceTable, feats_host, idxs: Sequence[int], fps: int, total_frames: int,
+                   face: FaceEmbedder, ref_feat, cfg, log: Optional[list] = None, distances=None):
     """Host replay of the reference's sequential loop over precomputed superset records.
     `distances` (tests only) replaces the GPU matcher with an object exposing get(bank).
 
@@ -828,6 +834,123 @@ def replay(records: Dict[int, SampleRecord], table: FaceTable, feats_host, idxs:
         if log is not None:
             log.append(dict(idx=idx, skip=skipped, best=best, active_before=active, nfaces=nfaces))
         trk.observe(idx, best)
+    return trk, bank
+
+
+def encode_records(records: Dict[int, SampleRecord], idxs: Sequence[int], n_rows: int):
+    """Flat form of the superset records for pcb_replay: meta int32 [n, PCB_REPLAY_META], quality f64 [rows], area i64 [rows]."""
+    meta = np.zeros((len(idxs), L.REPLAY_META), np.int32)
+    meta[:, 0] = meta[:, 6] = meta[:, 8] = -1
+    quality = np.zeros(max(n_rows, 1), np.float64)
+    area = np.zeros(max(n_rows, 1), np.int64)
+
+    def put(v: _Variant):
+        r0, k = int(v.rows[0]), len(v.rows)
+        if int(v.rows[-1]) - r0 + 1 != k:
+            raise ValueError("variant rows must be contiguous")
+        quality[r0:r0 + k] = v.quality
+        b = v.box.astype(np.int64)
+        area[r0:r0 + k] = (b[:, 2] - b[:, 0]) * (b[:, 3] - b[:, 1])
+        return r0, k
+
+    for s_i, idx in enumerate(idxs):
+        rec = records[idx]
+        m = meta[s_i]
+        if rec.up is not None:
+            m[0], m[1] = put(rec.up)
+        for d, deg in enumerate((90, 270)):
+            m[2 + d] = rec.hits.get(deg, 0)
+            m[4 + d] = rec.heavy_raw.get(deg, 0)
+            if deg in rec.heavy:
+                m[6 + 2 * d], m[7 + 2 * d] = put(rec.heavy[deg])
+    return meta, quality, area
+
+
+def replay(records: Dict[int, SampleRecord], table, feats_host, idxs: Sequence[int], fps: int, total_frames: int,
+           face: FaceEmbedder, ref_feat, cfg, log: Optional[list] = None, distances=None, native: Optional[bool] = None,
+           encoded=None):
+    """Replay of the reference's sequential loop over precomputed superset records.  The per-sample loop runs in
+    libpcb200 (pcb_replay); bank offers and missing flip features come back here through callbacks.  `native=False`
+    (or PCB_PY_REPLAY=1) runs the pure-Python statement of the same loop (`_replay_python`), which the tests hold the
+    native one against."""
+    import ctypes as C
+    if native is None:
+        native = os.environ.get("PCB_PY_REPLAY", "0") != "1"
+    if not native:
+        return _replay_python(records, table, feats_host, idxs, fps, total_frames, face, ref_feat, cfg, log, distances)
+    lib = L.load()
+    bank = RefBank(cfg, ref_feat)
+    trk = SpanTracker(cfg, fps, total_frames)
+    dist = distances if distances is not None else _LiveDistances(face.engine, table)
+    plain_h, flip_h = feats_host
+    lazy = table is not None and getattr(table, "lazy", False)
+    if lazy:
+        flip_h = table.flip_host
+    n_rows = int(table.count) if table is not None else len(plain_h)
+    idxs = list(idxs)
+    meta, quality, area = encoded if encoded is not None else encode_records(records, idxs, n_rows)
+    meta = np.ascontiguousarray(meta, np.int32)
+    frame_idx = np.asarray(idxs, np.int64)
+    fdp = np.full(max(n_rows, 1), FD_NONE, np.float64)
+    fdf = np.full(max(n_rows, 1), FD_NONE, np.float64)
+
+    def refresh():
+        a, b = dist.get(bank)
+        if n_rows:
+            fdp[:n_rows] = a
+            fdf[:n_rows] = b
+
+    refresh()
+    lookahead = 96
+
+    def on_offer(_user, s_i, row, q, active):
+        vec = (flip_h if active else plain_h)[row]
+        if bank.offer(vec, q) in ("added", "replaced"):
+            refresh()
+            return 1
+        return 0
+
+    def on_flip(_user, s_i):
+        want = []
+        for m in meta[s_i:s_i + lookahead]:
+            for c0 in (0, 6, 8):
+                if m[c0] >= 0:
+                    want.append(np.arange(m[c0], m[c0] + m[c0 + 1]))
+        if want and table.ensure_flip(getattr(face, "engine", None), np.concatenate(want)):
+            dist.invalidate()
+            refresh()
+        return 1
+
+    rc = L.ReplayCfg(enter=trk.enter, exit_thr=trk.exit, fd_add=float(getattr(cfg, "prescan_fd_add", trk.enter)),
+                     quality_min=float(cfg.face_quality_min), total_frames=trk.total, pad=trk.pad, min_len=trk.min_len,
+                     exit_cool=trk.exit_cool, stride=trk.stride, cooldown=int(getattr(cfg, "prescan_add_cooldown_samples", 5)),
+                     fd9_skip=int(trk._fd9_skip), fd9_grace=trk._fd9_grace, fd9_period=trk._fd9_period)
+    st = L.ReplayState(frame_idx=int(face._frame_idx), last_face_idx=int(max(face._last_face_idx, -2 ** 62)),
+                       no_face_streak=int(face._no_face_streak), rot_cycle=int(face._rot_cycle), prescan_rr=int(face._prescan_rr),
+                       trk_active=0)
+    n = len(idxs)
+    best = np.zeros(max(n, 1), np.float64)
+    skip = np.zeros(max(n, 1), np.uint8)
+    act = np.zeros(max(n, 1), np.uint8)
+    nf = np.zeros(max(n, 1), np.int32)
+    max_spans = n + 2
+    spans = np.zeros((max_spans, 2), np.int64)
+    n_spans = C.c_int32(0)
+    ready = table.flip_ready.view(np.uint8) if lazy else None
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+    cb_o, cb_f = L.REPLAY_OFFER_CB(on_offer), L.REPLAY_FLIP_CB(on_flip)
+    err = lib.pcb_replay(C.byref(rc), ptr(meta), ptr(frame_idx), n, ptr(quality), ptr(area), ptr(ready) if ready is not None else None,
+                         ptr(fdp), ptr(fdf), C.byref(st), cb_o, cb_f, None, ptr(best), ptr(skip), ptr(act), ptr(nf), ptr(spans),
+                         max_spans, C.byref(n_spans))
+    if err:
+        raise L.PcbError(f"pcb_replay failed (code {err})")
+    face._frame_idx, face._last_face_idx = int(st.frame_idx), int(st.last_face_idx)
+    face._no_face_streak, face._rot_cycle, face._prescan_rr = int(st.no_face_streak), int(st.rot_cycle), int(st.prescan_rr)
+    trk.spans = [(int(a), int(b)) for a, b in spans[:n_spans.value]]
+    trk.active = False          # pcb_replay already closed the open span (gui_app.py:1648-1655)
+    if log is not None:
+        for i, idx in enumerate(idxs):
+            log.append(dict(idx=idx, skip=bool(skip[i]), best=float(best[i]), active_before=bool(act[i]), nfaces=int(nf[i])))
     return trk, bank
 
 
@@ -938,10 +1061,13 @@ def prescan_batched(clip, fps: int, face: FaceEmbedder, ref_feat, cfg, batch: in
         plain_h = table.plain[:table.count].cpu().numpy() if table.count else np.zeros((0, L.FEAT_DIM), np.float32)
         flip_h = (table.flip[:table.count].cpu().numpy() if (table.count and not lazy) else np.zeros((0, L.FEAT_DIM), np.float32))
         local_table = table
+        encoded = None
         if world > 1:
-            records, table, plain_h, flip_h = _gather_shards(eng, records, table, plain_h, flip_h, world, dist_group)
+            enc_local = encode_records(records, mine, table.count)
+            table, plain_h, flip_h, encoded = _gather_shards(eng, enc_local, table, plain_h, flip_h, world, dist_group)
+            records = None
         mark("gather")
-        trk, bank = replay(records, table, (plain_h, flip_h), idxs, fps, total, face, ref_feat, cfg, log)
+        trk, bank = replay(records, table, (plain_h, flip_h), idxs, fps, total, face, ref_feat, cfg, log, encoded=encoded)
         mark("replay")
         _count_passes(stats, local_table)      # this rank's faces / ArcFace image passes
         spans = trk.finish()
@@ -959,19 +1085,17 @@ def prescan_batched(clip, fps: int, face: FaceEmbedder, ref_feat, cfg, batch: in
     return spans, (out_bank if out_bank is not None else ref_feat)
 
 
-def _gather_shards(eng, records, table, plain_h, flip_h, world, group):
-    """All-gather per-face records: features through NCCL (device tensors), the small per-sample
-    metadata through all_gather_object.  -> (records of all ranks, merged table, plain_h, flip_h)."""
+def _gather_shards(eng, enc_local, table, plain_h, flip_h, world, group):
+    """All-gather the per-face features (NCCL on device tensors) and the flat sample records (pcb_replay form; three
+    numpy arrays per rank).  -> (merged table, plain_h, flip_h, (meta, quality, area) of all ranks in sample order)."""
     import torch.distributed as dist
     rank = dist.get_rank(group)
     lazy = bool(getattr(table, "lazy", False))
-    counts = [None] * world
-    dist.all_gather_object(counts, table.count, group=group)
-    recs = [None] * world
-    dist.all_gather_object(recs, records, group=group)
-    readies = [None] * world
-    dist.all_gather_object(readies, getattr(table, "flip_ready", np.ones(table.count, bool)) if table.count else np.zeros((0,), bool),
-                           group=group)
+    meta_l, q_l, a_l = enc_local
+    parts = [None] * world
+    ready_l = getattr(table, "flip_ready", np.ones(table.count, bool)) if table.count else np.zeros((0,), bool)
+    dist.all_gather_object(parts, (int(table.count), meta_l, q_l[:table.count], a_l[:table.count], ready_l), group=group)
+    counts = [p[0] for p in parts]
     cap = max(max(counts), 1)
     backend_cuda = dist.get_backend(group) == "nccl"
     dev = eng.tdev if (backend_cuda and eng is not None) else torch.device("cpu")
@@ -987,15 +1111,15 @@ def _gather_shards(eng, records, table, plain_h, flip_h, world, group):
     if backend_cuda:
         torch.cuda.current_stream().wait_stream(eng.stream)
     dist.all_gather(recv, send, group=group)
-    merged: Dict[int, SampleRecord] = {}
-    plains, flips = [], []
+    metas, quals, areas, plains, flips = [], [], [], [], []
     base = 0
     for r in range(world):
-        for idx, rec in recs[r].items():
-            for v in [rec.up] + list(rec.heavy.values()):
-                if v is not None:
-                    v.rows = v.rows + base
-            merged[idx] = rec
+        m = parts[r][1].copy()
+        for c0 in (0, 6, 8):
+            m[:, c0] = np.where(m[:, c0] >= 0, m[:, c0] + base, -1)
+        metas.append(m)
+        quals.append(parts[r][2])
+        areas.append(parts[r][3])
         plains.append(recv[r][0, :counts[r]])
         flips.append(recv[r][1, :counts[r]])
         base += counts[r]
@@ -1008,13 +1132,15 @@ def _gather_shards(eng, records, table, plain_h, flip_h, world, group):
     plain_host = allp[:base].cpu().numpy()
     flip_host = allf[:base].cpu().numpy().copy()
     if lazy:
-        ready = np.concatenate([np.asarray(x, bool) for x in readies]) if base else np.zeros((0,), bool)
+        ready = np.concatenate([np.asarray(p[4], bool) for p in parts]) if base else np.zeros((0,), bool)
         new = _ShardedTable(table, counts, rank, group, plain_all, flip_all, ready, flip_host)
     else:
         new = FaceTable()
         new.count = base
         new.plain, new.flip = plain_all, flip_all
-    return merged, new, plain_host, flip_host
+    pad1 = lambda xs, dt: np.concatenate(xs).astype(dt) if base else np.zeros(1, dt)
+    encoded = (np.concatenate(metas, 0), pad1(quals, np.float64), pad1(areas, np.int64))
+    return new, plain_host, flip_host, encoded
 
 
 # --------------------------------------------------------------------------------------------

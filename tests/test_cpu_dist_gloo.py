@@ -36,10 +36,10 @@ def _worker(rank, world, port, q):
     table.count = len(P)
     table.plain = torch.from_numpy(P) if len(P) else torch.zeros((1, 512))
     table.flip = torch.from_numpy(Fl) if len(Fl) else torch.zeros((1, 512))
-    merged, new_table, allp, allf = PS._gather_shards(None, records, table, P, Fl, world, None)
+    new_table, allp, allf, enc = PS._gather_shards(None, PS.encode_records(records, mine, len(P)), table, P, Fl, world, None)
     log = []
-    trk, bank = PS.replay(merged, None, (allp, allf), idxs, 24, n, T.FakeFace(sc), ref, cfg, log=log,
-                          distances=T.NumpyDistances(allp, allf))
+    trk, bank = PS.replay(None, None, (allp, allf), idxs, 24, n, T.FakeFace(sc), ref, cfg, log=log,
+                          distances=T.NumpyDistances(allp, allf), encoded=enc)
     q.put((rank, trk.finish(), [(r["idx"], r["skip"], round(r["best"], 6)) for r in log], len(bank)))
     dist.destroy_process_group()
 
@@ -115,10 +115,10 @@ def _worker_lazy(rank, world, port, q):
     pred = PS._predict_flip_rows(records, mine, fd0, cfg, 24, carry_in=False, margin=-0.3)
     table = _FakeLazyTable(P, Fl, pred)
     predicted = int(table.flip_ready.sum())
-    merged, new_table, allp, allf = PS._gather_shards(None, records, table, P, None, world, None)
+    new_table, allp, allf, enc = PS._gather_shards(None, PS.encode_records(records, mine, len(P)), table, P, None, world, None)
     log = []
-    trk, bank = PS.replay(merged, new_table, (allp, None), idxs, 24, n, T.FakeFace(sc), ref, cfg, log=log,
-                          distances=_TableDistances(allp, new_table))
+    trk, bank = PS.replay(None, new_table, (allp, None), idxs, 24, n, T.FakeFace(sc), ref, cfg, log=log,
+                          distances=_TableDistances(allp, new_table), encoded=enc)
     q.put((rank, trk.finish(), [(r["idx"], r["skip"], round(r["best"], 6)) for r in log], len(bank), predicted, table.computed,
            int(new_table.flip_ready.sum()), new_table.count))
     dist.destroy_process_group()

@@ -157,14 +157,20 @@ def test_replay_matches_reference_loop(seed, stride, bank_max):
     OP.prescan(frame, 24, n, FakeFace(sc), ref_feat, cfg, log=olog)
 
     records, P, Fl = to_records(sc)
-    face = FakeFace(sc)
-    glog = []
     idxs = PS.sample_indices(n, stride)
-    trk, bank = PS.replay(records, None, (P, Fl), idxs, 24, n, face, ref_feat, cfg, log=glog, distances=NumpyDistances(P, Fl))
-    assert len(glog) == len(olog)
-    for g, o in zip(glog, olog):
-        assert g["idx"] == o["idx"] and g["skip"] == o["skip"] and g["active_before"] == o["active_before"], (g, o)
-        assert g["nfaces"] == o["nfaces"] and abs(g["best"] - o["best"]) < 1e-6, (g, o)
+    results = {}
+    for native in (True, False):       # pcb_replay (libpcb200, flat arrays) and the pure-Python statement of the same loop
+        face = FakeFace(sc)
+        glog = []
+        trk, bank = PS.replay(records, None, (P, Fl), idxs, 24, n, face, ref_feat, cfg, log=glog, distances=NumpyDistances(P, Fl),
+                              native=native)
+        assert len(glog) == len(olog)
+        for g, o in zip(glog, olog):
+            assert g["idx"] == o["idx"] and g["skip"] == o["skip"] and g["active_before"] == o["active_before"], (native, g, o)
+            assert g["nfaces"] == o["nfaces"] and abs(g["best"] - o["best"]) < 1e-6, (native, g, o)
+        results[native] = (trk.finish(), len(bank), face._prescan_rr, face._frame_idx, face._no_face_streak,
+                           [(g["idx"], g["skip"], g["best"]) for g in glog])
+    assert results[True] == results[False]
     assert any(r["active_before"] for r in olog) and any(r["skip"] for r in olog)
 
 
