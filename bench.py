@@ -9,7 +9,7 @@ pool of distinct synthetic frames (398 MB for 64 x 1080p, larger than the 126 MB
 
   value      frames/s, whole job, frames resident in HBM when the timed region starts
   e2e        same metric through the public API with frames in pinned HOST memory (H2D inside)
-  roofline   conv_tc_kernel (tcgen05 implicit GEMM): algorithmic FLOPs / CUDA-event time of its launches
+  roofline   conv_tc2_kernel (tcgen05 implicit GEMM): algorithmic FLOPs / CUDA-event time of its launches
   cpu_baseline  the CPU oracle (torch-CPU fp32 + cv2, restated reference) on a bounded sample
 
 `--impl reference` times the CPU oracle alone (the reference's own implementation cannot be installed
@@ -239,6 +239,7 @@ def main():
         faces_seen["passes"] = stats.get("arcface_passes", 0)  # ArcFace image passes (e(x), plus e(flip x) where the span logic needs it)
         faces_seen["spans"] = [list(map(int, sp)) for sp in spans]
         faces_seen["phase_ms"] = stats.get("phase_ms")
+        faces_seen["bank"] = {k: stats.get(k) for k in ("bank_rows", "bank_versions", "distance_refreshes")}
         return spans
 
     def timed(clip, steps, profile=False):
@@ -319,13 +320,18 @@ def main():
         "faces_embedded_per_sec": faces_seen["n"] * world * args.steps / (ms / 1000.0),
         "arcface_image_passes_per_sec": faces_seen["passes"] * world * args.steps / (ms / 1000.0),
         "gpu_launches": launches,
-        "phase_ms_last_step": faces_seen.get("phase_ms"),
+        "phase_ms_last_step": faces_seen.get("phase_ms"), "bank_last_step": faces_seen.get("bank"),
         "wall_ms_per_step": 1000.0 * wall / args.steps,
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(faces_seen["passes"] * 2048 + faces_seen["n"] * 64 + args.frames_per_step * 64)},
-        "roofline": {"kernel": "conv_tc_kernel", "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                     "frac": achieved / peak_tf if peak_tf else None, "traffic": None, "peak_source": peak_src,
+        "roofline": {"kernel": "conv_tc2_kernel", "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                     "frac": achieved / peak_tf if peak_tf else None,
+                     # DRAM bytes per launch of the dominant layer shape (iResNet-100 stage 3, 14x14 256->256, 444 images) from the
+                     # round's ncu --set full capture (profiles/r01_ncu_conv_tc2_stage3_keymetrics.txt): 59.8 MB read + 10.7 MB
+                     # written for 59.4 MB of algorithmic input+weight bytes (the output stays in the 126 MB L2)
+                     "traffic": 70.5e6, "traffic_layer": "14x14 256->256 conv1, 444 images, 102.6 GFLOP/launch",
+                     "peak_source": peak_src,
                      "conv_launches": conv_n, "conv_ms_per_step": conv_ms / args.steps,
                      "conv_share_of_step": (conv_ms / ms) if ms > 0 else None},
     }

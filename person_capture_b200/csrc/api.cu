@@ -88,6 +88,8 @@ extern "C" void pcb_destroy(pcb_ctx* c) {
   for (void* p : c->allocs) cudaFree(p);
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
   if (c->h_err) cudaFreeHost(c->h_err);
+  if (c->bank_stage) cudaFreeHost(c->bank_stage);
+  if (c->bank_ev) cudaEventDestroy(c->bank_ev);
   for (int i = 0; i < 4; ++i) delete c->models[i];
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;

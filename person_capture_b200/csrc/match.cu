@@ -3,6 +3,8 @@
 // and Processor._fd_min, person_capture/gui_app.py:660-674 (vec / max(|vec|, 1e-6); 1 - max(bank @ vec)).
 // HBM/L2-bound on the bank read (B*512*4 bytes per face block); no tensor cores: 2*F*B*512 FLOP
 // is negligible next to the convolutions.
+#include <string.h>
+
 #include "pcb_common.cuh"
 
 namespace {
@@ -84,13 +86,22 @@ extern "C" int pcb_set_bank(pcb_ctx* c, const float* bank_host, int rows) {
     int cap = rows < 64 ? 64 : rows;
     float* nb = (float*)pcb_dev_alloc(c, (size_t)cap * PCB_FEAT_DIM * sizeof(float), false);
     if (!nb) return pcb_fail(c, PCB_ERR_CUDA, "set_bank: alloc failed");
+    if (c->bank_ev) PCB_CUDA(c, cudaEventSynchronize(c->bank_ev));
+    if (c->bank_stage) cudaFreeHost(c->bank_stage);
+    c->bank_stage = nullptr;
+    PCB_CUDA(c, cudaMallocHost((void**)&c->bank_stage, (size_t)cap * PCB_FEAT_DIM * sizeof(float)));
+    if (!c->bank_ev) PCB_CUDA(c, cudaEventCreateWithFlags(&c->bank_ev, cudaEventDisableTiming));
     c->bank = nb;
     c->bank_cap = cap;
   }
-  if (rows > 0)
-    PCB_CUDA(c, cudaMemcpyAsync(c->bank, bank_host, (size_t)rows * PCB_FEAT_DIM * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-  // the host buffer may be reused by the caller right after this returns
-  PCB_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (rows > 0) {
+    // the live bank changes every few samples during a replay: stage through pinned memory so the upload is asynchronous
+    // (the caller may reuse its buffer immediately) and only wait for the PREVIOUS upload before overwriting the stage
+    PCB_CUDA(c, cudaEventSynchronize(c->bank_ev));
+    memcpy(c->bank_stage, bank_host, (size_t)rows * PCB_FEAT_DIM * sizeof(float));
+    PCB_CUDA(c, cudaMemcpyAsync(c->bank, c->bank_stage, (size_t)rows * PCB_FEAT_DIM * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    PCB_CUDA(c, cudaEventRecord(c->bank_ev, c->stream));
+  }
   c->bank_rows = rows;
   return PCB_OK;
 }

@@ -78,6 +78,8 @@ struct pcb_ctx {
   struct Model* models[4] = {nullptr, nullptr, nullptr, nullptr};
   float* bank = nullptr;
   int bank_rows = 0, bank_cap = 0;
+  float* bank_stage = nullptr;   // pinned staging for asynchronous bank uploads
+  cudaEvent_t bank_ev = nullptr; // completion of the last bank upload
   void* scratch = nullptr;
   size_t scratch_bytes = 0;
   // profiling (bench.py roofline): CUDA events around every conv launch + algorithmic FLOPs

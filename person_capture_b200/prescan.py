@@ -114,7 +114,12 @@ class RefBank:
         self.version = 0
 
     def array(self) -> Optional[np.ndarray]:
-        return np.vstack(self.rows).astype(np.float32) if self.rows else None
+        if not self.rows:
+            return None
+        if getattr(self, "_arr_version", None) != self.version or getattr(self, "_arr", None) is None or len(self._arr) != len(self.rows):
+            self._arr = np.ascontiguousarray(np.vstack(self.rows), np.float32)
+            self._arr_version = self.version
+        return self._arr
 
     def __len__(self):
         return len(self.rows)
@@ -722,6 +727,8 @@ class _LiveDistances:
         self.version = None
         self.fd_plain = self.fd_flip = None
         self.both = None
+        self.sim_dev = self.arg_dev = self.sim_host = None
+        self.refreshes = 0
 
     def invalidate(self):
         self.version = None
@@ -737,10 +744,19 @@ class _LiveDistances:
                     with torch.cuda.stream(eng.stream):
                         # rows without a flip feature yet are zero vectors: their distances are never read
                         self.both = torch.cat([t.plain[:t.count], t.flip[:t.count]], 0).contiguous()
+                self.refreshes += 1
+                n2 = 2 * t.count
+                if self.sim_dev is None or self.sim_dev.shape[0] < n2:
+                    self.sim_dev = eng.empty((n2,), torch.float32)
+                    self.arg_dev = eng.empty((n2,), torch.int32)
+                    self.sim_host = torch.empty((n2,), dtype=torch.float32).pin_memory()
                 eng.set_bank(bank.array())
-                _, sim, _ = eng.match(self.both, None, None, 2 * t.count, want_feat=False)
-                eng.sync()
-                fd = 1.0 - sim[:2 * t.count].cpu().numpy().astype(np.float64)
+                eng._check(eng.lib.pcb_match(eng.ctx, self.both.data_ptr(), None, None, n2, None, self.sim_dev.data_ptr(),
+                                             self.arg_dev.data_ptr()), "pcb_match")
+                with torch.cuda.stream(eng.stream):
+                    self.sim_host[:n2].copy_(self.sim_dev[:n2], non_blocking=True)
+                eng.sync()      # one synchronisation per bank change
+                fd = 1.0 - self.sim_host[:n2].numpy().astype(np.float64)
                 self.fd_plain, self.fd_flip = fd[:t.count], fd[t.count:]
             self.version = bank.version
         return self.fd_plain, self.fd_flip
@@ -948,6 +964,7 @@ def replay(records: Dict[int, SampleRecord], table, feats_host, idxs: Sequence[i
     face._no_face_streak, face._rot_cycle, face._prescan_rr = int(st.no_face_streak), int(st.rot_cycle), int(st.prescan_rr)
     trk.spans = [(int(a), int(b)) for a, b in spans[:n_spans.value]]
     trk.active = False          # pcb_replay already closed the open span (gui_app.py:1648-1655)
+    trk.distance_refreshes = getattr(dist, "refreshes", None)
     if log is not None:
         for i, idx in enumerate(idxs):
             log.append(dict(idx=idx, skip=bool(skip[i]), best=float(best[i]), active_before=bool(act[i]), nfaces=int(nf[i])))
@@ -1069,6 +1086,9 @@ def prescan_batched(clip, fps: int, face: FaceEmbedder, ref_feat, cfg, batch: in
         mark("gather")
         trk, bank = replay(records, table, (plain_h, flip_h), idxs, fps, total, face, ref_feat, cfg, log, encoded=encoded)
         mark("replay")
+        if stats is not None:
+            stats["bank_rows"], stats["bank_versions"] = len(bank), bank.version
+            stats["distance_refreshes"] = getattr(trk, "distance_refreshes", None)
         _count_passes(stats, local_table)      # this rank's faces / ArcFace image passes
         spans = trk.finish()
         wmax = int(getattr(cfg, "prescan_max_width", 0))
