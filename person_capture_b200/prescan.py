@@ -142,7 +142,7 @@ class RefBank:
             self.rows.append(v)
             self.version += 1
             return "added"
-        B = np.vstack(self.rows).astype(np.float32)
+        B = self.array()              # cached float32 stack of the rows (same values np.vstack(...).astype(float32) gives)
         sims = B @ v
         top = float(sims.max())
         if top >= dedup:
@@ -538,6 +538,9 @@ class FaceTable:
         self.pending: List[torch.Tensor] = []
         self.pending_n = 0
         self.count = 0
+        self.q_parts: List[np.ndarray] = []    # per-row quality / box area in row order (flat records for pcb_replay)
+        self.a_parts: List[np.ndarray] = []
+        self.encoded = None
         self.flip_passes = 0          # faces that went through the flip pass (bench: ArcFace image passes / s)
 
     def queue(self, eng, chips: torch.Tensor, k: int) -> np.ndarray:
@@ -622,10 +625,12 @@ class FaceTable:
         return True
 
 
-def _collect_variant(eng, frames, det, idx_list, records, key, table: FaceTable, max_faces: int):
-    """Align every accumulated face of `det` (batch over idx_list) and queue its chip for embedding."""
-    al = eng.align(frames, det, max_faces=max_faces)
-    eng.sync()
+def _collect_variant(eng, frames, det, idx_list, records, key, table: FaceTable, max_faces: int, al=None):
+    """Align every accumulated face of `det` (batch over idx_list) and queue its chip for embedding.  `al`: the align
+    result if the caller already enqueued it and waited for it."""
+    if al is None:
+        al = eng.align(frames, det, max_faces=max_faces)
+        eng.sync()
     total = int(al.face_total.cpu()[0])
     counts = al.face_count.cpu().numpy()
     if total == 0:
@@ -633,6 +638,9 @@ def _collect_variant(eng, frames, det, idx_list, records, key, table: FaceTable,
     rows = table.queue(eng, al.chips, total)
     boxes = al.face_box[:total].cpu().numpy()
     qual = al.quality[:total].cpu().numpy()
+    b64 = boxes.astype(np.int64)
+    table.q_parts.append(qual.astype(np.float64))
+    table.a_parts.append((b64[:, 2] - b64[:, 0]) * (b64[:, 3] - b64[:, 1]))
     off = 0
     for b, sidx in enumerate(idx_list):
         k = int(counts[b])
@@ -648,7 +656,11 @@ def _collect_variant(eng, frames, det, idx_list, records, key, table: FaceTable,
 def compute_superset(clip, idxs: Sequence[int], face: FaceEmbedder, cfg, batch: int = 32, max_faces: int = 4096,
                      lazy_flip: bool = False):
     """GPU stage of the batched pre-scan for the samples `idxs` (fast pre-scan settings must be active).
-    lazy_flip: compute e(flip x) later, only for the faces the replay evaluates while a span is active."""
+    lazy_flip: compute e(flip x) later, only for the faces the replay evaluates while a span is active.
+
+    Software-pipelined over frame batches: the upright SCRFD pass and K4 of batch k+1 are enqueued before the host waits
+    (on an event, not a stream sync) for batch k's counts, so the SMs never wait for the host's bookkeeping; host frames of
+    batch k+2 cross PCIe meanwhile on the copy stream."""
     eng = face.engine
     wmax = int(getattr(cfg, "prescan_max_width", 0))
     records: Dict[int, SampleRecord] = {}
@@ -656,22 +668,26 @@ def compute_superset(clip, idxs: Sequence[int], face: FaceEmbedder, cfg, batch: 
     chunks = [list(idxs[b0:b0 + batch]) for b0 in range(0, len(idxs), batch)]
     prefetch = bool(getattr(clip, "host_resident", False))
 
-    def fetch(chunk):
-        """Issue the H2D copy of a batch on the copy stream; -> (frames, event that marks its completion)."""
+    def fetch(ci):
+        """Issue the H2D copy of batch ci on the copy stream; -> (frames, event that marks its completion)."""
+        if not prefetch or ci >= len(chunks):
+            return None
         with torch.cuda.stream(eng.copy_stream):
-            fr = clip.device_batch(eng, chunk, stream=eng.copy_stream)
+            fr = clip.device_batch(eng, chunks[ci], stream=eng.copy_stream)
             ev = torch.cuda.Event()
             ev.record(eng.copy_stream)
         return fr, ev
 
-    pending = fetch(chunks[0]) if (prefetch and chunks) else None
-    for ci, chunk in enumerate(chunks):
+    fetched = {0: fetch(0)}
+
+    def issue(ci):
+        """Enqueue K0 + upright SCRFD + K4 of batch ci; nothing here waits for the GPU."""
+        chunk = chunks[ci]
         if prefetch:
-            frames, ev = pending
+            frames, ev = fetched.pop(ci)
             eng.stream.wait_event(ev)
             frames.record_stream(eng.stream)
-            # the next batch crosses PCIe while this one is on the SMs
-            pending = fetch(chunks[ci + 1]) if ci + 1 < len(chunks) else None
+            fetched[ci + 1] = fetch(ci + 1)
         else:
             frames = clip.device_batch(eng, chunk)
         n, h, w, _ = frames.shape
@@ -680,15 +696,45 @@ def compute_superset(clip, idxs: Sequence[int], face: FaceEmbedder, cfg, batch: 
             frames = eng.resize(frames, nh, nw, area=True)
             h, w = nh, nw
         dyn = face.upright_size(h, w, None)
-        heavy90, heavy180 = face.heavy_sizes(h, w, dyn)
+        det0 = eng.detect(frames, dyn, face.conf, min_box=int(face.scrfd_min_box_px), max_det=face.max_det)
+        al = eng.align(frames, det0, max_faces=max_faces)
+        done = torch.cuda.Event()
+        done.record(eng.stream)
+        return dict(chunk=chunk, frames=frames, h=h, w=w, dyn=dyn, det0=det0, al=al, done=done)
+
+    meta_parts: List[np.ndarray] = []
+
+    def encode_chunk(chunk):
+        # flat pcb_replay records of a finished chunk; runs while the next batch is on the SMs
+        m = np.zeros((len(chunk), L.REPLAY_META), np.int32)
+        m[:, 0] = m[:, 6] = m[:, 8] = -1
+        for s_i, idx in enumerate(chunk):
+            rec = records[idx]
+            if rec.up is not None:
+                m[s_i, 0], m[s_i, 1] = rec.up.rows[0], len(rec.up.rows)
+            if rec.hits or rec.heavy:
+                for d, deg in enumerate((90, 270)):
+                    m[s_i, 2 + d] = rec.hits.get(deg, 0)
+                    m[s_i, 4 + d] = rec.heavy_raw.get(deg, 0)
+                    if deg in rec.heavy:
+                        m[s_i, 6 + 2 * d], m[s_i, 7 + 2 * d] = rec.heavy[deg].rows[0], len(rec.heavy[deg].rows)
+        meta_parts.append(m)
+
+    cur = issue(0) if chunks else None
+    for ci in range(len(chunks)):
+        nxt = issue(ci + 1) if ci + 1 < len(chunks) else None
+        cur["done"].synchronize()
+        chunk, frames, dyn, det0 = cur["chunk"], cur["frames"], cur["dyn"], cur["det0"]
+        n = frames.shape[0]
+        heavy90, heavy180 = face.heavy_sizes(cur["h"], cur["w"], dyn)
         for i in chunk:
             records[i] = SampleRecord(i)
-        det0 = eng.detect(frames, dyn, face.conf, min_box=int(face.scrfd_min_box_px), max_det=face.max_det)
-        eng.sync()
         acc0 = det0.acc_count.cpu().numpy()
-        _collect_variant(eng, frames, det0, chunk, records, "up", table, max_faces)
+        _collect_variant(eng, frames, det0, chunk, records, "up", table, max_faces, al=cur["al"])
         empty = [b for b in range(n) if acc0[b] == 0]
+        cur = nxt
         if not empty:
+            encode_chunk(chunk)
             continue
         with torch.cuda.stream(eng.stream):
             sub = frames.index_select(0, torch.as_tensor(empty, device=frames.device)).contiguous()
@@ -713,7 +759,11 @@ def compute_superset(clip, idxs: Sequence[int], face: FaceEmbedder, cfg, batch: 
             for j, sidx in enumerate(sel_idx):
                 records[sidx].heavy_raw[deg] = int(raw[j])
             _collect_variant(eng, sub2, hv, sel_idx, records, deg, table, max_faces)
+        encode_chunk(chunk)
     table.finalize(eng)
+    one = lambda parts, dt: np.concatenate(parts).astype(dt) if parts else np.zeros(1, dt)
+    table.encoded = (np.concatenate(meta_parts, 0) if meta_parts else np.zeros((0, L.REPLAY_META), np.int32),
+                     one(table.q_parts, np.float64), one(table.a_parts, np.int64))
     return records, table
 
 
@@ -1078,10 +1128,9 @@ def prescan_batched(clip, fps: int, face: FaceEmbedder, ref_feat, cfg, batch: in
         plain_h = table.plain[:table.count].cpu().numpy() if table.count else np.zeros((0, L.FEAT_DIM), np.float32)
         flip_h = (table.flip[:table.count].cpu().numpy() if (table.count and not lazy) else np.zeros((0, L.FEAT_DIM), np.float32))
         local_table = table
-        encoded = None
+        encoded = table.encoded       # flat records built chunk by chunk during the GPU stage
         if world > 1:
-            enc_local = encode_records(records, mine, table.count)
-            table, plain_h, flip_h, encoded = _gather_shards(eng, enc_local, table, plain_h, flip_h, world, dist_group)
+            table, plain_h, flip_h, encoded = _gather_shards(eng, encoded, table, plain_h, flip_h, world, dist_group)
             records = None
         mark("gather")
         trk, bank = replay(records, table, (plain_h, flip_h), idxs, fps, total, face, ref_feat, cfg, log, encoded=encoded)
