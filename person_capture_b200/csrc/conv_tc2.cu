@@ -134,9 +134,10 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* e
   return true;
 }
 
-// mbar_wait that also accumulates the cycles spent waiting (debug instrumentation of block 0)
-__device__ __forceinline__ bool mbar_wait_t(uint64_t* bar, uint32_t parity, int* err, int code, long long& acc) {
-  if (mbar_try_wait(bar, parity)) return true;
+// mbar_wait that also accumulates the cycles spent waiting (debug instrumentation of block 0).  The first try_wait is
+// timed too: mbarrier.try_wait may suspend the thread inside the instruction before it reports success.
+__device__ __forceinline__ bool mbar_wait_t(uint64_t* bar, uint32_t parity, int* err, int code, long long& acc, bool timed) {
+  if (!timed) return mbar_wait(bar, parity, err, code);
   const long long t0 = clock64();
   const bool ok = mbar_wait(bar, parity, err, code);
   acc += clock64() - t0;
@@ -334,7 +335,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int mt_idx = tile / p.n_tiles;
         const int m0 = mt_idx * tile_rows;
         for (int kc = 0; kc < p.kchunks; ++kc) {
-          ok = __all_sync(0xffffffffu, mbar_wait_t(&a_empty[stage], phase ^ 1, p.err, 101, w_empty));
+          ok = __all_sync(0xffffffffu, mbar_wait_t(&a_empty[stage], phase ^ 1, p.err, 101, w_empty, p.dbg != nullptr));
           if (!ok) break;
           if (elect_one()) {
             const uint32_t sa = smem_u32(smem_a + (size_t)stage * p.a_stage_bytes);
@@ -378,7 +379,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           const int n0 = nt * p.n_tile;
           for (int ks = 0; ks < ksteps; ++ks) {
             const int kc = ks / p.taps, t = ks - kc * p.taps;
-            ok = __all_sync(0xffffffffu, mbar_wait_t(&b_empty[stage], phase ^ 1, p.err, 105, w_empty));
+            ok = __all_sync(0xffffffffu, mbar_wait_t(&b_empty[stage], phase ^ 1, p.err, 105, w_empty, p.dbg != nullptr));
             if (!ok) break;
             if (elect_one()) {
               mbar_expect_tx(&b_full[stage], (uint32_t)p.b_bytes);
@@ -406,19 +407,19 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       bool b_loaded = false;
       long long w_a = 0, w_b = 0, w_t = 0;
       for (int tile = blockIdx.x; ok && tile < total_tiles; tile += gridDim.x) {
-        ok = __all_sync(0xffffffffu, mbar_wait_t(&tempty_bar[acc], acc_phase ^ 1, p.err, 102, w_t));
+        ok = __all_sync(0xffffffffu, mbar_wait_t(&tempty_bar[acc], acc_phase ^ 1, p.err, 102, w_t, p.dbg != nullptr));
         if (!ok) break;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
         for (int kc = 0; ok && kc < p.kchunks; ++kc) {
-          ok = __all_sync(0xffffffffu, mbar_wait_t(&a_full[a_stage], a_phase, p.err, 103, w_a));
+          ok = __all_sync(0xffffffffu, mbar_wait_t(&a_full[a_stage], a_phase, p.err, 103, w_a, p.dbg != nullptr));
           if (!ok) break;
           const uint32_t sa = smem_u32(smem_a + (size_t)a_stage * p.a_stage_bytes);
           const int kinstr = (kc == p.kchunks - 1) ? p.kinstr_last : kKC / 16;
           for (int t = 0; t < p.taps; ++t) {
             const int slot = p.b_resident ? kc * p.taps + t : b_stage;
             if (!p.b_resident || !b_loaded) {
-              ok = __all_sync(0xffffffffu, mbar_wait_t(&b_full[slot], p.b_resident ? 0u : b_phase, p.err, 106, w_b));
+              ok = __all_sync(0xffffffffu, mbar_wait_t(&b_full[slot], p.b_resident ? 0u : b_phase, p.err, 106, w_b, p.dbg != nullptr));
               if (!ok) break;
             }
             tc_fence_after();
@@ -506,7 +507,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           }
         }
       }
-      if (ok) ok = mbar_wait_t(&tfull_bar[acc], acc_phase, p.err, 104, w_full);
+      if (ok) ok = mbar_wait_t(&tfull_bar[acc], acc_phase, p.err, 104, w_full, p.dbg != nullptr);
       ok = __all_sync(0xffffffffu, ok);
       if (!ok) break;
       tc_fence_after();
@@ -714,13 +715,16 @@ bool plan_a(Conv2Params& p, int mt, int* a2_rows) {
     return true;
   }
   const int halo = p.wp + 1;
-  const int merged_extra = pcb_round_up(2 * halo, 8);
+  // merged: one contiguous halo range = mt 128-row boxes + the 2*halo extra rows as one or two small boxes (<= 256 rows each)
+  const int merged_extra = pcb_round_up(2 * halo, 16);
+  const int n_small = merged_extra <= 256 ? 1 : 2;
   const long long merged_rows = (long long)mt * kBlockM + merged_extra;
   const long long banded_rows = 3LL * (mt * kBlockM + 8);
-  if (merged_extra <= 256 && merged_rows <= banded_rows) {
+  if (merged_extra <= 512 && merged_rows <= banded_rows) {
     for (int j = 0; j < mt; ++j) add(-halo + j * kBlockM, j * kSubBytes, 0);
-    add(-halo + mt * kBlockM, mt * kSubBytes, 1);
-    *a2_rows = merged_extra;
+    const int small = merged_extra / n_small;
+    for (int sidx = 0; sidx < n_small; ++sidx) add(-halo + mt * kBlockM + sidx * small, (mt * kBlockM + sidx * small) * 128, 1);
+    *a2_rows = small;
     for (int t = 0; t < 9; ++t) p.tap_off[t] = (halo + (t / 3 - 1) * p.wp + (t % 3 - 1)) * 128;
     p.a_tx_bytes = (int)merged_rows * 128;
     p.a_stage_bytes = pcb_round_up(p.a_tx_bytes, 1024);

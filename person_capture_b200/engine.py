@@ -236,7 +236,12 @@ class Engine:
                                            emb_flip.data_ptr() if emb_flip is not None else None), "pcb_embed")
         return emb, emb_flip
 
-    def set_bank(self, bank: Optional[np.ndarray]):
+    def set_bank(self, bank: Optional[np.ndarray], token=None):
+        """Upload the reference bank.  `token` (any hashable, e.g. (id(bank_object), version)): skip the upload when the
+        bank on the device already carries it -- a 10 000-row bank is 20 MB."""
+        if token is not None and token == getattr(self, "_bank_token", None):
+            return
+        self._bank_token = token
         if bank is None or np.asarray(bank).size == 0:
             self._check(self.lib.pcb_set_bank(self.ctx, None, 0), "pcb_set_bank")
             self.bank_rows = 0

@@ -321,8 +321,8 @@ def _fds_for_last_faces(face: FaceEmbedder, bank: RefBank) -> np.ndarray:
     eng = face.engine
     feats = face.last_feats_dev
     f = face.last_face_count
-    eng.set_bank(bank.array())
-    _, sim, _ = eng.match(feats, None, None, f)
+    eng.set_bank(bank.array(), token=(id(bank), bank.version))
+    _, sim, _ = eng.match(feats, None, None, f, want_feat=False)
     eng.sync()
     return 1.0 - sim[:f].cpu().numpy().astype(np.float64)
 
