@@ -36,12 +36,11 @@ namespace {
 
 constexpr int kBlockM = 128;
 constexpr int kKC = 64;                       // K elements per weight stage (one 128B swizzle atom)
-constexpr int kSubBytes = kBlockM * kKC * 2;  // 16 KB: one 128-row x 64-channel A sub-tile
 constexpr int kThreads = 352;
 constexpr int kEpiWarp0 = 3;
 constexpr int kEpiWarps = 8;
 constexpr uint32_t kTmemCols = 512;
-constexpr int kMaxA = 3;
+constexpr int kMaxA = 6;
 constexpr int kMaxB = 18;
 constexpr int kMaxALoads = 12;
 constexpr int kSmemBudget = 224 * 1024;
@@ -56,8 +55,11 @@ struct Conv2Params {
   int rows;        // input rows (N*(H+2)*(W+2)) or dense rows
   int hp, wp;      // input padded dims; 0 for dense
   int taps;        // 9 or 1
-  int kchunks;     // ceil(cin_eff / 64)
-  int kinstr_last; // 16-channel MMA steps in the last chunk (1..4)
+  int kchunks;     // ceil(cin_eff / kc)
+  int kinstr_last; // 16-channel MMA steps in the last chunk (1..kc/16)
+  int kc;          // K elements per stage: 64 (128-byte swizzled rows) or 32 (64-byte rows, layers with <= 32 input channels)
+  int row_bytes;   // shared-memory row pitch of an operand tile: 2 * kc
+  int sub_bytes;   // one 128-row A sub-tile: 128 * row_bytes
   int cin_w;       // packed weight K extent per tap
   int n_tile, n_tiles, m_tiles;   // m_tiles counts tiles of mt*128 rows
   int mt;          // 128-row sub-tiles per CTA tile
@@ -201,11 +203,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 // tensor core applies the 128B swizzle to ABSOLUTE shared-memory address bits (the same rule TMA writes
 // with), so a row-shifted start needs base-offset 0; setting base-offset = (addr >> 7) & 7 double-counts
 // the phase and gives wrong sums (desc_mode 0 is kept only to reproduce that experiment).
-__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr, int desc_mode) {
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr, int desc_mode, bool sw64 = false) {
+  // sw64: rows of 64 bytes (32 fp16 of K), 64B swizzle, 8-row groups 512 bytes apart -- layers with <= 32 input channels
   uint64_t lo = (uint64_t)((saddr >> 4) & 0x3fff);             // start address, LBO = 0
-  uint64_t hi = (uint64_t)(1024 >> 4)                           // SBO
+  uint64_t hi = (uint64_t)((sw64 ? 512 : 1024) >> 4)            // SBO
                 | (1ull << 14)                                  // descriptor version 1 (sm_100)
-                | (2ull << 29);                                 // layout type: SWIZZLE_128B
+                | ((sw64 ? 4ull : 2ull) << 29);                 // layout type: SWIZZLE_64B / SWIZZLE_128B
   if (desc_mode == 0) hi |= (uint64_t)((saddr >> 7) & 7) << 17; // base offset, bits 49-51
   return lo | (hi << 32);
 }
@@ -342,7 +345,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             mbar_expect_tx(&a_full[stage], (uint32_t)p.a_tx_bytes);
             for (int l = 0; l < p.n_aloads; ++l) {
               const ALoad ld = p.aloads[l];
-              tma_load_2d(ld.map2 ? &tmA2 : &tmA, &a_full[stage], sa + ld.smem_off, kc * kKC, m0 + ld.row_rel);
+              tma_load_2d(ld.map2 ? &tmA2 : &tmA, &a_full[stage], sa + ld.smem_off, kc * p.kc, m0 + ld.row_rel);
             }
           }
           __syncwarp();
@@ -366,7 +369,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           for (int ks = 0; ks < ksteps; ++ks) {
             const int kc = ks / p.taps, t = ks - kc * p.taps;
             mbar_expect_tx(&b_full[ks], (uint32_t)p.b_bytes);
-            tma_load_2d(&tmB, &b_full[ks], smem_u32(smem_b + (size_t)ks * p.b_bytes), t * p.cin_w + kc * kKC, 0);
+            tma_load_2d(&tmB, &b_full[ks], smem_u32(smem_b + (size_t)ks * p.b_bytes), t * p.cin_w + kc * p.kc, 0);
           }
         }
         __syncwarp();
@@ -383,7 +386,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             if (!ok) break;
             if (elect_one()) {
               mbar_expect_tx(&b_full[stage], (uint32_t)p.b_bytes);
-              tma_load_2d(&tmB, &b_full[stage], smem_u32(smem_b + (size_t)stage * p.b_bytes), t * p.cin_w + kc * kKC, n0);
+              tma_load_2d(&tmB, &b_full[stage], smem_u32(smem_b + (size_t)stage * p.b_bytes), t * p.cin_w + kc * p.kc, n0);
             }
             __syncwarp();
             if (++stage == p.b_stages) { stage = 0; phase ^= 1; }
@@ -415,7 +418,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           ok = __all_sync(0xffffffffu, mbar_wait_t(&a_full[a_stage], a_phase, p.err, 103, w_a, p.dbg != nullptr));
           if (!ok) break;
           const uint32_t sa = smem_u32(smem_a + (size_t)a_stage * p.a_stage_bytes);
-          const int kinstr = (kc == p.kchunks - 1) ? p.kinstr_last : kKC / 16;
+          const int kinstr = (kc == p.kchunks - 1) ? p.kinstr_last : p.kc / 16;
           for (int t = 0; t < p.taps; ++t) {
             const int slot = p.b_resident ? kc * p.taps + t : b_stage;
             if (!p.b_resident || !b_loaded) {
@@ -424,10 +427,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
             tc_fence_after();
             if (elect_one()) {
-              const uint64_t db = make_desc_sw128(smem_u32(smem_b + (size_t)slot * p.b_bytes), 1);
+              const uint64_t db = make_desc_sw128(smem_u32(smem_b + (size_t)slot * p.b_bytes), 1, p.kc == 32);
               const uint32_t first = (kc | t) != 0 ? 1u : 0u;
               for (int j = 0; j < p.mt; ++j) {
-                const uint64_t da = make_desc_sw128(sa + (uint32_t)p.tap_off[t] + (uint32_t)(j * kSubBytes), p.desc_mode);
+                const uint64_t da = make_desc_sw128(sa + (uint32_t)p.tap_off[t] + (uint32_t)(j * p.sub_bytes), p.desc_mode, p.kc == 32);
                 const uint32_t d = d_tmem + (uint32_t)(j * p.sub_cols);
                 // advance 16 elements (32 bytes) along K inside the swizzle atom; all-zero K slices are skipped
                 umma_f16(d, da, db, idesc, first);
@@ -678,15 +681,16 @@ EncodeTiledFn get_encode() {
 }
 
 // 2-D fp16 map over a row-major [rows][cols] matrix with a {64, box_rows} box, 128B swizzle.
-bool make_map_2d(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_elems, uint32_t box_rows) {
+bool make_map_2d(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_elems, uint32_t box_rows,
+                 int kc = kKC) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return false;
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {row_stride_elems * 2};
-  cuuint32_t box[2] = {(cuuint32_t)kKC, box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)kc, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
@@ -708,10 +712,10 @@ bool plan_a(Conv2Params& p, int mt, int* a2_rows) {
     return true;
   };
   if (p.taps == 1) {
-    for (int j = 0; j < mt; ++j) add(j * kBlockM, j * kSubBytes, 0);
+    for (int j = 0; j < mt; ++j) add(j * kBlockM, j * p.sub_bytes, 0);
     p.tap_off[0] = 0;
-    p.a_stage_bytes = mt * kSubBytes;
-    p.a_tx_bytes = mt * kSubBytes;
+    p.a_stage_bytes = mt * p.sub_bytes;
+    p.a_tx_bytes = mt * p.sub_bytes;
     return true;
   }
   const int halo = p.wp + 1;
@@ -721,23 +725,23 @@ bool plan_a(Conv2Params& p, int mt, int* a2_rows) {
   const long long merged_rows = (long long)mt * kBlockM + merged_extra;
   const long long banded_rows = 3LL * (mt * kBlockM + 8);
   if (merged_extra <= 512 && merged_rows <= banded_rows) {
-    for (int j = 0; j < mt; ++j) add(-halo + j * kBlockM, j * kSubBytes, 0);
+    for (int j = 0; j < mt; ++j) add(-halo + j * kBlockM, j * p.sub_bytes, 0);
     const int small = merged_extra / n_small;
-    for (int sidx = 0; sidx < n_small; ++sidx) add(-halo + mt * kBlockM + sidx * small, (mt * kBlockM + sidx * small) * 128, 1);
+    for (int sidx = 0; sidx < n_small; ++sidx) add(-halo + mt * kBlockM + sidx * small, (mt * kBlockM + sidx * small) * p.row_bytes, 1);
     *a2_rows = small;
-    for (int t = 0; t < 9; ++t) p.tap_off[t] = (halo + (t / 3 - 1) * p.wp + (t % 3 - 1)) * 128;
-    p.a_tx_bytes = (int)merged_rows * 128;
+    for (int t = 0; t < 9; ++t) p.tap_off[t] = (halo + (t / 3 - 1) * p.wp + (t % 3 - 1)) * p.row_bytes;
+    p.a_tx_bytes = (int)merged_rows * p.row_bytes;
     p.a_stage_bytes = pcb_round_up(p.a_tx_bytes, 1024);
     return true;
   }
-  const int band_bytes = pcb_round_up((mt * kBlockM + 8) * 128, 1024);
+  const int band_bytes = pcb_round_up((mt * kBlockM + 8) * p.row_bytes, 1024);
   for (int b = 0; b < 3; ++b) {
     for (int j = 0; j < mt; ++j)
-      if (!add((b - 1) * p.wp - 1 + j * kBlockM, b * band_bytes + j * kSubBytes, 0)) return false;
-    if (!add((b - 1) * p.wp - 1 + mt * kBlockM, b * band_bytes + mt * kSubBytes, 1)) return false;
+      if (!add((b - 1) * p.wp - 1 + j * kBlockM, b * band_bytes + j * p.sub_bytes, 0)) return false;
+    if (!add((b - 1) * p.wp - 1 + mt * kBlockM, b * band_bytes + mt * p.sub_bytes, 1)) return false;
   }
-  for (int t = 0; t < 9; ++t) p.tap_off[t] = (t / 3) * band_bytes + (t % 3) * 128;
-  p.a_tx_bytes = (int)banded_rows * 128;
+  for (int t = 0; t < 9; ++t) p.tap_off[t] = (t / 3) * band_bytes + (t % 3) * p.row_bytes;
+  p.a_tx_bytes = (int)banded_rows * p.row_bytes;
   p.a_stage_bytes = 3 * band_bytes;
   return true;
 }
@@ -757,8 +761,13 @@ int pcb_conv_tc2(pcb_ctx* c, const ConvArgs& a) {
   p.cin_w = w.cin_w;
   {
     const int cin_eff = in.dense ? w.cin : (w.taps == 1 && w.cin == 3) ? 27 : w.cin;   // stem: 27 patch channels
-    p.kchunks = (cin_eff + kKC - 1) / kKC;
-    p.kinstr_last = (cin_eff - (p.kchunks - 1) * kKC + 15) / 16;
+    // <= 32 input channels (SCRFD stems, patch tensors): 64-byte operand rows halve the shared memory per stage, which
+    // buys the deeper A pipeline those wide-map layers need (one K chunk per tile: a stage is only free per finished tile)
+    p.kc = (!in.dense && cin_eff <= 32 && !env_int("PCB_CONV_NO_NARROW", 0)) ? 32 : kKC;
+    p.row_bytes = 2 * p.kc;
+    p.sub_bytes = kBlockM * p.row_bytes;
+    p.kchunks = (cin_eff + p.kc - 1) / p.kc;
+    p.kinstr_last = (cin_eff - (p.kchunks - 1) * p.kc + 15) / 16;
   }
   p.n_tile = w.n_tile;
   p.n_tiles = w.npad / w.n_tile;
@@ -798,7 +807,7 @@ int pcb_conv_tc2(pcb_ctx* c, const ConvArgs& a) {
   }
   if (w.n_tile % 16 || w.n_tile > 256 || w.n_tile < 16) return pcb_fail(c, PCB_ERR_ARG, "conv_tc2: bad n_tile");
   p.sub_cols = pcb_round_up(w.n_tile, 32);
-  p.b_bytes = w.n_tile * kKC * 2;
+  p.b_bytes = w.n_tile * p.row_bytes;
   const int ksteps = p.taps * p.kchunks;
   const int fixed = 5 * p.vec_n * 4 + kEpiWarps * 2048 + (2 * kMaxA + 2 * kMaxB + 4) * 8 + 16 + 1024;
 
@@ -846,15 +855,14 @@ int pcb_conv_tc2(pcb_ctx* c, const ConvArgs& a) {
     if (p.b_stages > kMaxB) p.b_stages = kMaxB;
   }
   if (p.a_stages > kMaxA) p.a_stages = kMaxA;
-  if (p.a_stages > p.kchunks * 2 && p.a_stages > 2) p.a_stages = 2;
   const size_t smem = (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * p.b_bytes + fixed;
 
   CUtensorMap tmA, tmA2, tmB;
-  if (!make_map_2d(&tmA, in.data, (uint64_t)p.rows, (uint64_t)in.cp, (uint64_t)in.cp, kBlockM))
+  if (!make_map_2d(&tmA, in.data, (uint64_t)p.rows, (uint64_t)in.cp, (uint64_t)in.cp, kBlockM, p.kc))
     return pcb_fail(c, PCB_ERR_CUDA, "cuTensorMapEncodeTiled(A) failed");
-  if (!make_map_2d(&tmA2, in.data, (uint64_t)p.rows, (uint64_t)in.cp, (uint64_t)in.cp, (uint32_t)a2_rows))
+  if (!make_map_2d(&tmA2, in.data, (uint64_t)p.rows, (uint64_t)in.cp, (uint64_t)in.cp, (uint32_t)a2_rows, p.kc))
     return pcb_fail(c, PCB_ERR_CUDA, "cuTensorMapEncodeTiled(A2) failed");
-  if (!make_map_2d(&tmB, w.w, (uint64_t)w.npad, (uint64_t)w.taps * w.cin_w, (uint64_t)w.taps * w.cin_w, (uint32_t)w.n_tile))
+  if (!make_map_2d(&tmB, w.w, (uint64_t)w.npad, (uint64_t)w.taps * w.cin_w, (uint64_t)w.taps * w.cin_w, (uint32_t)w.n_tile, p.kc))
     return pcb_fail(c, PCB_ERR_CUDA, "cuTensorMapEncodeTiled(B) failed");
 
   const int total = p.m_tiles * p.n_tiles;

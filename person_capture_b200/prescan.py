@@ -477,16 +477,23 @@ def _refine_edges_batched(spans, clip, fps, face, bank: RefBank, ref_feat, cfg, 
     left_ids = []
     for s, e in spans:
         left_ids += list(range(s, min(e, s + search) + 1, stride_ref))
-    lhit = evaluate(left_ids)
+    # the right window starts at max(refined left edge, e - search); the refined left edge is at most s + search, so for
+    # spans with e - search >= s + search the window does not depend on the left result and both go in ONE GPU round
+    early_right = []
+    for s, e in spans:
+        if not (skip_trailing and e >= total - 1) and e - search >= s + search:
+            early_right += list(range(e - search, e + 1, stride_ref))
+    hit = evaluate(left_ids + early_right)
     lefts = []
     for s, e in spans:
-        first = next((j for j in range(s, min(e, s + search) + 1, stride_ref) if lhit[j]), None)
+        first = next((j for j in range(s, min(e, s + search) + 1, stride_ref) if hit[j]), None)
         lefts.append(max(s, first) if (first is not None and trim) else s)
     right_ids = []
     for (s, e), ls in zip(spans, lefts):
         if not (skip_trailing and e >= total - 1):
-            right_ids += list(range(max(ls, e - search), e + 1, stride_ref))
-    rhit = evaluate(right_ids)
+            right_ids += [j for j in range(max(ls, e - search), e + 1, stride_ref) if j not in hit]
+    rhit = dict(hit)
+    rhit.update(evaluate(right_ids))
     out = []
     for (s, e), ls in zip(spans, lefts):
         le = e
