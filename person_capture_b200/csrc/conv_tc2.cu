@@ -70,6 +70,14 @@ struct Conv2Params {
   int n_aloads;
   ALoad aloads[kMaxALoads];
   int tap_off[9];  // byte offset of tap t's first row inside the A stage
+  // strided mode (stride-2 convolutions): the tile is nb images x by output rows x bx output pixels (<= 128 GEMM rows),
+  // each tap is its own TMA load through a 4-D map with element strides {1,2,2,1} (only the even input pixels of the tap
+  // are fetched), so the GEMM runs on the OUTPUT grid instead of computing all input positions and dropping 3 of 4
+  int strided;
+  int s_bx, s_by, s_nb;        // output pixels / output rows / images per tile
+  int s_tx, s_ty;              // tiles per output row / per image column of rows
+  int s_n;                     // images
+  int s_ho, s_wo;              // output dims
   int desc_mode;   // 1 (product): base-offset 0; 0 (experiment): base-offset = (addr >> 7) & 7
   int stride;      // 1 | 2
   int hp_out, wp_out;
@@ -171,6 +179,13 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
       : "memory");
 }
 
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, uint32_t dst, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -229,6 +244,20 @@ struct RowInfo {
 
 __device__ __forceinline__ RowInfo row_info(const Conv2Params& p, long long prow) {
   RowInfo r;
+  if (p.strided) {
+    // prow = tile * 128 + row in tile; rows of a tile enumerate (image, output row, output pixel) of the strided box
+    const int tile = (int)(prow >> 7), rr = (int)(prow & 127);
+    const int tx = tile % p.s_tx;
+    const int ty = (tile / p.s_tx) % p.s_ty;
+    const int ig = tile / (p.s_tx * p.s_ty);
+    const int per_img = p.s_by * p.s_bx;
+    const int io = rr / per_img, rem = rr - io * per_img;
+    const int j = rem / p.s_bx, i = rem - j * p.s_bx;
+    const int img = ig * p.s_nb + io, oy = ty * p.s_by + j, ox = tx * p.s_bx + i;
+    r.valid = io < p.s_nb && img < p.s_n && oy < p.s_ho && ox < p.s_wo;
+    r.orow = ((long long)img * p.hp_out + oy + 1) * p.wp_out + ox + 1;
+    return r;
+  }
   r.valid = prow < p.rows;
   r.orow = prow;
   if (!p.dense) {
@@ -337,6 +366,27 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       for (int tile = blockIdx.x; ok && tile < total_tiles; tile += gridDim.x) {
         const int mt_idx = tile / p.n_tiles;
         const int m0 = mt_idx * tile_rows;
+        if (p.strided) {
+          // tile -> (image group, output row block, output column block); one 4-D strided load per (chunk, tap)
+          const int tx = mt_idx % p.s_tx;
+          const int ty = (mt_idx / p.s_tx) % p.s_ty;
+          const int ig = mt_idx / (p.s_tx * p.s_ty);
+          for (int kc = 0; ok && kc < p.kchunks; ++kc) {
+            for (int t = 0; t < p.taps; ++t) {
+              ok = __all_sync(0xffffffffu, mbar_wait_t(&a_empty[stage], phase ^ 1, p.err, 101, w_empty, p.dbg != nullptr));
+              if (!ok) break;
+              if (elect_one()) {
+                const int ky = p.taps == 9 ? t / 3 : 1, kx = p.taps == 9 ? t % 3 : 1;
+                mbar_expect_tx(&a_full[stage], (uint32_t)p.a_tx_bytes);
+                tma_load_4d(&tmA, &a_full[stage], smem_u32(smem_a + (size_t)stage * p.a_stage_bytes), kc * p.kc,
+                            2 * tx * p.s_bx + kx, 2 * ty * p.s_by + ky, ig * p.s_nb);
+              }
+              __syncwarp();
+              if (++stage == p.a_stages) { stage = 0; phase ^= 1; }
+            }
+          }
+          continue;
+        }
         for (int kc = 0; kc < p.kchunks; ++kc) {
           ok = __all_sync(0xffffffffu, mbar_wait_t(&a_empty[stage], phase ^ 1, p.err, 101, w_empty, p.dbg != nullptr));
           if (!ok) break;
@@ -415,11 +465,18 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
         for (int kc = 0; ok && kc < p.kchunks; ++kc) {
-          ok = __all_sync(0xffffffffu, mbar_wait_t(&a_full[a_stage], a_phase, p.err, 103, w_a, p.dbg != nullptr));
-          if (!ok) break;
-          const uint32_t sa = smem_u32(smem_a + (size_t)a_stage * p.a_stage_bytes);
+          if (!p.strided) {
+            ok = __all_sync(0xffffffffu, mbar_wait_t(&a_full[a_stage], a_phase, p.err, 103, w_a, p.dbg != nullptr));
+            if (!ok) break;
+          }
+          uint32_t sa = smem_u32(smem_a + (size_t)a_stage * p.a_stage_bytes);
           const int kinstr = (kc == p.kchunks - 1) ? p.kinstr_last : p.kc / 16;
           for (int t = 0; t < p.taps; ++t) {
+            if (p.strided) {
+              ok = __all_sync(0xffffffffu, mbar_wait_t(&a_full[a_stage], a_phase, p.err, 103, w_a, p.dbg != nullptr));
+              if (!ok) break;
+              sa = smem_u32(smem_a + (size_t)a_stage * p.a_stage_bytes);
+            }
             const int slot = p.b_resident ? kc * p.taps + t : b_stage;
             if (!p.b_resident || !b_loaded) {
               ok = __all_sync(0xffffffffu, mbar_wait_t(&b_full[slot], p.b_resident ? 0u : b_phase, p.err, 106, w_b, p.dbg != nullptr));
@@ -430,7 +487,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               const uint64_t db = make_desc_sw128(smem_u32(smem_b + (size_t)slot * p.b_bytes), 1, p.kc == 32);
               const uint32_t first = (kc | t) != 0 ? 1u : 0u;
               for (int j = 0; j < p.mt; ++j) {
-                const uint64_t da = make_desc_sw128(sa + (uint32_t)p.tap_off[t] + (uint32_t)(j * p.sub_bytes), p.desc_mode, p.kc == 32);
+                const uint64_t da = make_desc_sw128(sa + (p.strided ? 0u : (uint32_t)p.tap_off[t]) + (uint32_t)(j * p.sub_bytes), p.desc_mode, p.kc == 32);
                 const uint32_t d = d_tmem + (uint32_t)(j * p.sub_cols);
                 // advance 16 elements (32 bytes) along K inside the swizzle atom; all-zero K slices are skipped
                 umma_f16(d, da, db, idesc, first);
@@ -439,16 +496,22 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 if (kinstr > 3) umma_f16(d, da + 6, db + 6, idesc, 1u);
               }
               if (!p.b_resident) umma_commit(&b_empty[b_stage]);
+              if (p.strided) umma_commit(&a_empty[a_stage]);
             }
             __syncwarp();
             if (!p.b_resident) {
               if (++b_stage == p.b_stages) { b_stage = 0; b_phase ^= 1; }
             }
+            if (p.strided) {
+              if (++a_stage == p.a_stages) { a_stage = 0; a_phase ^= 1; }
+            }
           }
           if (!ok) break;
-          if (elect_one()) umma_commit(&a_empty[a_stage]);
-          __syncwarp();
-          if (++a_stage == p.a_stages) { a_stage = 0; a_phase ^= 1; }
+          if (!p.strided) {
+            if (elect_one()) umma_commit(&a_empty[a_stage]);
+            __syncwarp();
+            if (++a_stage == p.a_stages) { a_stage = 0; a_phase ^= 1; }
+          }
         }
         if (!ok) break;
         b_loaded = true;
@@ -695,6 +758,21 @@ bool make_map_2d(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols,
   return r == CUDA_SUCCESS;
 }
 
+// 4-D fp16 map over the P-layout [n][hp][wp][cp] for stride-2 taps: box {kc channels, 2*bx, 2*by, nb} traversed with
+// element strides {1, 2, 2, 1} -> nb * by * bx rows of kc channels in shared memory (128B / 64B swizzle as the 2-D maps).
+bool make_map_4d_s2(CUtensorMap* m, const void* base, int n, int hp, int wp, int cp, int kc, int bx, int by, int nb) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[4] = {(cuuint64_t)cp, (cuuint64_t)wp, (cuuint64_t)hp, (cuuint64_t)n};
+  cuuint64_t strides[3] = {(cuuint64_t)cp * 2, (cuuint64_t)wp * cp * 2, (cuuint64_t)hp * wp * cp * 2};
+  cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)(2 * bx), (cuuint32_t)(2 * by), (cuuint32_t)nb};
+  cuuint32_t estr[4] = {1, 2, 2, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
 int env_int(const char* name, int dflt) {
   const char* s = getenv(name);
   return s && *s ? atoi(s) : dflt;
@@ -811,12 +889,36 @@ int pcb_conv_tc2(pcb_ctx* c, const ConvArgs& a) {
   const int ksteps = p.taps * p.kchunks;
   const int fixed = 5 * p.vec_n * 4 + kEpiWarps * 2048 + (2 * kMaxA + 2 * kMaxB + 4) * 8 + 16 + 1024;
 
+  // stride-2 convolutions: GEMM on the output grid, one strided 4-D TMA load per tap (see Conv2Params::strided)
+  const bool strided = !in.dense && a.stride == 2 && a.out && !env_int("PCB_CONV_NO_STRIDED", 0);
+  if (strided) {
+    const int Ho = a.out->h, Wo = a.out->w;
+    int bx = 1;
+    for (int d = 1; d <= Wo && d <= 128; ++d) if (Wo % d == 0) bx = d;
+    int by = 1;
+    for (int d = 1; d <= Ho && d * bx <= 128; ++d) if (Ho % d == 0) by = d;
+    int nb = 1;
+    if (bx == Wo && by == Ho) nb = 128 / (bx * by);
+    if (nb > in.n) nb = in.n;
+    if (nb < 1) nb = 1;
+    p.strided = 1;
+    p.s_bx = bx; p.s_by = by; p.s_nb = nb;
+    p.s_tx = Wo / bx; p.s_ty = Ho / by;
+    p.s_n = in.n; p.s_ho = Ho; p.s_wo = Wo;
+    p.mt = 1;
+    p.n_aloads = 0;
+    p.a_stage_bytes = kBlockM * p.row_bytes;
+    p.a_tx_bytes = nb * by * bx * p.row_bytes;
+    p.m_tiles = ((in.n + nb - 1) / nb) * p.s_tx * p.s_ty;
+    p.acc_bufs = 2;
+  }
+
   // choose MT (1 or 2): fewer L2 bytes per FLOP at MT=2, but half as many tiles to spread over the SMs
   const int force_mt = env_int("PCB_CONV_MT", 0);
   int best_mt = 0;
   double best_cost = 0.0;
   int a2_rows = 8;
-  for (int mt = 1; mt <= 2; ++mt) {
+  for (int mt = 1; mt <= 2 && !strided; ++mt) {
     if (force_mt && mt != force_mt) continue;
     if (mt * p.sub_cols > (int)kTmemCols) continue;
     Conv2Params q = p;
@@ -833,11 +935,13 @@ int pcb_conv_tc2(pcb_ctx* c, const ConvArgs& a) {
     const double cost = (double)waves * mt * (mt == 1 ? 1.0 : (2 * p.sub_cols > 256 ? 1.05 : 0.72));
     if (!best_mt || cost < best_cost) { best_mt = mt; best_cost = cost; }
   }
-  if (!best_mt) return pcb_conv_tc(c, a);   // no shared-memory plan (very wide maps): baseline kernel
-  plan_a(p, best_mt, &a2_rows);
-  if (env_int("PCB_TAP_ALIGN", 0)) for (int t = 0; t < 9; ++t) p.tap_off[t] &= ~1023;   // timing experiment only (wrong sums)
-  p.m_tiles = (int)(((long long)p.rows + p.mt * kBlockM - 1) / (p.mt * kBlockM));
-  p.acc_bufs = (p.mt * p.sub_cols <= 256) ? 2 : 1;
+  if (!strided) {
+    if (!best_mt) return pcb_conv_tc(c, a);   // no shared-memory plan (very wide maps): baseline kernel
+    plan_a(p, best_mt, &a2_rows);
+    if (env_int("PCB_TAP_ALIGN", 0)) for (int t = 0; t < 9; ++t) p.tap_off[t] &= ~1023;   // timing experiment only (wrong sums)
+    p.m_tiles = (int)(((long long)p.rows + p.mt * kBlockM - 1) / (p.mt * kBlockM));
+    p.acc_bufs = (p.mt * p.sub_cols <= 256) ? 2 : 1;
+  }
   const int room = kSmemBudget - fixed;
   p.b_resident = 0;
   if (p.n_tiles == 1 && ksteps <= kMaxB && 2 * p.a_stage_bytes + ksteps * p.b_bytes <= room && !env_int("PCB_CONV_NO_RESIDENT", 0)) {
@@ -854,14 +958,26 @@ int pcb_conv_tc2(pcb_ctx* c, const ConvArgs& a) {
     }
     if (p.b_stages > kMaxB) p.b_stages = kMaxB;
   }
+  if (strided && !p.b_resident) {
+    // every tap is its own A stage: split the room evenly between the A and B rings
+    p.a_stages = (room / 2) / p.a_stage_bytes;
+    p.b_stages = (room - p.a_stages * p.a_stage_bytes) / p.b_bytes;
+    if (p.b_stages > kMaxB) p.b_stages = kMaxB;
+  }
   if (p.a_stages > kMaxA) p.a_stages = kMaxA;
   const size_t smem = (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * p.b_bytes + fixed;
 
   CUtensorMap tmA, tmA2, tmB;
-  if (!make_map_2d(&tmA, in.data, (uint64_t)p.rows, (uint64_t)in.cp, (uint64_t)in.cp, kBlockM, p.kc))
-    return pcb_fail(c, PCB_ERR_CUDA, "cuTensorMapEncodeTiled(A) failed");
-  if (!make_map_2d(&tmA2, in.data, (uint64_t)p.rows, (uint64_t)in.cp, (uint64_t)in.cp, (uint32_t)a2_rows, p.kc))
-    return pcb_fail(c, PCB_ERR_CUDA, "cuTensorMapEncodeTiled(A2) failed");
+  if (strided) {
+    if (!make_map_4d_s2(&tmA, in.data, in.n, in.h + 2, in.w + 2, in.cp, p.kc, p.s_bx, p.s_by, p.s_nb))
+      return pcb_fail(c, PCB_ERR_CUDA, "cuTensorMapEncodeTiled(A strided) failed");
+    tmA2 = tmA;
+  } else {
+    if (!make_map_2d(&tmA, in.data, (uint64_t)p.rows, (uint64_t)in.cp, (uint64_t)in.cp, kBlockM, p.kc))
+      return pcb_fail(c, PCB_ERR_CUDA, "cuTensorMapEncodeTiled(A) failed");
+    if (!make_map_2d(&tmA2, in.data, (uint64_t)p.rows, (uint64_t)in.cp, (uint64_t)in.cp, (uint32_t)a2_rows, p.kc))
+      return pcb_fail(c, PCB_ERR_CUDA, "cuTensorMapEncodeTiled(A2) failed");
+  }
   if (!make_map_2d(&tmB, w.w, (uint64_t)w.npad, (uint64_t)w.taps * w.cin_w, (uint64_t)w.taps * w.cin_w, (uint32_t)w.n_tile, p.kc))
     return pcb_fail(c, PCB_ERR_CUDA, "cuTensorMapEncodeTiled(B) failed");
 
@@ -873,9 +989,10 @@ int pcb_conv_tc2(pcb_ctx* c, const ConvArgs& a) {
   char desc[200];
   desc[0] = 0;
   if (c->profile)
-    snprintf(desc, sizeof desc, "n=%d,h=%d,w=%d,cin=%d,cout=%d,taps=%d,stride=%d,ntile=%d,mt=%d,tiles=%d,grid=%d,res=%d,f32out=%d,out2=%d,ast=%d,bst=%d,bres=%d",
+    snprintf(desc, sizeof desc, "n=%d,h=%d,w=%d,cin=%d,cout=%d,taps=%d,stride=%d,ntile=%d,mt=%d,tiles=%d,grid=%d,res=%d,f32out=%d,out2=%d,ast=%d,bst=%d,bres=%d,sbox=%dx%dx%d",
              in.n, in.h, in.w, w.cin, w.cout, w.taps, p.stride, p.n_tile, p.mt, total, grid, a.residual ? 1 : 0,
-             (a.out && a.out->f32) ? 1 : 0, a.out2 ? 1 : 0, p.a_stages, p.b_stages, p.b_resident);
+             (a.out && a.out->f32) ? 1 : 0, a.out2 ? 1 : 0, p.a_stages, p.b_stages, p.b_resident, p.strided ? p.s_nb : 0,
+             p.strided ? p.s_by : 0, p.strided ? p.s_bx : 0);
   static const int debug = env_int("PCB_CONV_DEBUG", 0);
   static unsigned long long* dbg_dev = nullptr;
   if (debug && c->profile) {
