@@ -73,6 +73,9 @@ struct Conv2Params {
   // strided mode (stride-2 convolutions): the tile is nb images x by output rows x bx output pixels (<= 128 GEMM rows),
   // each tap is its own TMA load through a 4-D map with element strides {1,2,2,1} (only the even input pixels of the tap
   // are fetched), so the GEMM runs on the OUTPUT grid instead of computing all input positions and dropping 3 of 4
+  // weight multicast: the two CTAs of a 2-CTA cluster work on adjacent M tiles, each loads half of every weight stage and
+  // multicasts it to both (halves the L2->SM weight traffic that bounds the 256-channel layers at MT=1)
+  int mc;
   int strided;
   int s_bx, s_by, s_nb;        // output pixels / output rows / images per tile
   int s_tx, s_ty;              // tiles per output row / per image column of rows
@@ -177,6 +180,21 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
+}
+
+__device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap* map, uint64_t* bar, uint32_t dst, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 __device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, uint32_t dst, int c0, int c1, int c2, int c3) {
@@ -323,7 +341,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
     for (int s = 0; s < p.b_stages; ++s) {
       mbar_init(&b_full[s], 1);
-      mbar_init(&b_empty[s], 1);
+      mbar_init(&b_empty[s], p.mc ? 2 : 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
@@ -347,8 +365,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
+  if (p.mc) cluster_sync_all();     // the peer's barriers are initialised before any multicast load / commit targets them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const int mc_rank = p.mc ? (int)(blockIdx.x & 1) : 0;   // clusters are consecutive CTA pairs along x
 
   if (warp == 0) {
     // ===================== A producer (whole warp loops, one elected lane issues) =====================
@@ -363,7 +383,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       long long w_empty = 0;
       const long long c0 = clock64();
       const unsigned long long n0s = globaltimer_ns();
-      for (int tile = blockIdx.x; ok && tile < total_tiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x; ok && tile - mc_rank < total_tiles; tile += gridDim.x) {
         const int mt_idx = tile / p.n_tiles;
         const int m0 = mt_idx * tile_rows;
         if (p.strided) {
@@ -427,7 +447,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         int stage = 0;
         uint32_t phase = 0;
         bool ok = true;
-        for (int tile = blockIdx.x; ok && tile < total_tiles; tile += gridDim.x) {
+        for (int tile = blockIdx.x; ok && tile - mc_rank < total_tiles; tile += gridDim.x) {
           const int mt_idx = tile / p.n_tiles, nt = tile - mt_idx * p.n_tiles;
           const int n0 = nt * p.n_tile;
           for (int ks = 0; ks < ksteps; ++ks) {
@@ -436,7 +456,14 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             if (!ok) break;
             if (elect_one()) {
               mbar_expect_tx(&b_full[stage], (uint32_t)p.b_bytes);
-              tma_load_2d(&tmB, &b_full[stage], smem_u32(smem_b + (size_t)stage * p.b_bytes), t * p.cin_w + kc * p.kc, n0);
+              if (p.mc) {
+                // my half of the weight stage, delivered to both CTAs of the pair
+                const uint32_t half_bytes = (uint32_t)p.b_bytes / 2;
+                tma_load_2d_mc(&tmB, &b_full[stage], smem_u32(smem_b + (size_t)stage * p.b_bytes) + mc_rank * half_bytes,
+                               t * p.cin_w + kc * p.kc, n0 + mc_rank * (p.n_tile / 2), (uint16_t)3);
+              } else {
+                tma_load_2d(&tmB, &b_full[stage], smem_u32(smem_b + (size_t)stage * p.b_bytes), t * p.cin_w + kc * p.kc, n0);
+              }
             }
             __syncwarp();
             if (++stage == p.b_stages) { stage = 0; phase ^= 1; }
@@ -459,7 +486,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       bool ok = true;
       bool b_loaded = false;
       long long w_a = 0, w_b = 0, w_t = 0;
-      for (int tile = blockIdx.x; ok && tile < total_tiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x; ok && tile - mc_rank < total_tiles; tile += gridDim.x) {
         ok = __all_sync(0xffffffffu, mbar_wait_t(&tempty_bar[acc], acc_phase ^ 1, p.err, 102, w_t, p.dbg != nullptr));
         if (!ok) break;
         tc_fence_after();
@@ -495,7 +522,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 if (kinstr > 2) umma_f16(d, da + 4, db + 4, idesc, 1u);
                 if (kinstr > 3) umma_f16(d, da + 6, db + 6, idesc, 1u);
               }
-              if (!p.b_resident) umma_commit(&b_empty[b_stage]);
+              if (!p.b_resident) {
+                if (p.mc) umma_commit_mc(&b_empty[b_stage], (uint16_t)3);   // both CTAs of the pair must be done with the stage
+                else umma_commit(&b_empty[b_stage]);
+              }
               if (p.strided) umma_commit(&a_empty[a_stage]);
             }
             __syncwarp();
@@ -554,7 +584,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     uint32_t acc_phase = 0;
     bool ok = true;
     long long w_full = 0, t_epi = 0, t_ld = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x; tile - mc_rank < total_tiles; tile += gridDim.x) {
       const int mt_idx = tile / p.n_tiles, nt = tile - mt_idx * p.n_tiles;
       const int n0 = nt * p.n_tile;
       const long long row0 = (long long)mt_idx * tile_rows + row_in_tile;
@@ -718,6 +748,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
   tc_fence_before();
   __syncthreads();
+  if (p.mc) cluster_sync_all();     // no CTA leaves while its peer can still multicast into it or arrive on its barriers
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
   }
@@ -965,6 +996,12 @@ int pcb_conv_tc2(pcb_ctx* c, const ConvArgs& a) {
     if (p.b_stages > kMaxB) p.b_stages = kMaxB;
   }
   if (p.a_stages > kMaxA) p.a_stages = kMaxA;
+  // Experiment, off by default (PCB_CONV_MC=1): measured on B200 it changes nothing (14x14 256->256: 873 vs 872 TFLOP/s) --
+  // at cluster size 2 unicast loads of the same lines are already served once by L2, and these layers are paced by the
+  // ~175-cycle SS-mode tcgen05.mma (tensor pipe 70-75 % active), not by L2->SM bytes.  What would help is cta_group::2
+  // (each SM reads only half of B from its own shared memory per MMA).
+  p.mc = (!strided && !p.b_resident && p.n_tiles == 1 && p.n_tile >= 128 && p.n_tile % 32 == 0 && p.m_tiles >= 2 &&
+          env_int("PCB_CONV_MC", 0)) ? 1 : 0;
   const size_t smem = (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * p.b_bytes + fixed;
 
   CUtensorMap tmA, tmA2, tmB;
@@ -978,21 +1015,22 @@ int pcb_conv_tc2(pcb_ctx* c, const ConvArgs& a) {
     if (!make_map_2d(&tmA2, in.data, (uint64_t)p.rows, (uint64_t)in.cp, (uint64_t)in.cp, (uint32_t)a2_rows, p.kc))
       return pcb_fail(c, PCB_ERR_CUDA, "cuTensorMapEncodeTiled(A2) failed");
   }
-  if (!make_map_2d(&tmB, w.w, (uint64_t)w.npad, (uint64_t)w.taps * w.cin_w, (uint64_t)w.taps * w.cin_w, (uint32_t)w.n_tile, p.kc))
+  if (!make_map_2d(&tmB, w.w, (uint64_t)w.npad, (uint64_t)w.taps * w.cin_w, (uint64_t)w.taps * w.cin_w, (uint32_t)(p.mc ? w.n_tile / 2 : w.n_tile), p.kc))
     return pcb_fail(c, PCB_ERR_CUDA, "cuTensorMapEncodeTiled(B) failed");
 
   const int total = p.m_tiles * p.n_tiles;
-  const int grid = total < c->num_sms ? total : c->num_sms;
+  int grid = total < c->num_sms ? total : c->num_sms;
+  if (p.mc) grid = (grid + 1) & ~1;          // whole 2-CTA clusters (148 SMs: 74 pairs)
   // algorithmic FLOPs of this layer: 2 * output pixels * cout * cin * taps (real, unpadded extents)
   double out_px = in.dense ? (double)in.n : (double)in.n * (in.h / p.stride) * (in.w / p.stride);
   const double k_real = (w.taps == 1 && w.cin == 3) ? 27.0 : (double)w.cin * w.taps;
   char desc[200];
   desc[0] = 0;
   if (c->profile)
-    snprintf(desc, sizeof desc, "n=%d,h=%d,w=%d,cin=%d,cout=%d,taps=%d,stride=%d,ntile=%d,mt=%d,tiles=%d,grid=%d,res=%d,f32out=%d,out2=%d,ast=%d,bst=%d,bres=%d,sbox=%dx%dx%d",
+    snprintf(desc, sizeof desc, "n=%d,h=%d,w=%d,cin=%d,cout=%d,taps=%d,stride=%d,ntile=%d,mt=%d,tiles=%d,grid=%d,res=%d,f32out=%d,out2=%d,ast=%d,bst=%d,bres=%d,sbox=%dx%dx%d,mc=%d",
              in.n, in.h, in.w, w.cin, w.cout, w.taps, p.stride, p.n_tile, p.mt, total, grid, a.residual ? 1 : 0,
              (a.out && a.out->f32) ? 1 : 0, a.out2 ? 1 : 0, p.a_stages, p.b_stages, p.b_resident, p.strided ? p.s_nb : 0,
-             p.strided ? p.s_by : 0, p.strided ? p.s_bx : 0);
+             p.strided ? p.s_by : 0, p.strided ? p.s_bx : 0, p.mc);
   static const int debug = env_int("PCB_CONV_DEBUG", 0);
   static unsigned long long* dbg_dev = nullptr;
   if (debug && c->profile) {
@@ -1012,8 +1050,24 @@ int pcb_conv_tc2(pcb_ctx* c, const ConvArgs& a) {
       cudaFuncSetAttribute(conv_tc2_kernel<ACT, RES, OUT2, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
       attr = true;                                                                                                     \
     }                                                                                                                  \
-    conv_tc2_kernel<ACT, RES, OUT2, MODE><<<grid, kThreads, smem, c->stream>>>(tmA, tmA2, tmB, p);                     \
-    le = cudaSuccess;                                                                                                  \
+    if (p.mc) {                                                                                                        \
+      cudaLaunchConfig_t cfg = {};                                                                                     \
+      cfg.gridDim = dim3(grid);                                                                                        \
+      cfg.blockDim = dim3(kThreads);                                                                                   \
+      cfg.dynamicSmemBytes = smem;                                                                                     \
+      cfg.stream = c->stream;                                                                                          \
+      cudaLaunchAttribute at[1];                                                                                       \
+      at[0].id = cudaLaunchAttributeClusterDimension;                                                                  \
+      at[0].val.clusterDim.x = 2;                                                                                      \
+      at[0].val.clusterDim.y = 1;                                                                                      \
+      at[0].val.clusterDim.z = 1;                                                                                      \
+      cfg.attrs = at;                                                                                                  \
+      cfg.numAttrs = 1;                                                                                                \
+      le = cudaLaunchKernelEx(&cfg, conv_tc2_kernel<ACT, RES, OUT2, MODE>, tmA, tmA2, tmB, p);                         \
+    } else {                                                                                                           \
+      conv_tc2_kernel<ACT, RES, OUT2, MODE><<<grid, kThreads, smem, c->stream>>>(tmA, tmA2, tmB, p);                   \
+      le = cudaSuccess;                                                                                                \
+    }                                                                                                                  \
     break;                                                                                                             \
   }
     switch (key) {

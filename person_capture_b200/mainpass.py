@@ -182,7 +182,11 @@ def fullframe_identity(clip, idxs: Sequence[int], face: FaceEmbedder, ref_face_f
     qmin = float(cfg.face_quality_min)
     use_qv = bool(getattr(cfg, "face_visible_uses_quality", True))
     thr = float(cfg.face_thresh)
-    out = []
+    # phase 1: SCRFD + K4 per frame batch; chips are queued and embedded in 444-image runs (the ArcFace batch must not
+    # depend on how few faces a frame batch holds)
+    from .prescan import FaceTable
+    table = FaceTable(lazy=False)
+    metas = []
     for b0 in range(0, len(idxs), batch):
         chunk = list(idxs[b0:b0 + batch])
         frames = clip.device_batch(eng, chunk)
@@ -192,13 +196,19 @@ def fullframe_identity(clip, idxs: Sequence[int], face: FaceEmbedder, ref_face_f
         eng.sync()
         total = int(al.face_total.cpu()[0])
         counts = al.face_count.cpu().numpy()
-        if total:
-            emb, emb_flip = eng.embed(al.chips, total, True)
-            _, sim, _ = eng.match(emb, emb_flip, None, total)
-            eng.sync()
-            fds = 1.0 - sim[:total].cpu().numpy().astype(np.float64)
-            boxes = al.face_box[:total].cpu().numpy()
-            qual = al.quality[:total].cpu().numpy()
+        rows = table.queue(eng, al.chips, total) if total else np.zeros((0,), np.int64)
+        metas.append((chunk, H2, W2, counts, rows, al.face_box[:total].cpu().numpy() if total else None,
+                      al.quality[:total].cpu().numpy() if total else None))
+    table.finalize(eng)
+    # phase 2: distances of normalise(e(x) + e(flip x)) against the bank, then gbest + accept per frame
+    fds_all = np.zeros((0,), np.float64)
+    if table.count:
+        _, sim, _ = eng.match(table.flip, None, None, table.count, want_feat=False)
+        eng.sync()
+        fds_all = 1.0 - sim[:table.count].cpu().numpy().astype(np.float64)
+    out = []
+    for chunk, H2, W2, counts, rows, boxes, qual in metas:
+        fds = fds_all[rows] if len(rows) else None
         off = 0
         for b, idx in enumerate(chunk):
             k = int(counts[b])
