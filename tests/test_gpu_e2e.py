@@ -324,3 +324,32 @@ def test_fullframe_identity_batched_matches_per_frame_extract(engine_25g_r50):
         assert abs(float(fds[g]) - rec["fd"]) <= 1e-5 and (float(fds[g]) <= cfg.face_thresh) == rec["accept"]
         n_checked += 1
     assert n_checked >= 8 and any(r["accept"] for r in recs)
+
+
+def test_curator_identity_matches_oracle(engine_25g_r50):
+    """Curator consumer (dataset_curator.py): centred 640 letterbox + best face + 1-row fd, GPU vs oracle on saved-crop-like images."""
+    from oracle.curator import CuratorIdentityOracle, letterbox_square
+    from person_capture_b200.curator import CuratorIdentity
+    from person_capture_b200.face_embedder import FaceEmbedder
+    face = FaceEmbedder("cuda:0", "scrfd_2.5g_bnkps", conf=0.5, engine=engine_25g_r50)
+    ora = H.oracle_embedder("scrfd_2.5g_bnkps", "arcface_r50", conf=0.5)
+    ref = synth.reference_image(1, 512, seed=5)
+    g, o = CuratorIdentity(face, ref), CuratorIdentityOracle(ora, ref)
+    assert g.ref_feat is not None and H.cos(g.ref_feat, o.ref_feat) >= 0.999
+    rng = np.random.default_rng(8)
+    n_faces = 0
+    for k, (w, h, ident) in enumerate([(300, 420, 1), (512, 384, 2), (260, 260, 1), (700, 500, 3), (200, 320, 1)]):
+        img = synth.background(rng, h, w, clutter=3)
+        if k != 3:
+            synth.paste_face(img, ident, w / 2 + rng.uniform(-10, 10), h / 2 + rng.uniform(-10, 10), min(w, h) * 0.45, float(rng.uniform(-4, 4)))
+        canvas, scale, dx, dy = g.letterbox_square(img, 640)
+        face.engine.sync()
+        ref_canvas, s2, dx2, dy2 = letterbox_square(img, 640)
+        assert (scale, dx, dy) == (s2, dx2, dy2) and np.array_equal(canvas.cpu().numpy(), ref_canvas)      # bit-exact letterbox
+        a, b = g.describe(img), o.describe(img)
+        assert (a["bbox"] is None) == (b["bbox"] is None)
+        if a["bbox"] is not None:
+            n_faces += 1
+            assert np.abs(np.array(a["bbox"]) - np.array(b["bbox"])).max() <= 1
+            assert abs(a["fd"] - b["fd"]) <= FD_TOL_E2E * 2 and H.cos(a["feat"], b["feat"]) >= 0.99
+    assert n_faces >= 3

@@ -47,7 +47,7 @@ class Pooled:
 
 src = Pooled(frames, args.frames)
 idxs = list(range(args.frames))
-MP.fullframe_identity(src, idxs[:16], face, bank, cfg, batch=8)
+MP.fullframe_identity(src, idxs, face, bank, cfg, batch=8)      # warm-up at full size (activation sets are allocated per capacity)
 eng.sync()
 e0 = ev()
 recs = MP.fullframe_identity(src, idxs, face, bank, cfg, batch=8)
