@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpcb200.so")
+LIB_PATH = os.environ.get("PCB_LIB") or os.path.join(_HERE, "libpcb200.so")   # PCB_LIB: A/B another build of the library
 
 FEAT_DIM = 512
 CHIP = 112

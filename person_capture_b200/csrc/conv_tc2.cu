@@ -17,13 +17,26 @@
 // Pipelines: A ring (2-3 stages) and B ring (up to 18 stages) with separate producer warps, TMEM
 // accumulators double-buffered when MT*N <= 256 columns.
 //
-// Warp roles (352 threads, 1 CTA/SM, persistent over tiles):
-//   warp 0  A producer (TMA)    warp 1  MMA issuer (+TMEM alloc)    warp 2  B producer (TMA)
-//   warps 3-10  epilogue: TMEM lane quarter = warp % 4, column half = (warp - 3) / 4.
+// Warp roles (384 threads, 1 CTA/SM, persistent over tiles):
+//   warp 0  A producer (TMA)    warp 1  MMA issuer 0 (+TMEM alloc)    warp 2  B producer (TMA)
+//   warps 3-10  epilogue: TMEM lane quarter = warp % 4, column half = (warp - 3) / 4.    warp 11  MMA issuer 1
+// Two issuers: measured with tools/mma_rate.cu, ONE thread sustains a tcgen05.mma every ~65-85 cycles (59 + 0.2 N), so
+// instructions with N <= 128 (32-64 tensor-pipe cycles) leave the pipe half idle however the loop is written; two warps
+// issuing to disjoint accumulators reach the nominal rate (N = 128: 64.0 cycles, 8190 FLOP/clk/SM).  The issuers split a
+// K step by accumulator: MT = 2 -> one 128-row sub-tile each; MT = 1 -> one half of the N columns each (two N/2-wide
+// instructions on the same A rows).  Empty / TMEM-full barriers then take one commit per issuer.
 // Epilogue per 32 columns: tcgen05.ld.x32 -> y = acc*scale+bias (+residual) -> ReLU/PReLU -> fp16
 // (or fp32 head maps) -> 16-byte stores of interior pixels; optional second output scale2*y+bias2
 // (the next block's BatchNorm).  Per-channel vectors live in shared memory; the residual rows of a
 // tile are prefetched into registers before the accumulator is waited for.
+//
+// Kernel variants (template parameter kVar, so the role loops carry no per-variant branches):
+//   0 halo     the formulation above, one CTA per tile, tcgen05.mma.cta_group::1 (M = 128)
+//   1 strided  stride-2 convolutions on the output grid, one 4-D strided TMA load per tap
+//   2 pair     halo formulation on a 2-CTA cluster (one TPC): the CTAs own adjacent M tiles and HALF of every
+//              weight stage each; the leader issues tcgen05.mma.cta_group::2 (M = 256, 128 rows per SM), so an SM
+//              reads only half of B from its own shared memory per MMA and TMA writes half the weight bytes into
+//              it -- the shared-memory port, not the tensor pipe, paces the cta_group::1 kernel on the wide layers.
 //
 // Every mbarrier wait is bounded (watchdog): on timeout the kernel raises the context's error word
 // and drains instead of hanging the GPU.
@@ -36,7 +49,8 @@ namespace {
 
 constexpr int kBlockM = 128;
 constexpr int kKC = 64;                       // K elements per weight stage (one 128B swizzle atom)
-constexpr int kThreads = 352;
+constexpr int kThreads = 384;
+constexpr int kIss1Warp = 11;                 // second MMA issuer warp
 constexpr int kEpiWarp0 = 3;
 constexpr int kEpiWarps = 8;
 constexpr uint32_t kTmemCols = 512;
@@ -44,6 +58,7 @@ constexpr int kMaxA = 6;
 constexpr int kMaxB = 18;
 constexpr int kMaxALoads = 12;
 constexpr int kSmemBudget = 224 * 1024;
+constexpr int kPairMinN = 128;               // default policy: pair mode for layers with n_tile >= this and >= 2 K chunks (PCB_CONV_PAIR=2 overrides)
 
 struct ALoad {
   int row_rel;    // first global row of the box relative to m0
@@ -66,21 +81,26 @@ struct Conv2Params {
   int sub_cols;    // TMEM columns between sub-tile accumulators (n_tile rounded up to 32)
   int acc_bufs;    // 1 | 2
   int a_stages, a_stage_bytes, a_tx_bytes;
-  int b_stages, b_bytes, b_resident;
+  int b_stages, b_bytes, b_resident;   // b_bytes: bytes of one weight stage in THIS CTA's shared memory
+  int b_rows;      // weight rows per stage in this CTA (n_tile, or n_tile/2 in pair mode)
+  int n_iss;       // MMA issuer warps in use (1 | 2)
+  int split_n;     // 1: the issuers split the N columns (MT = 1); 0: they split the sub-tiles (MT = 2) or there is one issuer
+  int b_nloads;    // TMA loads per weight stage and CTA (2 in pair + split_n mode: this CTA's quarter of each column half)
+  int b_load_rows; // weight rows per load (= box rows of the weight map)
   int n_aloads;
   ALoad aloads[kMaxALoads];
   int tap_off[9];  // byte offset of tap t's first row inside the A stage
   // strided mode (stride-2 convolutions): the tile is nb images x by output rows x bx output pixels (<= 128 GEMM rows),
   // each tap is its own TMA load through a 4-D map with element strides {1,2,2,1} (only the even input pixels of the tap
   // are fetched), so the GEMM runs on the OUTPUT grid instead of computing all input positions and dropping 3 of 4
-  // weight multicast: the two CTAs of a 2-CTA cluster work on adjacent M tiles, each loads half of every weight stage and
-  // multicasts it to both (halves the L2->SM weight traffic that bounds the 256-channel layers at MT=1)
-  int mc;
   int strided;
+  int pair;        // 1: 2-CTA cluster, cta_group::2 (m_tiles counts PAIR tiles of 2*mt*128 rows; b_bytes is this CTA's half stage)
   int s_bx, s_by, s_nb;        // output pixels / output rows / images per tile
   int s_tx, s_ty;              // tiles per output row / per image column of rows
   int s_n;                     // images
   int s_ho, s_wo;              // output dims
+  uint32_t fd_plane_mul, fd_wp_mul;   // fast_div multipliers for hp*wp and wp
+  int fd_plane_shift, fd_wp_shift;
   int desc_mode;   // 1 (product): base-offset 0; 0 (experiment): base-offset = (addr >> 7) & 7
   int stride;      // 1 | 2
   int hp_out, wp_out;
@@ -175,26 +195,33 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   return t;
 }
 
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, uint32_t dst, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
+// Address of `bar` in the shared memory of the cluster's rank-0 CTA (the pair's MMA leader).
+__device__ __forceinline__ uint32_t leader_addr(const void* bar) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(r) : "r"(smem_u32(bar)));
+  return r;
 }
-
-__device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap* map, uint64_t* bar, uint32_t dst, int c0, int c1, uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
-      ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+// kPair: the destination is this CTA's shared memory, the mbarrier (a shared::cluster address) is the leader's.
+template <bool kPair>
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1) {
+  if (kPair)
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+  else
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
 }
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on a barrier given by its shared::cluster address (own or peer CTA)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
 __device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, uint32_t dst, int c0, int c1, int c2, int c3) {
@@ -204,16 +231,32 @@ __device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* ba
       : "memory");
 }
 
+template <bool kPair>
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accum)
-      : "memory");
+  if (kPair)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accum)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accum)
+        : "memory");
 }
+// kPair: the arrival is multicast to the barrier at this offset in BOTH CTAs of the pair (each frees its own stage /
+// wakes its own epilogue) once the pair's MMAs issued so far have completed.
+template <bool kPair>
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+  if (kPair)
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+  else
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -255,14 +298,25 @@ __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
   return v;
 }
 
+__device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+// n / d for 0 <= n < 2^31 with the multiplier the host precomputed (fd_mul = floor(2^32 * (2^s - d) / d) + 1, s = ceil(log2 d))
+__device__ __forceinline__ int fast_div(int n, uint32_t mul, int shift) {
+  return (int)(((uint64_t)__umulhi((uint32_t)n, mul) + (uint32_t)n) >> shift);
+}
+
 struct RowInfo {
   bool valid;
   long long orow;
 };
 
+template <bool kStrided>
 __device__ __forceinline__ RowInfo row_info(const Conv2Params& p, long long prow) {
   RowInfo r;
-  if (p.strided) {
+  if (kStrided) {
     // prow = tile * 128 + row in tile; rows of a tile enumerate (image, output row, output pixel) of the strided box
     const int tile = (int)(prow >> 7), rr = (int)(prow & 127);
     const int tx = tile % p.s_tx;
@@ -280,9 +334,9 @@ __device__ __forceinline__ RowInfo row_info(const Conv2Params& p, long long prow
   r.orow = prow;
   if (!p.dense) {
     const int plane = p.hp * p.wp;
-    const int img = (int)(prow / plane);
-    const int rem = (int)(prow - (long long)img * plane);
-    const int y = rem / p.wp, x = rem - y * p.wp;
+    const int img = fast_div((int)prow, p.fd_plane_mul, p.fd_plane_shift);
+    const int rem = (int)prow - img * plane;
+    const int y = fast_div(rem, p.fd_wp_mul, p.fd_wp_shift), x = rem - y * p.wp;
     r.valid = r.valid && y >= 1 && y <= p.hp - 2 && x >= 1 && x <= p.wp - 2;
     if (p.stride == 2) {
       r.valid = r.valid && (((y - 1) | (x - 1)) & 1) == 0;
@@ -309,11 +363,16 @@ __device__ __forceinline__ uint4 pack_h8(const float* f) {
   return v;
 }
 
-// kAct: PCB_ACT_*; kRes: residual add; kOut2: second (affine) output; kOutMode: 0 fp16 P-layout, 1 fp32 P-layout, 2 dense fp32
-template <int kAct, bool kRes, bool kOut2, int kOutMode>
+constexpr int kVarHalo = 0, kVarStrided = 1, kVarPair = 2;
+
+// kAct: PCB_ACT_*; kRes: residual add; kOut2: second (affine) output; kOutMode: 0 fp16 P-layout, 1 fp32 P-layout, 2 dense fp32;
+// kVar: kVarHalo | kVarStrided | kVarPair (launched as 2-CTA clusters)
+template <int kAct, bool kRes, bool kOut2, int kOutMode, int kVar>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                 const __grid_constant__ CUtensorMap tmB, const __grid_constant__ Conv2Params p) {
+  constexpr bool kPair = kVar == kVarPair;
+  constexpr bool kStrided = kVar == kVarStrided;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_a = smem;
@@ -331,28 +390,42 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform by construction
   const int lane = threadIdx.x & 31;
+  // pair mode: clusters are consecutive CTA pairs along x; rank 0 leads.  Both CTAs walk the same PAIR tiles; inside a
+  // pair tile CTA r owns M tile 2*mt_idx + r.  The full barriers that count are the leader's (both CTAs' TMA loads
+  // complete on them, the leader alone expects the bytes); the empty / TMEM-full barriers are per CTA (multicast commit);
+  // the TMEM-empty barrier that counts is the leader's (both CTAs' epilogue warps arrive on it).
+  const int cta_rank = kPair ? (int)(blockIdx.x & 1) : 0;
+  const bool leader = cta_rank == 0;
+  const int tile0 = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_step = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int total_tiles = p.m_tiles * p.n_tiles;
   const int tile_rows = p.mt * kBlockM;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.a_stages; ++s) {
       mbar_init(&a_full[s], 1);
-      mbar_init(&a_empty[s], 1);
+      mbar_init(&a_empty[s], p.n_iss);
     }
     for (int s = 0; s < p.b_stages; ++s) {
       mbar_init(&b_full[s], 1);
-      mbar_init(&b_empty[s], p.mc ? 2 : 1);
+      mbar_init(&b_empty[s], p.n_iss);
     }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], kEpiWarps);
+      mbar_init(&tfull_bar[s], p.n_iss);
+      mbar_init(&tempty_bar[s], kPair ? 2 * kEpiWarps : kEpiWarps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (kPair) {
+      // the same warp of both CTAs allocates; the columns are the same in both halves of the pair
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   // per-channel vectors -> shared memory (epilogue reads them as broadcast float4)
   for (int i = threadIdx.x; i < p.vec_n; i += kThreads) {
@@ -365,10 +438,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
-  if (p.mc) cluster_sync_all();     // the peer's barriers are initialised before any multicast load / commit targets them
+  if (kPair) cluster_sync_all();     // the leader's barriers exist before the peer's loads / arrivals target them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int mc_rank = p.mc ? (int)(blockIdx.x & 1) : 0;   // clusters are consecutive CTA pairs along x
 
   if (warp == 0) {
     // ===================== A producer (whole warp loops, one elected lane issues) =====================
@@ -383,10 +455,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       long long w_empty = 0;
       const long long c0 = clock64();
       const unsigned long long n0s = globaltimer_ns();
-      for (int tile = blockIdx.x; ok && tile - mc_rank < total_tiles; tile += gridDim.x) {
+      for (int tile = tile0; ok && tile < total_tiles; tile += tile_step) {
         const int mt_idx = tile / p.n_tiles;
-        const int m0 = mt_idx * tile_rows;
-        if (p.strided) {
+        if (kStrided) {
           // tile -> (image group, output row block, output column block); one 4-D strided load per (chunk, tap)
           const int tx = mt_idx % p.s_tx;
           const int ty = (mt_idx / p.s_tx) % p.s_ty;
@@ -405,21 +476,23 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               if (++stage == p.a_stages) { stage = 0; phase ^= 1; }
             }
           }
-          continue;
-        }
-        for (int kc = 0; kc < p.kchunks; ++kc) {
-          ok = __all_sync(0xffffffffu, mbar_wait_t(&a_empty[stage], phase ^ 1, p.err, 101, w_empty, p.dbg != nullptr));
-          if (!ok) break;
-          if (elect_one()) {
-            const uint32_t sa = smem_u32(smem_a + (size_t)stage * p.a_stage_bytes);
-            mbar_expect_tx(&a_full[stage], (uint32_t)p.a_tx_bytes);
-            for (int l = 0; l < p.n_aloads; ++l) {
-              const ALoad ld = p.aloads[l];
-              tma_load_2d(ld.map2 ? &tmA2 : &tmA, &a_full[stage], sa + ld.smem_off, kc * p.kc, m0 + ld.row_rel);
+        } else {
+          const int m0 = (kPair ? 2 * mt_idx + cta_rank : mt_idx) * tile_rows;
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            ok = __all_sync(0xffffffffu, mbar_wait_t(&a_empty[stage], phase ^ 1, p.err, 101, w_empty, p.dbg != nullptr));
+            if (!ok) break;
+            if (elect_one()) {
+              const uint32_t sa = smem_u32(smem_a + (size_t)stage * p.a_stage_bytes);
+              const uint32_t bar = kPair ? leader_addr(&a_full[stage]) : smem_u32(&a_full[stage]);
+              if (leader) mbar_expect_tx(&a_full[stage], (uint32_t)(kPair ? 2 * p.a_tx_bytes : p.a_tx_bytes));
+              for (int l = 0; l < p.n_aloads; ++l) {
+                const ALoad ld = p.aloads[l];
+                tma_load_2d<kPair>(ld.map2 ? &tmA2 : &tmA, bar, sa + ld.smem_off, kc * p.kc, m0 + ld.row_rel);
+              }
             }
+            __syncwarp();
+            if (++stage == p.a_stages) { stage = 0; phase ^= 1; }
           }
-          __syncwarp();
-          if (++stage == p.a_stages) { stage = 0; phase ^= 1; }
         }
       }
       if (p.dbg && blockIdx.x == 0 && lane == 0) {
@@ -433,13 +506,20 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     {
       if (elect_one()) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
       const int ksteps = p.taps * p.kchunks;
+      const uint32_t b_tx = (uint32_t)(kPair ? 2 * p.b_bytes : p.b_bytes);
+      // weight rows of load h of a stage: h * n_tile/2 + rank * b_load_rows (one load: this CTA's rows of the stage; two loads,
+      // pair + split_n: this CTA's quarter of each issuer's column half), packed back to back in the stage
+      const int n_off = cta_rank * p.b_load_rows;
+      const uint32_t load_bytes = (uint32_t)(p.b_load_rows * p.row_bytes);
       long long w_empty = 0;
       if (p.b_resident) {
         if (elect_one()) {
           for (int ks = 0; ks < ksteps; ++ks) {
             const int kc = ks / p.taps, t = ks - kc * p.taps;
-            mbar_expect_tx(&b_full[ks], (uint32_t)p.b_bytes);
-            tma_load_2d(&tmB, &b_full[ks], smem_u32(smem_b + (size_t)ks * p.b_bytes), t * p.cin_w + kc * p.kc, 0);
+            if (leader) mbar_expect_tx(&b_full[ks], b_tx);
+            for (int h = 0; h < p.b_nloads; ++h)
+              tma_load_2d<kPair>(&tmB, kPair ? leader_addr(&b_full[ks]) : smem_u32(&b_full[ks]),
+                                 smem_u32(smem_b + (size_t)ks * p.b_bytes) + h * load_bytes, t * p.cin_w + kc * p.kc, n_off + h * (p.n_tile / 2));
           }
         }
         __syncwarp();
@@ -447,23 +527,18 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         int stage = 0;
         uint32_t phase = 0;
         bool ok = true;
-        for (int tile = blockIdx.x; ok && tile - mc_rank < total_tiles; tile += gridDim.x) {
+        for (int tile = tile0; ok && tile < total_tiles; tile += tile_step) {
           const int mt_idx = tile / p.n_tiles, nt = tile - mt_idx * p.n_tiles;
-          const int n0 = nt * p.n_tile;
+          const int n0 = nt * p.n_tile + n_off;
           for (int ks = 0; ks < ksteps; ++ks) {
             const int kc = ks / p.taps, t = ks - kc * p.taps;
             ok = __all_sync(0xffffffffu, mbar_wait_t(&b_empty[stage], phase ^ 1, p.err, 105, w_empty, p.dbg != nullptr));
             if (!ok) break;
             if (elect_one()) {
-              mbar_expect_tx(&b_full[stage], (uint32_t)p.b_bytes);
-              if (p.mc) {
-                // my half of the weight stage, delivered to both CTAs of the pair
-                const uint32_t half_bytes = (uint32_t)p.b_bytes / 2;
-                tma_load_2d_mc(&tmB, &b_full[stage], smem_u32(smem_b + (size_t)stage * p.b_bytes) + mc_rank * half_bytes,
-                               t * p.cin_w + kc * p.kc, n0 + mc_rank * (p.n_tile / 2), (uint16_t)3);
-              } else {
-                tma_load_2d(&tmB, &b_full[stage], smem_u32(smem_b + (size_t)stage * p.b_bytes), t * p.cin_w + kc * p.kc, n0);
-              }
+              if (leader) mbar_expect_tx(&b_full[stage], b_tx);
+              for (int h = 0; h < p.b_nloads; ++h)
+                tma_load_2d<kPair>(&tmB, kPair ? leader_addr(&b_full[stage]) : smem_u32(&b_full[stage]),
+                                   smem_u32(smem_b + (size_t)stage * p.b_bytes) + h * load_bytes, t * p.cin_w + kc * p.kc, n0 + h * (p.n_tile / 2));
             }
             __syncwarp();
             if (++stage == p.b_stages) { stage = 0; phase ^= 1; }
@@ -472,13 +547,19 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
       if (p.dbg && blockIdx.x == 0 && lane == 0) p.dbg[5] = (unsigned long long)w_empty;
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (whole warp loops, one elected lane issues) =====================
-    {
+  } else if (warp == 1 || warp == kIss1Warp) {
+    // ===================== MMA issuers (whole warp loops, one elected lane issues; pair: the leader CTA only) =====================
+    const int iss = warp == 1 ? 0 : 1;
+    if (leader && iss < p.n_iss) {
+      const int n_instr = p.split_n ? p.n_tile / 2 : p.n_tile;
       const uint32_t idesc = (1u << 4)                          // D format: F32
                              | (0u << 7) | (0u << 10)           // A, B format: F16
-                             | ((uint32_t)(p.n_tile >> 3) << 17)
-                             | ((uint32_t)(kBlockM >> 4) << 24);
+                             | ((uint32_t)(n_instr >> 3) << 17)
+                             | ((uint32_t)((kPair ? 2 * kBlockM : kBlockM) >> 4) << 24);
+      // my share of every K step: sub-tiles j0, j0 + jstep, ... and the weight rows / accumulator columns from b_off / d_off
+      const int j0 = p.split_n ? 0 : iss, jstep = p.split_n ? 1 : p.n_iss;
+      const uint32_t b_off = p.split_n ? (uint32_t)(iss * (p.b_rows / 2) * p.row_bytes) : 0u;
+      const uint32_t d_off = p.split_n ? (uint32_t)(iss * (p.n_tile / 2)) : 0u;
       int a_stage = 0, b_stage = 0;
       uint32_t a_phase = 0, b_phase = 0;
       int acc = 0;
@@ -486,20 +567,20 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       bool ok = true;
       bool b_loaded = false;
       long long w_a = 0, w_b = 0, w_t = 0;
-      for (int tile = blockIdx.x; ok && tile - mc_rank < total_tiles; tile += gridDim.x) {
+      for (int tile = tile0; ok && tile < total_tiles; tile += tile_step) {
         ok = __all_sync(0xffffffffu, mbar_wait_t(&tempty_bar[acc], acc_phase ^ 1, p.err, 102, w_t, p.dbg != nullptr));
         if (!ok) break;
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256) + d_off;
         for (int kc = 0; ok && kc < p.kchunks; ++kc) {
-          if (!p.strided) {
+          if (!kStrided) {
             ok = __all_sync(0xffffffffu, mbar_wait_t(&a_full[a_stage], a_phase, p.err, 103, w_a, p.dbg != nullptr));
             if (!ok) break;
           }
           uint32_t sa = smem_u32(smem_a + (size_t)a_stage * p.a_stage_bytes);
           const int kinstr = (kc == p.kchunks - 1) ? p.kinstr_last : p.kc / 16;
           for (int t = 0; t < p.taps; ++t) {
-            if (p.strided) {
+            if (kStrided) {
               ok = __all_sync(0xffffffffu, mbar_wait_t(&a_full[a_stage], a_phase, p.err, 103, w_a, p.dbg != nullptr));
               if (!ok) break;
               sa = smem_u32(smem_a + (size_t)a_stage * p.a_stage_bytes);
@@ -511,41 +592,38 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
             tc_fence_after();
             if (elect_one()) {
-              const uint64_t db = make_desc_sw128(smem_u32(smem_b + (size_t)slot * p.b_bytes), 1, p.kc == 32);
+              const uint64_t db = make_desc_sw128(smem_u32(smem_b + (size_t)slot * p.b_bytes) + b_off, 1, p.kc == 32);
               const uint32_t first = (kc | t) != 0 ? 1u : 0u;
-              for (int j = 0; j < p.mt; ++j) {
-                const uint64_t da = make_desc_sw128(sa + (p.strided ? 0u : (uint32_t)p.tap_off[t]) + (uint32_t)(j * p.sub_bytes), p.desc_mode, p.kc == 32);
+              for (int j = j0; j < p.mt; j += jstep) {
+                const uint64_t da = make_desc_sw128(sa + (kStrided ? 0u : (uint32_t)p.tap_off[t]) + (uint32_t)(j * p.sub_bytes), p.desc_mode, p.kc == 32);
                 const uint32_t d = d_tmem + (uint32_t)(j * p.sub_cols);
                 // advance 16 elements (32 bytes) along K inside the swizzle atom; all-zero K slices are skipped
-                umma_f16(d, da, db, idesc, first);
-                if (kinstr > 1) umma_f16(d, da + 2, db + 2, idesc, 1u);
-                if (kinstr > 2) umma_f16(d, da + 4, db + 4, idesc, 1u);
-                if (kinstr > 3) umma_f16(d, da + 6, db + 6, idesc, 1u);
+                umma_f16<kPair>(d, da, db, idesc, first);
+                if (kinstr > 1) umma_f16<kPair>(d, da + 2, db + 2, idesc, 1u);
+                if (kinstr > 2) umma_f16<kPair>(d, da + 4, db + 4, idesc, 1u);
+                if (kinstr > 3) umma_f16<kPair>(d, da + 6, db + 6, idesc, 1u);
               }
-              if (!p.b_resident) {
-                if (p.mc) umma_commit_mc(&b_empty[b_stage], (uint16_t)3);   // both CTAs of the pair must be done with the stage
-                else umma_commit(&b_empty[b_stage]);
-              }
-              if (p.strided) umma_commit(&a_empty[a_stage]);
+              if (!p.b_resident) umma_commit<kPair>(&b_empty[b_stage]);
+              if (kStrided) umma_commit<kPair>(&a_empty[a_stage]);
             }
             __syncwarp();
             if (!p.b_resident) {
               if (++b_stage == p.b_stages) { b_stage = 0; b_phase ^= 1; }
             }
-            if (p.strided) {
+            if (kStrided) {
               if (++a_stage == p.a_stages) { a_stage = 0; a_phase ^= 1; }
             }
           }
           if (!ok) break;
-          if (!p.strided) {
-            if (elect_one()) umma_commit(&a_empty[a_stage]);
+          if (!kStrided) {
+            if (elect_one()) umma_commit<kPair>(&a_empty[a_stage]);
             __syncwarp();
             if (++a_stage == p.a_stages) { a_stage = 0; a_phase ^= 1; }
           }
         }
         if (!ok) break;
         b_loaded = true;
-        if (elect_one()) umma_commit(&tfull_bar[acc]);
+        if (elect_one()) umma_commit<kPair>(&tfull_bar[acc]);
         __syncwarp();
         if (p.acc_bufs == 2) {
           acc ^= 1;
@@ -554,7 +632,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           acc_phase ^= 1;
         }
       }
-      if (p.dbg && blockIdx.x == 0 && lane == 0) {
+      if (p.dbg && blockIdx.x == 0 && lane == 0 && iss == 0) {
         p.dbg[6] = (unsigned long long)w_a;
         p.dbg[7] = (unsigned long long)w_b;
         p.dbg[8] = (unsigned long long)w_t;
@@ -569,174 +647,236 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int split = ((p.n_tile / 2 + 31) / 32) * 32;
     const int col_lo = half ? split : 0;
     const int col_hi = half ? p.n_tile : (split < p.n_tile ? split : p.n_tile);
-    const float* v_scale = vec;
-    const float* v_bias = vec + p.vec_n;
-    const float* v_slope = vec + 2 * p.vec_n;
-    const float* v_scale2 = vec + 3 * p.vec_n;
-    const float* v_bias2 = vec + 4 * p.vec_n;
+    const int nch = col_hi > col_lo ? (col_hi - col_lo + 31) / 32 : 0;     // chunks per 128-row sub-tile for this warp
+    // per-channel vectors, as shared-memory byte addresses (explicit ld.shared: through a generic pointer these were LD.E)
+    const uint32_t v_scale = smem_u32(vec), v_bias = v_scale + 4u * p.vec_n, v_slope = v_scale + 8u * p.vec_n,
+                   v_scale2 = v_scale + 12u * p.vec_n, v_bias2 = v_scale + 16u * p.vec_n;
     // this warp's 2 KB transpose buffer: 32 rows x 64 B (32 fp16 channels), 16-byte pieces XOR-swizzled by
     // (row >> 1) & 3 so that both the row-wise writes and the 4-lanes-per-row read-back are conflict-free
     uint8_t* stg = stage_buf + (warp - kEpiWarp0) * 2048;
     const uint32_t stg_w = smem_u32(stg) + (uint32_t)(lane * 64);          // my row, as writer
     const int w_sw = (lane >> 1) & 3;
     const int rb_piece = lane & 3;                                          // as reader: piece rb_piece of row i*8 + lane/4
+    const uint32_t tempty_l0 = kPair ? leader_addr(&tempty_bar[0]) : 0u, tempty_l1 = kPair ? leader_addr(&tempty_bar[1]) : 0u;
     int acc = 0;
     uint32_t acc_phase = 0;
     bool ok = true;
     long long w_full = 0, t_epi = 0, t_ld = 0;
-    for (int tile = blockIdx.x; tile - mc_rank < total_tiles; tile += gridDim.x) {
-      const int mt_idx = tile / p.n_tiles, nt = tile - mt_idx * p.n_tiles;
-      const int n0 = nt * p.n_tile;
-      const long long row0 = (long long)mt_idx * tile_rows + row_in_tile;
-      RowInfo ri = row_info(p, row0);
-      // residual prefetch for sub-tile 0 (independent of the accumulator): 4 chunks x 32 channels
-      uint4 R[4][4];
-      if (kRes) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const int ch = n0 + col_lo + c * 32;
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            R[c][g] = make_uint4(0, 0, 0, 0);
-            if (ri.valid && col_lo + c * 32 < col_hi && ch + g * 8 < p.out_c_store)
-              R[c][g] = *(const uint4*)(p.residual + ri.orow * p.res_cp + ch + g * 8);
-          }
-        }
-      }
-      if (ok) ok = mbar_wait_t(&tfull_bar[acc], acc_phase, p.err, 104, w_full, p.dbg != nullptr);
-      ok = __all_sync(0xffffffffu, ok);
-      if (!ok) break;
-      tc_fence_after();
-      const long long te0 = clock64();
-      for (int j = 0; j < p.mt; ++j) {
-        RowInfo rn;
-        rn.valid = false;
-        rn.orow = 0;
-        if (j + 1 < p.mt) rn = row_info(p, row0 + (long long)(j + 1) * kBlockM);
-        // rows this lane writes back after the transpose: i*8 + lane/4, i = 0..3
-        long long wrow[4];
-        bool wvalid[4];
-        if (kOutMode == 0) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int src = i * 8 + (lane >> 2);
-            wrow[i] = __shfl_sync(0xffffffffu, ri.orow, src);
-            wvalid[i] = __shfl_sync(0xffffffffu, ri.valid ? 1 : 0, src) != 0;
-          }
-        }
-        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256 + j * p.sub_cols);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const int col = col_lo + c * 32;
-          if (col >= col_hi) break;
-          uint32_t v[32];
-          __syncwarp();   // tcgen05.ld is .sync.aligned; also orders the previous read-back before this chunk's staging writes
-          const long long tl0 = clock64();
-          tmem_ld32(t_row + col, v);
-          t_ld += clock64() - tl0;
-          const int ch = n0 + col;
-          float y[32];
-#pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            const float4 s4 = *(const float4*)(v_scale + ch + g * 4);
-            const float4 b4 = *(const float4*)(v_bias + ch + g * 4);
-            y[g * 4 + 0] = fmaf(__uint_as_float(v[g * 4 + 0]), s4.x, b4.x);
-            y[g * 4 + 1] = fmaf(__uint_as_float(v[g * 4 + 1]), s4.y, b4.y);
-            y[g * 4 + 2] = fmaf(__uint_as_float(v[g * 4 + 2]), s4.z, b4.z);
-            y[g * 4 + 3] = fmaf(__uint_as_float(v[g * 4 + 3]), s4.w, b4.w);
-          }
-          if (kOutMode == 2) {
-            if (ri.valid) {
-              float* o = p.out_f32 + ri.orow * p.out_f32_stride + ch;
-#pragma unroll
-              for (int g = 0; g < 8; ++g)
-                if (ch + g * 4 < p.out_f32_cols) *(float4*)(o + g * 4) = make_float4(y[g * 4], y[g * 4 + 1], y[g * 4 + 2], y[g * 4 + 3]);
-            }
-          } else {
-            if (kRes) {
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                float f[8];
-                unpack_h8(R[c][g], f);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) y[g * 8 + e] += f[e];
-              }
-            }
-            if (kAct == PCB_ACT_RELU) {
-#pragma unroll
-              for (int e = 0; e < 32; ++e) y[e] = fmaxf(y[e], 0.f);
-            } else if (kAct == PCB_ACT_PRELU) {
-#pragma unroll
-              for (int g = 0; g < 8; ++g) {
-                const float4 a4 = *(const float4*)(v_slope + ch + g * 4);
-                y[g * 4 + 0] = y[g * 4 + 0] >= 0.f ? y[g * 4 + 0] : y[g * 4 + 0] * a4.x;
-                y[g * 4 + 1] = y[g * 4 + 1] >= 0.f ? y[g * 4 + 1] : y[g * 4 + 1] * a4.y;
-                y[g * 4 + 2] = y[g * 4 + 2] >= 0.f ? y[g * 4 + 2] : y[g * 4 + 2] * a4.z;
-                y[g * 4 + 3] = y[g * 4 + 3] >= 0.f ? y[g * 4 + 3] : y[g * 4 + 3] * a4.w;
-              }
-            }
-            if (kOutMode == 1) {
-              if (ri.valid) {
-                float* o = p.out_s32 + ri.orow * p.out_cp + ch;
-#pragma unroll
-                for (int g = 0; g < 8; ++g)
-                  if (ch + g * 4 < p.out_c_store) *(float4*)(o + g * 4) = make_float4(y[g * 4], y[g * 4 + 1], y[g * 4 + 2], y[g * 4 + 3]);
-              }
-            } else {
-              // transpose through shared memory so that 4 lanes write one row's 64 contiguous bytes (full sectors)
-#pragma unroll
-              for (int g = 0; g < 4; ++g) st_shared_v4(stg_w + (uint32_t)(((g ^ w_sw) & 3) * 16), pack_h8(y + g * 8));
-              __syncwarp();
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const int r = i * 8 + (lane >> 2);
-                const uint4 o4 = ld_shared_v4(smem_u32(stg) + (uint32_t)(r * 64 + ((rb_piece ^ (r >> 1)) & 3) * 16));
-                if (wvalid[i] && ch + rb_piece * 8 < p.out_c_store) *(uint4*)(p.out + wrow[i] * p.out_cp + ch + rb_piece * 8) = o4;
-              }
-              if (kOut2) {
-#pragma unroll
-                for (int g = 0; g < 8; ++g) {
-                  const float4 s4 = *(const float4*)(v_scale2 + ch + g * 4);
-                  const float4 b4 = *(const float4*)(v_bias2 + ch + g * 4);
-                  y[g * 4 + 0] = fmaf(y[g * 4 + 0], s4.x, b4.x);
-                  y[g * 4 + 1] = fmaf(y[g * 4 + 1], s4.y, b4.y);
-                  y[g * 4 + 2] = fmaf(y[g * 4 + 2], s4.z, b4.z);
-                  y[g * 4 + 3] = fmaf(y[g * 4 + 3], s4.w, b4.w);
-                }
-                __syncwarp();
-#pragma unroll
-                for (int g = 0; g < 4; ++g) st_shared_v4(stg_w + (uint32_t)(((g ^ w_sw) & 3) * 16), pack_h8(y + g * 8));
-                __syncwarp();
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const int r = i * 8 + (lane >> 2);
-                  const uint4 o4 = ld_shared_v4(smem_u32(stg) + (uint32_t)(r * 64 + ((rb_piece ^ (r >> 1)) & 3) * 16));
-                  if (wvalid[i] && ch + rb_piece * 8 < p.out_c_store) *(uint4*)(p.out2 + wrow[i] * p.out2_cp + ch + rb_piece * 8) = o4;
-                }
-              }
-            }
-          }
-          // refill this chunk's residual registers with the next sub-tile's row
-          if (kRes && j + 1 < p.mt) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              R[c][g] = make_uint4(0, 0, 0, 0);
-              if (rn.valid && ch + g * 8 < p.out_c_store)
-                R[c][g] = *(const uint4*)(p.residual + rn.orow * p.res_cp + ch + g * 8);
-            }
-          }
-        }
-        ri = rn;
-      }
+    const bool timed = p.dbg != nullptr;
+    const int my_tiles = tile0 < total_tiles ? (total_tiles - tile0 + tile_step - 1) / tile_step : 0;
+    auto tile_done = [&]() {
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-      t_epi += clock64() - te0;
+      if (lane == 0) {
+        if (kPair) mbar_arrive_cluster(acc ? tempty_l1 : tempty_l0);
+        else mbar_arrive(&tempty_bar[acc]);
+      }
       if (p.acc_bufs == 2) {
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       } else {
         acc_phase ^= 1;
+      }
+    };
+    if (nch == 0) {
+      // no columns for this warp (n_tile <= 32, upper half): it only takes part in the accumulator hand-shake
+      for (int ti = 0; ti < my_tiles; ++ti) {
+        ok = __all_sync(0xffffffffu, mbar_wait(&tfull_bar[acc], acc_phase, p.err, 104));
+        if (!ok) break;
+        tile_done();
+      }
+    } else {
+      // The warp's work is the flat sequence g = 0 .. my_tiles*S-1 of 32-column chunks, S = mt*nch per tile, in the order
+      // (tile, sub-tile j, chunk c).  Residual rows are fetched FOUR chunks ahead of their use into a ring of four register
+      // sets (static slot = g & 3 through the 4x unrolled inner loop), i.e. at least one whole tile ahead: with the fetch
+      // issued at the start of the tile that needs it, the narrow residual layers (one or two chunks per tile and warp)
+      // exposed a global-memory latency per chunk and ran epilogue-bound (MMA warp waiting on TMEM 14-27 % of the time).
+      const int S = p.mt * nch;
+      const int G = my_tiles * S;
+      uint4 R[4][4];
+      // the prefetch stream runs four chunks ahead of the consumer; (p_tile, p_j, p_c) is its position, p_row its row
+      int p_g = 0, p_tile = tile0, p_j = 0, p_c = 0;
+      RowInfo p_row;
+      p_row.valid = false;
+      p_row.orow = 0;
+      int p_n0 = 0;
+      auto res_load = [&](uint4 (&dst)[4]) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) dst[e] = make_uint4(0, 0, 0, 0);
+        if (p_g >= G) return;
+        if (p_c == 0) {
+          const int mt_idx = p_tile / p.n_tiles;
+          p_n0 = (p_tile - mt_idx * p.n_tiles) * p.n_tile;
+          p_row = row_info<kStrided>(p, (long long)(kPair ? 2 * mt_idx + cta_rank : mt_idx) * tile_rows + p_j * kBlockM + row_in_tile);
+        }
+        const int ch = p_n0 + col_lo + p_c * 32;
+        if (p_row.valid) {
+          const __half* src = p.residual + p_row.orow * p.res_cp + ch;
+          if (ch + 32 <= p.out_c_store) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) dst[e] = *(const uint4*)(src + e * 8);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (ch + e * 8 < p.out_c_store) dst[e] = *(const uint4*)(src + e * 8);
+          }
+        }
+        ++p_g;
+        if (++p_c == nch) {
+          p_c = 0;
+          if (++p_j == p.mt) {
+            p_j = 0;
+            p_tile += tile_step;
+          }
+        }
+      };
+      if (kRes) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) res_load(R[u]);
+      }
+      int ti = 0, j = 0, c = 0;            // decode of g, advanced incrementally
+      int n0 = 0;
+      long long row0 = 0;
+      RowInfo ri;
+      ri.valid = false;
+      ri.orow = 0;
+      // rows this lane writes back after the transpose: i*8 + lane/4, i = 0..3, as element offsets of piece rb_piece
+      long long woff[4] = {0, 0, 0, 0}, woff2[4] = {0, 0, 0, 0};
+      bool wvalid[4] = {false, false, false, false};
+      long long te0 = 0;
+      for (int g0 = 0; ok && g0 < G; g0 += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int g = g0 + u;
+          if (g >= G) break;
+          if (j == 0 && c == 0) {
+            // first chunk of a tile: wait for its accumulator
+            const int tile = tile0 + ti * tile_step;
+            const int mt_idx = tile / p.n_tiles, nt = tile - mt_idx * p.n_tiles;
+            n0 = nt * p.n_tile;
+            row0 = (long long)(kPair ? 2 * mt_idx + cta_rank : mt_idx) * tile_rows + row_in_tile;
+            ok = __all_sync(0xffffffffu, mbar_wait_t(&tfull_bar[acc], acc_phase, p.err, 104, w_full, p.dbg != nullptr));
+            if (!ok) break;
+            tc_fence_after();
+            if (timed) te0 = clock64();
+          }
+          if (c == 0) {
+            ri = row_info<kStrided>(p, row0 + (long long)j * kBlockM);
+            if (kOutMode == 0) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int src = i * 8 + (lane >> 2);
+                const long long wr = __shfl_sync(0xffffffffu, ri.orow, src);
+                woff[i] = wr * p.out_cp + rb_piece * 8;
+                if (kOut2) woff2[i] = wr * p.out2_cp + rb_piece * 8;
+                wvalid[i] = __shfl_sync(0xffffffffu, ri.valid ? 1 : 0, src) != 0;
+              }
+            }
+          }
+          const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256 + j * p.sub_cols);
+          const int col = col_lo + c * 32;
+          {
+            uint32_t v[32];
+            __syncwarp();   // tcgen05.ld is .sync.aligned; also orders the previous read-back before this chunk's staging writes
+            long long tl0 = 0;
+            if (timed) tl0 = clock64();
+            tmem_ld32(t_row + col, v);
+            if (timed) t_ld += clock64() - tl0;
+            const int ch = n0 + col;
+            float y[32];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float4 s4 = ld_shared_f4(v_scale + 4u * (uint32_t)(ch + e * 4));
+              const float4 b4 = ld_shared_f4(v_bias + 4u * (uint32_t)(ch + e * 4));
+              y[e * 4 + 0] = fmaf(__uint_as_float(v[e * 4 + 0]), s4.x, b4.x);
+              y[e * 4 + 1] = fmaf(__uint_as_float(v[e * 4 + 1]), s4.y, b4.y);
+              y[e * 4 + 2] = fmaf(__uint_as_float(v[e * 4 + 2]), s4.z, b4.z);
+              y[e * 4 + 3] = fmaf(__uint_as_float(v[e * 4 + 3]), s4.w, b4.w);
+            }
+            if (kOutMode == 2) {
+              if (ri.valid) {
+                float* o = p.out_f32 + ri.orow * p.out_f32_stride + ch;
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                  if (ch + e * 4 < p.out_f32_cols) *(float4*)(o + e * 4) = make_float4(y[e * 4], y[e * 4 + 1], y[e * 4 + 2], y[e * 4 + 3]);
+              }
+            } else {
+              if (kRes) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  float f[8];
+                  unpack_h8(R[u][e], f);
+#pragma unroll
+                  for (int k = 0; k < 8; ++k) y[e * 8 + k] += f[k];
+                }
+              }
+              if (kAct == PCB_ACT_RELU) {
+#pragma unroll
+                for (int e = 0; e < 32; ++e) y[e] = fmaxf(y[e], 0.f);
+              } else if (kAct == PCB_ACT_PRELU) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  const float4 a4 = ld_shared_f4(v_slope + 4u * (uint32_t)(ch + e * 4));
+                  y[e * 4 + 0] = y[e * 4 + 0] >= 0.f ? y[e * 4 + 0] : y[e * 4 + 0] * a4.x;
+                  y[e * 4 + 1] = y[e * 4 + 1] >= 0.f ? y[e * 4 + 1] : y[e * 4 + 1] * a4.y;
+                  y[e * 4 + 2] = y[e * 4 + 2] >= 0.f ? y[e * 4 + 2] : y[e * 4 + 2] * a4.z;
+                  y[e * 4 + 3] = y[e * 4 + 3] >= 0.f ? y[e * 4 + 3] : y[e * 4 + 3] * a4.w;
+                }
+              }
+              if (kOutMode == 1) {
+                if (ri.valid) {
+                  float* o = p.out_s32 + ri.orow * p.out_cp + ch;
+#pragma unroll
+                  for (int e = 0; e < 8; ++e)
+                    if (ch + e * 4 < p.out_c_store) *(float4*)(o + e * 4) = make_float4(y[e * 4], y[e * 4 + 1], y[e * 4 + 2], y[e * 4 + 3]);
+                }
+              } else {
+                // transpose through shared memory so that 4 lanes write one row's 64 contiguous bytes (full sectors)
+                const bool piece_ok = ch + rb_piece * 8 < p.out_c_store;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) st_shared_v4(stg_w + (uint32_t)(((e ^ w_sw) & 3) * 16), pack_h8(y + e * 8));
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const int r = i * 8 + (lane >> 2);
+                  const uint4 o4 = ld_shared_v4(smem_u32(stg) + (uint32_t)(r * 64 + ((rb_piece ^ (r >> 1)) & 3) * 16));
+                  if (wvalid[i] && piece_ok) *(uint4*)(p.out + woff[i] + ch) = o4;
+                }
+                if (kOut2) {
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) {
+                    const float4 s4 = ld_shared_f4(v_scale2 + 4u * (uint32_t)(ch + e * 4));
+                    const float4 b4 = ld_shared_f4(v_bias2 + 4u * (uint32_t)(ch + e * 4));
+                    y[e * 4 + 0] = fmaf(y[e * 4 + 0], s4.x, b4.x);
+                    y[e * 4 + 1] = fmaf(y[e * 4 + 1], s4.y, b4.y);
+                    y[e * 4 + 2] = fmaf(y[e * 4 + 2], s4.z, b4.z);
+                    y[e * 4 + 3] = fmaf(y[e * 4 + 3], s4.w, b4.w);
+                  }
+                  __syncwarp();
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) st_shared_v4(stg_w + (uint32_t)(((e ^ w_sw) & 3) * 16), pack_h8(y + e * 8));
+                  __syncwarp();
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    const int r = i * 8 + (lane >> 2);
+                    const uint4 o4 = ld_shared_v4(smem_u32(stg) + (uint32_t)(r * 64 + ((rb_piece ^ (r >> 1)) & 3) * 16));
+                    if (wvalid[i] && piece_ok) *(uint4*)(p.out2 + woff2[i] + ch) = o4;
+                  }
+                }
+              }
+            }
+          }
+          if (kRes) res_load(R[u]);     // this slot's next use: four chunks from now
+          if (++c == nch) {
+            c = 0;
+            if (++j == p.mt) {
+              j = 0;
+              ++ti;
+              tile_done();
+              if (timed) t_epi += clock64() - te0;
+            }
+          }
+        }
       }
     }
     if (p.dbg && blockIdx.x == 0 && warp == kEpiWarp0 && lane == 0) {
@@ -748,9 +888,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
   tc_fence_before();
   __syncthreads();
-  if (p.mc) cluster_sync_all();     // no CTA leaves while its peer can still multicast into it or arrive on its barriers
+  if (kPair) cluster_sync_all();     // no CTA leaves while its peer can still commit to / arrive on its barriers or read its operands
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    if (kPair) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
   }
   if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) {
     p.dbg[2] = (unsigned long long)clock64();
@@ -889,6 +1030,16 @@ int pcb_conv_tc2(pcb_ctx* c, const ConvArgs& a) {
   p.slope = w.slope;
   p.err = c->d_err;
   p.desc_mode = env_int("PCB_DESC_MODE", 1);
+  {
+    auto fd = [](int d, uint32_t* mul, int* shift) {
+      int sft = 0;
+      while ((1LL << sft) < d) ++sft;
+      *mul = (uint32_t)((((1ULL << sft) - (unsigned long long)d) << 32) / (unsigned long long)d + 1ULL);
+      *shift = sft;
+    };
+    fd(p.hp * p.wp > 0 ? p.hp * p.wp : 1, &p.fd_plane_mul, &p.fd_plane_shift);
+    fd(p.wp > 0 ? p.wp : 1, &p.fd_wp_mul, &p.fd_wp_shift);
+  }
   if (a.out_f32) {
     p.out_f32 = a.out_f32;
     p.out_f32_stride = a.out_f32_stride;
@@ -916,9 +1067,9 @@ int pcb_conv_tc2(pcb_ctx* c, const ConvArgs& a) {
   }
   if (w.n_tile % 16 || w.n_tile > 256 || w.n_tile < 16) return pcb_fail(c, PCB_ERR_ARG, "conv_tc2: bad n_tile");
   p.sub_cols = pcb_round_up(w.n_tile, 32);
-  p.b_bytes = w.n_tile * p.row_bytes;
   const int ksteps = p.taps * p.kchunks;
   const int fixed = 5 * p.vec_n * 4 + kEpiWarps * 2048 + (2 * kMaxA + 2 * kMaxB + 4) * 8 + 16 + 1024;
+  const int room = kSmemBudget - fixed;
 
   // stride-2 convolutions: GEMM on the output grid, one strided 4-D TMA load per tap (see Conv2Params::strided)
   const bool strided = !in.dense && a.stride == 2 && a.out && !env_int("PCB_CONV_NO_STRIDED", 0);
@@ -944,6 +1095,17 @@ int pcb_conv_tc2(pcb_ctx* c, const ConvArgs& a) {
     p.acc_bufs = 2;
   }
 
+  // Pair mode (2-CTA cluster, cta_group::2): PCB_CONV_PAIR = 0 never, 1 (default) by the policy below, 2 wherever it is legal.
+  // Policy from per-layer A/B runs on B200 (tools/profile_layers.py with PCB_CONV_PAIR=0/2, profiles/): see DESIGN.md 3.1.
+  static const int pair_mode = env_int("PCB_CONV_PAIR", 1);
+  const long long m_tiles128 = ((long long)p.rows + kBlockM - 1) / kBlockM;
+  const bool pair_legal = !strided && (c->num_sms % 2 == 0) && m_tiles128 >= 4;
+  const bool pair_wanted = pair_mode == 2 || (pair_mode == 1 && w.n_tile >= kPairMinN && p.kchunks >= 2 && m_tiles128 * p.n_tiles >= 2 * c->num_sms);
+  p.pair = (pair_legal && pair_wanted) ? 1 : 0;
+  p.b_rows = p.pair ? w.n_tile / 2 : w.n_tile;
+  p.b_bytes = p.b_rows * p.row_bytes;
+  const int units = p.pair ? c->num_sms / 2 : c->num_sms;     // tiles in flight: one per CTA, or one per CTA pair
+
   // choose MT (1 or 2): fewer L2 bytes per FLOP at MT=2, but half as many tiles to spread over the SMs
   const int force_mt = env_int("PCB_CONV_MT", 0);
   int best_mt = 0;
@@ -957,9 +1119,10 @@ int pcb_conv_tc2(pcb_ctx* c, const ConvArgs& a) {
     if (!plan_a(q, mt, &a2)) continue;
     const int min_b = ksteps < 3 ? ksteps : 3;
     if (2 * q.a_stage_bytes + min_b * q.b_bytes + fixed > kSmemBudget) continue;
-    const long long m_tiles = ((long long)p.rows + mt * kBlockM - 1) / (mt * kBlockM);
+    const long long unit_rows = (long long)mt * kBlockM * (p.pair ? 2 : 1);
+    const long long m_tiles = ((long long)p.rows + unit_rows - 1) / unit_rows;
     const long long tiles = m_tiles * p.n_tiles;
-    const long long waves = (tiles + c->num_sms - 1) / c->num_sms;
+    const long long waves = (tiles + units - 1) / units;
     // relative time per tile, measured on B200 (tools/profile_layers.py, PCB_CONV_MT): MT=2 shares each weight stage
     // between two accumulators and is ~1.4x faster per row while TMEM can still be double-buffered (2*N <= 256);
     // for N > 128 it would be single-buffered and the exposed epilogue costs more than the saved weight traffic
@@ -970,10 +1133,20 @@ int pcb_conv_tc2(pcb_ctx* c, const ConvArgs& a) {
     if (!best_mt) return pcb_conv_tc(c, a);   // no shared-memory plan (very wide maps): baseline kernel
     plan_a(p, best_mt, &a2_rows);
     if (env_int("PCB_TAP_ALIGN", 0)) for (int t = 0; t < 9; ++t) p.tap_off[t] &= ~1023;   // timing experiment only (wrong sums)
-    p.m_tiles = (int)(((long long)p.rows + p.mt * kBlockM - 1) / (p.mt * kBlockM));
+    const long long unit_rows = (long long)p.mt * kBlockM * (p.pair ? 2 : 1);
+    p.m_tiles = (int)(((long long)p.rows + unit_rows - 1) / unit_rows);
     p.acc_bufs = (p.mt * p.sub_cols <= 256) ? 2 : 1;
   }
-  const int room = kSmemBudget - fixed;
+  // two MMA issuers where the K step can be split by accumulator (PCB_CONV_ISS=1 forces one)
+  static const int iss_mode = env_int("PCB_CONV_ISS", 2);
+  p.n_iss = 1;
+  p.split_n = 0;
+  if (iss_mode >= 2) {
+    if (p.mt == 2) p.n_iss = 2;
+    else if (w.n_tile % 32 == 0) { p.n_iss = 2; p.split_n = 1; }
+  }
+  p.b_nloads = (p.pair && p.split_n) ? 2 : 1;
+  p.b_load_rows = p.b_rows / p.b_nloads;
   p.b_resident = 0;
   if (p.n_tiles == 1 && ksteps <= kMaxB && 2 * p.a_stage_bytes + ksteps * p.b_bytes <= room && !env_int("PCB_CONV_NO_RESIDENT", 0)) {
     p.b_resident = 1;
@@ -996,12 +1169,6 @@ int pcb_conv_tc2(pcb_ctx* c, const ConvArgs& a) {
     if (p.b_stages > kMaxB) p.b_stages = kMaxB;
   }
   if (p.a_stages > kMaxA) p.a_stages = kMaxA;
-  // Experiment, off by default (PCB_CONV_MC=1): measured on B200 it changes nothing (14x14 256->256: 873 vs 872 TFLOP/s) --
-  // at cluster size 2 unicast loads of the same lines are already served once by L2, and these layers are paced by the
-  // ~175-cycle SS-mode tcgen05.mma (tensor pipe 70-75 % active), not by L2->SM bytes.  What would help is cta_group::2
-  // (each SM reads only half of B from its own shared memory per MMA).
-  p.mc = (!strided && !p.b_resident && p.n_tiles == 1 && p.n_tile >= 128 && p.n_tile % 32 == 0 && p.m_tiles >= 2 &&
-          env_int("PCB_CONV_MC", 0)) ? 1 : 0;
   const size_t smem = (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * p.b_bytes + fixed;
 
   CUtensorMap tmA, tmA2, tmB;
@@ -1015,22 +1182,21 @@ int pcb_conv_tc2(pcb_ctx* c, const ConvArgs& a) {
     if (!make_map_2d(&tmA2, in.data, (uint64_t)p.rows, (uint64_t)in.cp, (uint64_t)in.cp, (uint32_t)a2_rows, p.kc))
       return pcb_fail(c, PCB_ERR_CUDA, "cuTensorMapEncodeTiled(A2) failed");
   }
-  if (!make_map_2d(&tmB, w.w, (uint64_t)w.npad, (uint64_t)w.taps * w.cin_w, (uint64_t)w.taps * w.cin_w, (uint32_t)(p.mc ? w.n_tile / 2 : w.n_tile), p.kc))
+  if (!make_map_2d(&tmB, w.w, (uint64_t)w.npad, (uint64_t)w.taps * w.cin_w, (uint64_t)w.taps * w.cin_w, (uint32_t)p.b_load_rows, p.kc))
     return pcb_fail(c, PCB_ERR_CUDA, "cuTensorMapEncodeTiled(B) failed");
 
   const int total = p.m_tiles * p.n_tiles;
-  int grid = total < c->num_sms ? total : c->num_sms;
-  if (p.mc) grid = (grid + 1) & ~1;          // whole 2-CTA clusters (148 SMs: 74 pairs)
+  const int grid = p.pair ? 2 * (total < units ? total : units) : (total < c->num_sms ? total : c->num_sms);
   // algorithmic FLOPs of this layer: 2 * output pixels * cout * cin * taps (real, unpadded extents)
   double out_px = in.dense ? (double)in.n : (double)in.n * (in.h / p.stride) * (in.w / p.stride);
   const double k_real = (w.taps == 1 && w.cin == 3) ? 27.0 : (double)w.cin * w.taps;
   char desc[200];
   desc[0] = 0;
   if (c->profile)
-    snprintf(desc, sizeof desc, "n=%d,h=%d,w=%d,cin=%d,cout=%d,taps=%d,stride=%d,ntile=%d,mt=%d,tiles=%d,grid=%d,res=%d,f32out=%d,out2=%d,ast=%d,bst=%d,bres=%d,sbox=%dx%dx%d,mc=%d",
+    snprintf(desc, sizeof desc, "n=%d,h=%d,w=%d,cin=%d,cout=%d,taps=%d,stride=%d,ntile=%d,mt=%d,tiles=%d,grid=%d,res=%d,f32out=%d,out2=%d,ast=%d,bst=%d,bres=%d,sbox=%dx%dx%d,pair=%d,iss=%d",
              in.n, in.h, in.w, w.cin, w.cout, w.taps, p.stride, p.n_tile, p.mt, total, grid, a.residual ? 1 : 0,
              (a.out && a.out->f32) ? 1 : 0, a.out2 ? 1 : 0, p.a_stages, p.b_stages, p.b_resident, p.strided ? p.s_nb : 0,
-             p.strided ? p.s_by : 0, p.strided ? p.s_bx : 0, p.mc);
+             p.strided ? p.s_by : 0, p.strided ? p.s_bx : 0, p.pair, p.n_iss + p.split_n * 10);
   static const int debug = env_int("PCB_CONV_DEBUG", 0);
   static unsigned long long* dbg_dev = nullptr;
   if (debug && c->profile) {
@@ -1043,14 +1209,14 @@ int pcb_conv_tc2(pcb_ctx* c, const ConvArgs& a) {
     if (mode != 0 && (p.residual || p.out2)) return pcb_fail(c, PCB_ERR_ARG, "conv_tc2: fp32 outputs take no residual / second output");
     const int key = mode == 0 ? (p.act * 4 + (p.residual ? 2 : 0) + (p.out2 ? 1 : 0)) : (100 + mode * 4 + p.act);
     cudaError_t le = cudaErrorInvalidValue;
-#define PCB_TC2_CASE(KEY, ACT, RES, OUT2, MODE)                                                                         \
-  case KEY: {                                                                                                          \
+#define PCB_TC2_LAUNCH(ACT, RES, OUT2, MODE, VAR)                                                                       \
+  {                                                                                                                    \
     static bool attr = false;                                                                                          \
     if (!attr) {                                                                                                       \
-      cudaFuncSetAttribute(conv_tc2_kernel<ACT, RES, OUT2, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
+      cudaFuncSetAttribute(conv_tc2_kernel<ACT, RES, OUT2, MODE, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
       attr = true;                                                                                                     \
     }                                                                                                                  \
-    if (p.mc) {                                                                                                        \
+    if (VAR == kVarPair) {                                                                                             \
       cudaLaunchConfig_t cfg = {};                                                                                     \
       cfg.gridDim = dim3(grid);                                                                                        \
       cfg.blockDim = dim3(kThreads);                                                                                   \
@@ -1063,13 +1229,18 @@ int pcb_conv_tc2(pcb_ctx* c, const ConvArgs& a) {
       at[0].val.clusterDim.z = 1;                                                                                      \
       cfg.attrs = at;                                                                                                  \
       cfg.numAttrs = 1;                                                                                                \
-      le = cudaLaunchKernelEx(&cfg, conv_tc2_kernel<ACT, RES, OUT2, MODE>, tmA, tmA2, tmB, p);                         \
+      le = cudaLaunchKernelEx(&cfg, conv_tc2_kernel<ACT, RES, OUT2, MODE, VAR>, tmA, tmA2, tmB, p);                    \
     } else {                                                                                                           \
-      conv_tc2_kernel<ACT, RES, OUT2, MODE><<<grid, kThreads, smem, c->stream>>>(tmA, tmA2, tmB, p);                   \
+      conv_tc2_kernel<ACT, RES, OUT2, MODE, VAR><<<grid, kThreads, smem, c->stream>>>(tmA, tmA2, tmB, p);              \
       le = cudaSuccess;                                                                                                \
     }                                                                                                                  \
-    break;                                                                                                             \
   }
+#define PCB_TC2_CASE(KEY, ACT, RES, OUT2, MODE)                                                                         \
+  case KEY:                                                                                                            \
+    if (p.pair) PCB_TC2_LAUNCH(ACT, RES, OUT2, MODE, kVarPair)                                                         \
+    else if (p.strided) PCB_TC2_LAUNCH(ACT, RES, OUT2, MODE, kVarStrided)                                              \
+    else PCB_TC2_LAUNCH(ACT, RES, OUT2, MODE, kVarHalo)                                                                \
+    break;
     switch (key) {
       PCB_TC2_CASE(0, 0, false, false, 0)
       PCB_TC2_CASE(1, 0, false, true, 0)
@@ -1090,6 +1261,7 @@ int pcb_conv_tc2(pcb_ctx* c, const ConvArgs& a) {
       default: break;
     }
 #undef PCB_TC2_CASE
+#undef PCB_TC2_LAUNCH
     if (le != cudaSuccess) return pcb_fail(c, PCB_ERR_ARG, "conv_tc2: unsupported epilogue combination");
   }
   PCB_LAUNCH_CHECK(c, "conv_tc2_kernel");

@@ -12,6 +12,7 @@ ap.add_argument("--n", type=int, default=64)
 ap.add_argument("--faces", type=int, default=128)
 ap.add_argument("--out", default="gpurun_out/layers.csv")
 ap.add_argument("--impl", type=int, default=0)
+ap.add_argument("--reps", type=int, default=1, help="profiled passes (times are summed; divide by reps)")
 ap.add_argument("--sustain", type=int, default=0, help="run the ArcFace pass this many times back to back and report TF/s + clocks")
 args = ap.parse_args()
 if os.path.exists(args.out):
@@ -33,13 +34,14 @@ if os.path.exists(args.out):
     os.remove(args.out)
 eng.set_profile(True)
 t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True); t2 = torch.cuda.Event(enable_timing=True)
-t0.record(eng.stream)
-eng.detect(frames, args.S, 0.5)
-t1.record(eng.stream)
-eng.embed(chips, args.faces, True)
-t2.record(eng.stream)
+for rep in range(args.reps):
+    t0.record(eng.stream)
+    eng.detect(frames, args.S, 0.5)
+    t1.record(eng.stream)
+    eng.embed(chips, args.faces, True)
+    t2.record(eng.stream)
 ms, fl, n = eng.profile_read()
-print(f"scrfd pass {t0.elapsed_time(t1):.3f} ms for {args.n} frames; arcface pass {t1.elapsed_time(t2):.3f} ms for {2*args.faces} images")
+print(f"scrfd pass {t0.elapsed_time(t1):.3f} ms for {args.n} frames; arcface pass {t1.elapsed_time(t2):.3f} ms for {2*args.faces} images (last of {args.reps} passes)")
 print(f"conv total {ms:.3f} ms, {fl/1e12:.3f} TFLOP -> {fl/ms/1e9:.1f} TFLOP/s over {n} launches")
 rows = collections.OrderedDict()
 for line in open(args.out):
