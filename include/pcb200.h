@@ -38,9 +38,11 @@ const char* pcb_last_error(pcb_ctx* ctx);
 /* Waits for the stream and checks the device-side error word (watchdogs, capacity overflow). */
 int pcb_sync(pcb_ctx* ctx);
 /* 0 = tcgen05/TMEM implicit GEMM (default), 1 = CUDA-core validation kernel (tests only),
- * 2 = first tcgen05 formulation (one TMA load per tap; A/B baseline for profiles),
- * 3 = transposed tcgen05 experiment (couts on the UMMA M dimension). */
+ * 2 = first tcgen05 formulation (one TMA load per tap; A/B baseline for profiles). */
 int pcb_set_conv_impl(pcb_ctx* ctx, int impl);
+/* Geometry of the activation layout device buffers such as pcb_letterbox's patch tensor use: [n][h + pad][w + pad][c], image
+ * pixel (y, x) at [y + pad_lo][x + pad_lo], every other element zero (default build: pad_lo = 1, pad = 2, a ring of zeros). */
+void pcb_layout_pad(int* pad_lo, int* pad);
 /* Number of kernels this library launched on the context since the last reset. */
 long long pcb_launch_count(pcb_ctx* ctx);
 void pcb_reset_launch_count(pcb_ctx* ctx);
@@ -130,7 +132,7 @@ typedef struct pcb_detect_args {
 int pcb_detect(pcb_ctx* ctx, const pcb_detect_args* a);
 
 /* K1 alone: letterbox-resize + normalise + stem patch tensor.  out_dev is fp16
- * [n][S/2+2][S/2+2][32] (P-layout, ring of zeros). det_img_dev (optional, may be NULL) receives
+ * [n][S/2+pad][S/2+pad][32] (P-layout, see pcb_layout_pad). det_img_dev (optional, may be NULL) receives
  * the uint8 letterboxed image [n][S][S][3] for parity tests. */
 int pcb_letterbox(pcb_ctx* ctx, const uint8_t* frames_dev, int n, int h, int w, int S, int rot_deg,
                   int pad_replicate, void* out_dev, uint8_t* det_img_dev);

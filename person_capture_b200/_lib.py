@@ -12,6 +12,11 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PCB_LIB") or os.path.join(_HERE, "libpcb200.so")   # PCB_LIB: A/B another build of the library
 
+# P-layout padding (csrc/pcb_common.cuh kPadLo / kPad): activations are [n][h + P_PAD][w + P_PAD][cp], image pixel (y, x) at
+# [y + P_PAD_LO][x + P_PAD_LO], zeros elsewhere.  load() overwrites these with what the loaded library reports (pcb_layout_pad).
+P_PAD_LO = 1
+P_PAD = 2
+
 FEAT_DIM = 512
 CHIP = 112
 
@@ -22,7 +27,7 @@ FIX_NONE, FIX_SCALE, FIX_PADPROBE, FIX_UNPAD = 0, 1, 2, 3
 OPF_OUT_F32 = 1
 
 EXPORTS = (
-    "pcb_create", "pcb_destroy", "pcb_last_error", "pcb_sync", "pcb_set_conv_impl", "pcb_launch_count",
+    "pcb_create", "pcb_destroy", "pcb_last_error", "pcb_sync", "pcb_layout_pad", "pcb_set_conv_impl", "pcb_launch_count",
     "pcb_reset_launch_count", "pcb_set_profile", "pcb_profile_read", "pcb_model_load", "pcb_model_get_tensor", "pcb_resize_area", "pcb_resize_linear", "pcb_resize_factor",
     "pcb_detect", "pcb_letterbox", "pcb_decode_nms", "pcb_align", "pcb_embed", "pcb_set_bank", "pcb_match", "pcb_replay",
 )
@@ -124,5 +129,10 @@ def load():
         fn = getattr(lib, name)
         if fn.restype is C.c_int:
             pass
+    global P_PAD_LO, P_PAD
+    lo, pad = C.c_int(), C.c_int()
+    lib.pcb_layout_pad.restype = None
+    lib.pcb_layout_pad(C.byref(lo), C.byref(pad))
+    P_PAD_LO, P_PAD = lo.value, pad.value     # follow the library that was actually loaded (PCB_LIB A/B builds)
     _lib = lib
     return lib

@@ -118,8 +118,13 @@ extern "C" int pcb_sync(pcb_ctx* c) {
   return PCB_OK;
 }
 
+extern "C" void pcb_layout_pad(int* pad_lo, int* pad) {
+  if (pad_lo) *pad_lo = kPadLo;
+  if (pad) *pad = kPad;
+}
+
 extern "C" int pcb_set_conv_impl(pcb_ctx* c, int impl) {
-  if (impl < 0 || impl > 3) return pcb_fail(c, PCB_ERR_ARG, "conv impl must be 0..3");
+  if (impl < 0 || impl > 2) return pcb_fail(c, PCB_ERR_ARG, "conv impl must be 0..2");
   c->conv_impl = impl;
   return PCB_OK;
 }
@@ -215,7 +220,7 @@ extern "C" int pcb_model_load(pcb_ctx* c, int slot, const pcb_op* ops, int n_ops
       w.cin_w = pcb_round_up(cin_eff, 64);
       w.npad = op.cout <= 256 ? pcb_round_up(op.cout, 16) : pcb_round_up(op.cout, 256);
       w.n_tile = w.npad <= 256 ? w.npad : 256;
-      w.rows_alloc = pcb_round_up(w.npad, 128);   // zero rows up to a multiple of 128: conv_tc3 uses couts as the UMMA M dimension
+      w.rows_alloc = pcb_round_up(w.npad, 128);   // zero rows up to a multiple of 128 (TMA boxes of the weight map never run past the allocation)
       const size_t wbytes = (size_t)op.cout * op.cin * kk * sizeof(__half);
       if (!need(op.w_off, wbytes) || !need(op.scale_off, op.cout * 4) || !need(op.bias_off, op.cout * 4)) {
         delete m;
@@ -385,7 +390,7 @@ static int model_run(pcb_ctx* c, Model* m, Model::Run* r) {
           }
         }
         w.n_tile = pick_n_tile(c, w, a.in->rows());
-        rc = c->conv_impl == 0 ? pcb_conv_tc2(c, a) : c->conv_impl == 3 ? pcb_conv_tc3(c, a) : c->conv_impl == 2 ? pcb_conv_tc(c, a) : pcb_conv_simple(c, a);
+        rc = c->conv_impl == 0 ? pcb_conv_tc2(c, a) : c->conv_impl == 2 ? pcb_conv_tc(c, a) : pcb_conv_simple(c, a);
         break;
       }
       case PCB_OP_AFFINE: rc = pcb_op_affine(c, r->t[op.in0], r->t[op.out], m->aff_scale[i], m->aff_bias[i]); break;
@@ -410,7 +415,7 @@ __global__ void gather_nchw_kernel(const __half* __restrict__ in, float* __restr
     const int y = (int)((idx / w) % h);
     const int ch = (int)((idx / ((long long)w * h)) % c);
     const int img = (int)(idx / ((long long)w * h * c));
-    const long long row = dense ? img : ((long long)img * (h + 2) + y + 1) * (w + 2) + x + 1;
+    const long long row = dense ? img : pcb_prow(img, y, x, h, w);
     out[idx] = is_f32 ? ((const float*)in)[row * cp + ch] : __half2float(in[row * cp + ch]);
   }
 }

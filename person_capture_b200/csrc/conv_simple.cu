@@ -44,15 +44,15 @@ __global__ void conv_simple_kernel(const SimpleParams p) {
       const int xo = (int)(pix % p.wo);
       const int yo = (int)((pix / p.wo) % p.ho);
       const int img = (int)(pix / ((long long)p.wo * p.ho));
-      const int hp = p.h + 2, wp = p.w_ + 2;
-      const int yc = yo * p.stride + 1, xc = xo * p.stride + 1;  // centre in padded input coords
+      const int yc = yo * p.stride, xc = xo * p.stride;  // centre in image coords
       for (int t = 0; t < p.taps; ++t) {
         const int dy = p.taps == 9 ? t / 3 - 1 : 0, dx = p.taps == 9 ? t % 3 - 1 : 0;
-        const __half* a = p.in + (((long long)img * hp + yc + dy) * wp + xc + dx) * p.cp_in;
+        if (yc + dy < 0 || yc + dy >= p.h || xc + dx < 0 || xc + dx >= p.w_) continue;   // zero padding
+        const __half* a = p.in + pcb_prow(img, yc + dy, xc + dx, p.h, p.w_) * p.cp_in;
         const __half* wr = p.w + ((long long)co * p.taps + t) * p.cin_w;
         for (int ci = 0; ci < p.cin_eff; ++ci) acc = fmaf(__half2float(a[ci]), __half2float(wr[ci]), acc);
       }
-      orow = ((long long)img * (p.ho + 2) + yo + 1) * (p.wo + 2) + xo + 1;
+      orow = pcb_prow(img, yo, xo, p.ho, p.wo);
     }
     float y = fmaf(acc, p.scale[co], p.bias[co]);
     if (p.out_f32) {

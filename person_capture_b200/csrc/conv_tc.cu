@@ -261,10 +261,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int img = (int)(prow / plane);
         const int rem = (int)(prow - (long long)img * plane);
         const int y = rem / p.wp, x = rem - y * p.wp;
-        valid = valid && y >= 1 && y <= p.hp - 2 && x >= 1 && x <= p.wp - 2;
+        valid = valid && y >= kPadLo && y <= p.hp - 1 - (kPad - kPadLo) && x >= kPadLo && x <= p.wp - 1 - (kPad - kPadLo);
         if (p.stride == 2) {
-          valid = valid && (((y - 1) | (x - 1)) & 1) == 0;
-          orow = ((long long)img * p.hp_out + ((y - 1) >> 1) + 1) * p.wp_out + ((x - 1) >> 1) + 1;
+          valid = valid && (((y - kPadLo) | (x - kPadLo)) & 1) == 0;
+          orow = ((long long)img * p.hp_out + ((y - kPadLo) >> 1) + kPadLo) * p.wp_out + ((x - kPadLo) >> 1) + kPadLo;
         }
       }
       if (ok) ok = mbar_wait(&tfull_bar[acc], acc_phase, p.err, 104);
@@ -407,8 +407,8 @@ int pcb_conv_tc(pcb_ctx* c, const ConvArgs& a) {
   ConvTcParams p{};
   p.rows = (int)in.rows();
   p.dense = in.dense ? 1 : 0;
-  p.hp = in.dense ? 0 : in.h + 2;
-  p.wp = in.dense ? 0 : in.w + 2;
+  p.hp = in.dense ? 0 : in.h + kPad;
+  p.wp = in.dense ? 0 : in.w + kPad;
   p.taps = w.taps;
   p.cin_w = w.cin_w;
   p.kchunks = w.cin_w / kKC;
@@ -431,8 +431,8 @@ int pcb_conv_tc(pcb_ctx* c, const ConvArgs& a) {
     else p.out = out.data;
     p.out_cp = out.cp;
     p.out_c_store = out.cp;
-    p.hp_out = out.h + 2;
-    p.wp_out = out.w + 2;
+    p.hp_out = out.h + kPad;
+    p.wp_out = out.w + kPad;
     if (out.cp > w.npad) return pcb_fail(c, PCB_ERR_ARG, "conv_tc: output channels exceed packed weight rows");
     if (a.residual) {
       if (a.residual->f32) p.residual_f32 = (const float*)a.residual->data;

@@ -18,8 +18,12 @@
 // accumulators double-buffered when MT*N <= 256 columns.
 //
 // Warp roles (384 threads, 1 CTA/SM, persistent over tiles):
-//   warp 0  A producer (TMA)    warp 1  MMA issuer 0 (+TMEM alloc)    warp 2  B producer (TMA)
-//   warps 3-10  epilogue: TMEM lane quarter = warp % 4, column half = (warp - 3) / 4.    warp 11  MMA issuer 1
+//   warp 0  A producer (TMA)    warp 1  MMA issuer 0 (+TMEM alloc)    warp 2  B producer (TMA)    warp 3  MMA issuer 1
+//   warps 4-11  epilogue: TMEM lane quarter = warp % 4, column half = (warp - 4) / 4.
+// Registers: the kernel is built for 168 per thread (384 threads); warps 0-3 (one warpgroup) give theirs back with
+// setmaxnreg.dec 56 and the two epilogue warpgroups take 224 each with setmaxnreg.inc.  At 168 the epilogue spilled loop
+// invariants to local memory, and with the L1 squeezed to ~28 KB by the operand rings every reload was a long-scoreboard
+// stall (ncu: 22 % of the epilogue's samples on the instruction after an LDL).
 // Two issuers: measured with tools/mma_rate.cu, ONE thread sustains a tcgen05.mma every ~65-85 cycles (59 + 0.2 N), so
 // instructions with N <= 128 (32-64 tensor-pipe cycles) leave the pipe half idle however the loop is written; two warps
 // issuing to disjoint accumulators reach the nominal rate (N = 128: 64.0 cycles, 8190 FLOP/clk/SM).  The issuers split a
@@ -50,8 +54,8 @@ namespace {
 constexpr int kBlockM = 128;
 constexpr int kKC = 64;                       // K elements per weight stage (one 128B swizzle atom)
 constexpr int kThreads = 384;
-constexpr int kIss1Warp = 11;                 // second MMA issuer warp
-constexpr int kEpiWarp0 = 3;
+constexpr int kIss1Warp = 3;                  // second MMA issuer warp
+constexpr int kEpiWarp0 = 4;
 constexpr int kEpiWarps = 8;
 constexpr uint32_t kTmemCols = 512;
 constexpr int kMaxA = 6;
@@ -139,6 +143,8 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// (A suspend-time hint on try_wait was tried -- 20 us, to park the eight epilogue warps and the producers instead of letting them
+// come back every ~500 cycles -- and measured 5-8 % SLOWER on the layer profile: the wake-up is late.  Plain try_wait stays.)
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -219,9 +225,11 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// arrive on a barrier given by its shared::cluster address (own or peer CTA)
+// arrive on a barrier given by its shared::cluster address (own or peer CTA).  Relaxed: the hand-over is of TMEM columns,
+// ordered by tcgen05.wait::ld + tcgen05.fence::before_thread_sync; no generic-memory data rides on it, and the release
+// form cost a MEMBAR + ERRBAR per tile (5 % of the epilogue's stall samples in ncu).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
 __device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, uint32_t dst, int c0, int c1, int c2, int c3) {
@@ -327,7 +335,7 @@ __device__ __forceinline__ RowInfo row_info(const Conv2Params& p, long long prow
     const int j = rem / p.s_bx, i = rem - j * p.s_bx;
     const int img = ig * p.s_nb + io, oy = ty * p.s_by + j, ox = tx * p.s_bx + i;
     r.valid = io < p.s_nb && img < p.s_n && oy < p.s_ho && ox < p.s_wo;
-    r.orow = ((long long)img * p.hp_out + oy + 1) * p.wp_out + ox + 1;
+    r.orow = ((long long)img * p.hp_out + oy + kPadLo) * p.wp_out + ox + kPadLo;
     return r;
   }
   r.valid = prow < p.rows;
@@ -337,10 +345,10 @@ __device__ __forceinline__ RowInfo row_info(const Conv2Params& p, long long prow
     const int img = fast_div((int)prow, p.fd_plane_mul, p.fd_plane_shift);
     const int rem = (int)prow - img * plane;
     const int y = fast_div(rem, p.fd_wp_mul, p.fd_wp_shift), x = rem - y * p.wp;
-    r.valid = r.valid && y >= 1 && y <= p.hp - 2 && x >= 1 && x <= p.wp - 2;
+    r.valid = r.valid && y >= kPadLo && y <= p.hp - 1 - (kPad - kPadLo) && x >= kPadLo && x <= p.wp - 1 - (kPad - kPadLo);
     if (p.stride == 2) {
-      r.valid = r.valid && (((y - 1) | (x - 1)) & 1) == 0;
-      r.orow = ((long long)img * p.hp_out + ((y - 1) >> 1) + 1) * p.wp_out + ((x - 1) >> 1) + 1;
+      r.valid = r.valid && (((y - kPadLo) | (x - kPadLo)) & 1) == 0;
+      r.orow = ((long long)img * p.hp_out + ((y - kPadLo) >> 1) + kPadLo) * p.wp_out + ((x - kPadLo) >> 1) + kPadLo;
     }
   }
   return r;
@@ -442,6 +450,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // (setmaxnreg sits at the top of each role branch: ptxas bounds the registers of the code a setmaxnreg dominates)
+  if (warp < kEpiWarp0) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");     // one instruction for the whole warpgroup (warps 0-3)
   if (warp == 0) {
     // ===================== A producer (whole warp loops, one elected lane issues) =====================
     {
@@ -470,7 +481,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 const int ky = p.taps == 9 ? t / 3 : 1, kx = p.taps == 9 ? t % 3 : 1;
                 mbar_expect_tx(&a_full[stage], (uint32_t)p.a_tx_bytes);
                 tma_load_4d(&tmA, &a_full[stage], smem_u32(smem_a + (size_t)stage * p.a_stage_bytes), kc * p.kc,
-                            2 * tx * p.s_bx + kx, 2 * ty * p.s_by + ky, ig * p.s_nb);
+                            2 * tx * p.s_bx + kx - 1 + kPadLo, 2 * ty * p.s_by + ky - 1 + kPadLo, ig * p.s_nb);   // -1: left / top pad = out-of-bounds zero fill
               }
               __syncwarp();
               if (++stage == p.a_stages) { stage = 0; phase ^= 1; }
@@ -638,8 +649,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         p.dbg[8] = (unsigned long long)w_t;
       }
     }
+  }
   } else {
-    // ===================== epilogue (warps 3..10) =====================
+    // ===================== epilogue (warps 4..11) =====================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
     const int half = (warp - kEpiWarp0) >> 2;     // column half
     const int row_in_tile = q * 32 + lane;
@@ -1005,8 +1018,8 @@ int pcb_conv_tc2(pcb_ctx* c, const ConvArgs& a) {
   Conv2Params p{};
   p.rows = (int)in.rows();
   p.dense = in.dense ? 1 : 0;
-  p.hp = in.dense ? 0 : in.h + 2;
-  p.wp = in.dense ? 0 : in.w + 2;
+  p.hp = in.dense ? 0 : in.h + kPad;
+  p.wp = in.dense ? 0 : in.w + kPad;
   p.taps = w.taps;
   p.cin_w = w.cin_w;
   {
@@ -1050,8 +1063,8 @@ int pcb_conv_tc2(pcb_ctx* c, const ConvArgs& a) {
     else p.out = out.data;
     p.out_cp = out.cp;
     p.out_c_store = out.cp;
-    p.hp_out = out.h + 2;
-    p.wp_out = out.w + 2;
+    p.hp_out = out.h + kPad;
+    p.wp_out = out.w + kPad;
     if (out.cp > w.npad) return pcb_fail(c, PCB_ERR_ARG, "conv_tc2: output channels exceed packed weight rows");
     if (a.residual) {
       p.residual = a.residual->data;
@@ -1173,7 +1186,7 @@ int pcb_conv_tc2(pcb_ctx* c, const ConvArgs& a) {
 
   CUtensorMap tmA, tmA2, tmB;
   if (strided) {
-    if (!make_map_4d_s2(&tmA, in.data, in.n, in.h + 2, in.w + 2, in.cp, p.kc, p.s_bx, p.s_by, p.s_nb))
+    if (!make_map_4d_s2(&tmA, in.data, in.n, in.h + kPad, in.w + kPad, in.cp, p.kc, p.s_bx, p.s_by, p.s_nb))
       return pcb_fail(c, PCB_ERR_CUDA, "cuTensorMapEncodeTiled(A strided) failed");
     tmA2 = tmA;
   } else {

@@ -47,7 +47,7 @@ __global__ void decode_kernel(const DecodeParams p) {
     const int loc = r >> 1;
     const int w = p.hw[lvl];
     const int y = loc / w, x = loc - y * w;
-    const float* px = p.head[lvl] + ((((size_t)img * (w + 2)) + y + 1) * (w + 2) + x + 1) * 32;
+    const float* px = p.head[lvl] + pcb_prow(img, y, x, w, w) * 32;
     const float logit = px[a];
     if (!(logit >= lthr)) continue;
     // torch.sigmoid on float32: evaluate in double and round once

@@ -1,7 +1,7 @@
 // Elementwise / pooling ops of the two graphs over the P-layout (HBM-bound, 16-byte vector
 // accesses, 8 channels per thread).  They replace the BatchNorm / MaxPool / AveragePool /
 // Resize(nearest)+Add / Flatten nodes that ONNX Runtime executes for the reference
-// (face_embedder.py:1102-1107, 1369).  Only interior pixels are written (zero ring invariant).
+// (face_embedder.py:1102-1107, 1369).  Only image pixels are written (zero pad invariant).
 #include "pcb_common.cuh"
 
 namespace {
@@ -12,7 +12,7 @@ struct Geo {
 };
 
 __device__ __forceinline__ long long prow(int img, int y, int x, int h, int w) {
-  return ((long long)img * (h + 2) + (y + 1)) * (w + 2) + (x + 1);
+  return pcb_prow(img, y, x, h, w);
 }
 
 __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {

@@ -20,18 +20,37 @@
 #define PCB_ERR_STATE 4
 
 // ---------------------------------------------------------------------------------------
-// Activation layout ("P-layout"): fp16 [N][H+2][W+2][Cp] with a one-pixel ring of zeros and
-// Cp = channels rounded up to 8.  A 3x3/pad-1 convolution over it is nine row-shifted views
-// of the same [rows, Cp] matrix (rows = N*(H+2)*(W+2)), which is what the TMA-fed implicit
-// GEMM in conv_tc.cu consumes.  Kernels only ever write interior pixels, so the ring stays
-// zero after the one-time memset at allocation.
+// Activation layout ("P-layout"): fp16 [N][H+kPad][W+kPad][Cp], Cp = channels rounded up to 8, image pixel (y, x) at
+// [y+kPadLo][x+kPadLo], every other element zero.  A 3x3/pad-1 convolution over it is nine row-shifted views of the same
+// [rows, Cp] matrix (rows = N*(H+kPad)*(W+kPad)): tap (dy,dx) of row r reads row r + dy*(W+kPad) + dx, which is what
+// the TMA-fed implicit GEMM consumes.  Kernels only ever write image pixels, so the padding stays zero after the
+// one-time memset at allocation.
+//   kPadLo/kPad = 1/2 (default): a one-pixel ring of zeros around every image.
+//   kPadLo/kPad = 0/1 (-DPCB_PAD_LO=0 -DPCB_PAD=1): ONE trailing zero column per image row and ONE trailing zero row per
+//     image -- x = -1 is then the pad column that ends the previous row, y = -1 the pad row that ends the previous image,
+//     rows before the tensor's first are TMA out-of-bounds zero fill.  It cuts the GEMM rows spent on padding from
+//     (H+2)(W+2)/(HW) to (H+1)(W+1)/(HW) (1.31 -> 1.15 at 14x14, 1.65 -> 1.31 at 7x7) and passes every parity test, but
+//     measured on B200 it is SLOWER overall (651-684 vs 732-761 TFLOP/s on the layer profile, same process, alternating
+//     libraries): 7x7 and 16x16 layers gain 13-20 %, the 14x14 stage gains nothing at 444 images (391 pair tiles still
+//     take 6 waves on 74 CTA pairs) and every wide-map layer loses 12-30 % in its MMA phase (tensor pipe 37 % active
+//     instead of 49 % on the 112x112 64->64 layer, ncu) although tools/mma_rate.cu shows the tensor pipe itself is
+//     indifferent to the row pitch -- an interaction not understood yet, so the ring stays the product layout.
 // ---------------------------------------------------------------------------------------
+#ifndef PCB_PAD_LO
+#define PCB_PAD_LO 1
+#define PCB_PAD 2
+#endif
+constexpr int kPadLo = PCB_PAD_LO;   // pad elements before the first row / column of an image
+constexpr int kPad = PCB_PAD;        // pad elements per dimension in total
+__host__ __device__ __forceinline__ long long pcb_prow(int img, int y, int x, int h, int w) {
+  return ((long long)img * (h + kPad) + (y + kPadLo)) * (w + kPad) + (x + kPadLo);
+}
 struct PTensor {
   __half* data = nullptr;
   int n = 0, h = 0, w = 0, c = 0, cp = 0;  // logical dims, cp = padded channel stride
-  bool dense = false;                      // dense: [n][cp] rows without spatial ring (FC input)
+  bool dense = false;                      // dense: [n][cp] rows without spatial padding (FC input)
   bool f32 = false;                        // elements are float (iResNet residual stream) instead of __half
-  size_t rows() const { return dense ? (size_t)n : (size_t)n * (h + 2) * (w + 2); }
+  size_t rows() const { return dense ? (size_t)n : (size_t)n * (h + kPad) * (w + kPad); }
   size_t bytes() const { return rows() * cp * (f32 ? sizeof(float) : sizeof(__half)); }
 };
 
@@ -117,7 +136,6 @@ void* pcb_dev_alloc(pcb_ctx* c, size_t bytes, bool zero);
 
 // conv_tc.cu / conv_simple.cu
 int pcb_conv_tc2(pcb_ctx* c, const ConvArgs& a);   // product kernel: pixels on UMMA M, couts on N, operand reuse in shared memory
-int pcb_conv_tc3(pcb_ctx* c, const ConvArgs& a);   // experiment (impl 3): couts on M, 256 pixels on N; faster MMA phase, slower epilogue
 int pcb_conv_tc(pcb_ctx* c, const ConvArgs& a);    // first formulation, kept as the A/B baseline (impl 2)
 int pcb_conv_simple(pcb_ctx* c, const ConvArgs& a);
 // ops.cu

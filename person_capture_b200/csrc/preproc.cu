@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(256) letterbox_kernel(const LetterboxParams p)
     }
 #pragma unroll
   for (int j = 27; j < 32; ++j) vals[j] = __float2half_rn(0.f);
-  __half* o = p.out + ((((size_t)img * (half + 2)) + oy + 1) * (half + 2) + ox + 1) * 32;
+  __half* o = p.out + pcb_prow(img, oy, ox, half, half) * 32;
 #pragma unroll
   for (int j = 0; j < 4; ++j) ((uint4*)o)[j] = ((const uint4*)vals)[j];
 }
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(256) chip_patch_kernel(const uint8_t* __restri
       }
 #pragma unroll
     for (int j = 27; j < 32; ++j) vals[j] = __float2half_rn(0.f);
-    __half* o = out + (((size_t)img * (PCB_CHIP + 2) + y + 1) * (PCB_CHIP + 2) + x + 1) * 32;
+    __half* o = out + pcb_prow(img, y, x, PCB_CHIP, PCB_CHIP) * 32;
 #pragma unroll
     for (int j = 0; j < 4; ++j) ((uint4*)o)[j] = ((const uint4*)vals)[j];
   }

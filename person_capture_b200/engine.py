@@ -179,7 +179,7 @@ class Engine:
     def letterbox(self, frames: torch.Tensor, S: int, rot: int = 0, pad: int = 0, want_det_img: bool = False):
         n, h, w, _ = frames.shape
         half = S // 2
-        out = self.zeros((n, half + 2, half + 2, 32), torch.float16)
+        out = self.zeros((n, half + L.P_PAD, half + L.P_PAD, 32), torch.float16)
         det = self.empty((n, S, S, 3), torch.uint8) if want_det_img else None
         self._check(self.lib.pcb_letterbox(self.ctx, frames.data_ptr(), n, h, w, S, rot, pad, out.data_ptr(),
                                            det.data_ptr() if det is not None else None), "pcb_letterbox")

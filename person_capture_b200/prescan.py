@@ -534,7 +534,9 @@ class FaceTable:
     Lazy mode (single process): only e(x) is computed up front, as the reference does while no span is active
     (face_embedder.py:1295); chips and raw embeddings stay resident and `ensure_flip` computes e(flip x) for the rows the
     replay actually evaluates in the active state (plus a look-ahead window, so the GPU sees large batches)."""
-    EMBED_RUN = 444       # images per ArcFace graph run (pcb_embed chunk; 222 faces when both variants are computed)
+    # images per ArcFace graph run (pcb_embed chunk; half as many faces when both variants are computed).  444 fills the 148 SMs
+    # to >= 95 % in every iResNet stage (14x14: 888 tiles = 6.0 waves, 28x28: 10.5, 56x56: 39.4)
+    EMBED_RUN = int(os.environ.get("PCB_EMBED_RUN", "444"))
 
     def __init__(self, lazy: bool = False):
         self.lazy = lazy

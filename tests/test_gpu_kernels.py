@@ -9,6 +9,7 @@ import torch
 import cv2
 
 import pcb_test_helpers as H
+from person_capture_b200 import _lib as L
 
 pytestmark = pytest.mark.gpu
 
@@ -68,14 +69,15 @@ def test_letterbox_bit_exact(engine_25g_r50, h, w, S, rot, pad):
     # patch tensor == 3x3 stride-2 neighbourhood of blobFromImage(ref)
     blob = cv2.dnn.blobFromImage(ref, 1.0 / 128, (S, S), (127.5, 127.5, 127.5), swapRB=True)[0]   # [3,S,S]
     bp = np.pad(blob, ((0, 0), (1, 1), (1, 1)))
-    P = patches.cpu().numpy()[0].astype(np.float32)     # [S/2+2, S/2+2, 32]
+    P = patches.cpu().numpy()[0].astype(np.float32)     # [S/2+P_PAD, S/2+P_PAD, 32]
+    lo = L.P_PAD_LO
     half = S // 2
     for ky in range(3):
         for kx in range(3):
             want = bp[:, ky:ky + S:2, kx:kx + S:2]        # [3, half, half]
-            got = P[1:half + 1, 1:half + 1, (ky * 3 + kx) * 3:(ky * 3 + kx) * 3 + 3].transpose(2, 0, 1)
+            got = P[lo:half + lo, lo:half + lo, (ky * 3 + kx) * 3:(ky * 3 + kx) * 3 + 3].transpose(2, 0, 1)
             assert np.array_equal(got, want), (ky, kx)
-    assert not P[0].any() and not P[:, 0].any() and not P[..., 27:].any()
+    assert not P[half + lo:].any() and not P[:, half + lo:].any() and not P[..., 27:].any()   # trailing pad stays zero
 
 
 # ---------------------------------------------------------------- K2 (graphs)
@@ -170,10 +172,11 @@ def test_decode_nms_bit_exact(engine_25g_r50, S, thr, seed, rot, pad, fix):
             logit[y, x, rng.integers(0, 2)] = np.float16(rng.uniform(-1, 6))
         reg = rng.uniform(0.5, 6.0, (h, h, 8)).astype(np.float16)
         kps = rng.uniform(-3.0, 3.0, (h, h, 20)).astype(np.float16)
-        hm = np.zeros((1, h + 2, h + 2, 32), np.float32)
-        hm[0, 1:-1, 1:-1, 0:2] = logit
-        hm[0, 1:-1, 1:-1, 2:10] = reg
-        hm[0, 1:-1, 1:-1, 10:30] = kps
+        hm = np.zeros((1, h + L.P_PAD, h + L.P_PAD, 32), np.float32)
+        lo = L.P_PAD_LO
+        hm[0, lo:h + lo, lo:h + lo, 0:2] = logit
+        hm[0, lo:h + lo, lo:h + lo, 2:10] = reg
+        hm[0, lo:h + lo, lo:h + lo, 10:30] = kps
         heads_t.append(_dev(eng, hm))
         sc = (1.0 / (1.0 + np.exp(-logit.astype(np.float64)))).astype(np.float32).reshape(-1, 1)
         outs_sc.append(sc)

@@ -33,6 +33,7 @@ __device__ __forceinline__ void umma(uint32_t d, uint64_t da, uint64_t db, uint3
 struct Args {
   int n, iters, a_shift_rows, b_slots, mt;   // mt: accumulators cycled (sub-tiles sharing a B slot)
   int issuers;                                // 1 | 2 issuing warps (accumulators split between them)
+  int wp;                                     // > 0: A start rows follow the nine tap offsets (wp + 1 + dy*wp + dx) of a halo tile with this row pitch
   int order;                                  // 0: four K steps per accumulator, then the next accumulator; 1: accumulators innermost
   unsigned long long* out;                    // [grid] cycles
 };
@@ -81,6 +82,19 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(Args a) {
     for (int it = 0; it < a.iters; ++it) {
       const uint64_t db = make_desc(sb + (uint32_t)(it % a.b_slots) * 32768u);
       if (!elect_one()) continue;
+      if (a.wp > 0) {
+        // the product kernel's inner loop: tap t of a halo tile, issuer w owns sub-tile w (128 rows further down), resident weights
+        const int t = it % 9;
+        const uint32_t off = (uint32_t)(a.wp + 1 + (t / 3 - 1) * a.wp + (t % 3 - 1)) * 128u;
+        const uint64_t da = make_desc(smem_u32(smem) + off + (uint32_t)uwarp * 16384u);
+        const uint64_t db = make_desc(sb + (uint32_t)t * 8192u);
+        const uint32_t d = tmem + (uint32_t)(uwarp * a.n);
+        umma<kPair>(d, da, db, idesc, it ? 1u : 0u);
+        umma<kPair>(d, da + 2, db + 2, idesc, 1u);
+        umma<kPair>(d, da + 4, db + 4, idesc, 1u);
+        umma<kPair>(d, da + 6, db + 6, idesc, 1u);
+        continue;
+      }
       if (a.order == 2) {
         // straight line: descriptors precomputed, 16 instructions per iteration on 4 accumulators x 4 K steps
         const uint64_t da0 = make_desc(sa), db0 = make_desc(sb);
@@ -141,6 +155,21 @@ int main() {
   cudaFuncSetAttribute(rate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   cudaFuncSetAttribute(rate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   printf("%5s %5s %4s %6s %6s %6s | %10s %12s %10s\n", "pair", "N", "mt", "order", "issuers", "grid", "cyc/mma", "FLOP/clk/SM", "nominal");
+  printf("halo-tap sweep: N, wp -> cycles per MMA per issuer (2 issuers, one sub-tile each)\n");
+  for (int n : {64, 128}) {
+    for (int wp : {113, 114, 112, 120, 57, 58, 56, 64, 29, 30, 32, 15, 16, 129, 130, 128}) {
+      Args a{n, 3600, 0, 1, 2, 2, wp, 0, d_out};
+      cudaMemset(d_out, 0, 148 * sizeof(unsigned long long));
+      for (int rep = 0; rep < 2; ++rep) rate_kernel<false><<<148, 128, smem>>>(a);
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) { printf("error: %s\n", cudaGetErrorString(e)); return 1; }
+      unsigned long long h[148];
+      cudaMemcpy(h, d_out, sizeof h, cudaMemcpyDeviceToHost);
+      double cyc = 0; int cnt = 0;
+      for (int i = 0; i < 148; ++i) if (h[i]) { cyc += (double)h[i]; ++cnt; }
+      printf("  N=%3d wp=%3d (wp mod 8 = %d): %.1f\n", n, wp, wp % 8, cyc / cnt / (a.iters * 4.0));
+    }
+  }
   for (int grid : {148}) {
     for (int pair = 0; pair < 1; ++pair) {
       for (int n : {32, 64, 96, 128, 224, 256}) {
@@ -152,7 +181,7 @@ int main() {
             if (cfg == 2) continue;
             {
               const int shift = 17, bslots = 3;
-              Args a{n, 4000, shift, bslots, mt, issuers, order, d_out};
+              Args a{n, 4000, shift, bslots, mt, issuers, 0, order, d_out};
               cudaMemset(d_out, 0, 148 * sizeof(unsigned long long));
               for (int rep = 0; rep < 2; ++rep) {
                 if (pair) {
