@@ -136,7 +136,7 @@ int pcb_detect(pcb_ctx* ctx, const pcb_detect_args* a);
  * the uint8 letterboxed image [n][S][S][3] for parity tests. */
 int pcb_letterbox(pcb_ctx* ctx, const uint8_t* frames_dev, int n, int h, int w, int S, int rot_deg,
                   int pad_replicate, void* out_dev, uint8_t* det_img_dev);
-/* K3 alone on explicit head maps (fp16 P-layout [n][S/s+2][S/s+2][32] for s=8,16,32). */
+/* K3 alone on explicit head maps (P-layout [n][S/s+pad][S/s+pad][32] for s=8,16,32; see pcb_layout_pad). */
 int pcb_decode_nms(pcb_ctx* ctx, const void* head8_dev, const void* head16_dev, const void* head32_dev,
                    const float* reg_scale3_host, const pcb_detect_args* a, float det_scale);
 

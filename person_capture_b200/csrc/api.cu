@@ -356,9 +356,10 @@ static int pick_n_tile(const pcb_ctx* c, const ConvWeights& w, size_t rows) {
   if (w.npad <= 128) return w.npad;
   const long long m_tiles = (long long)((rows + 127) / 128);
   const int cands[3] = {256, 128, 64};
+  static const int nt_max = getenv("PCB_CONV_NTILE_MAX") ? atoi(getenv("PCB_CONV_NTILE_MAX")) : 256;   // A/B knob
   for (int i = 0; i < 3; ++i) {
     const int nt = cands[i];
-    if (nt > w.npad || w.npad % nt) continue;
+    if (nt > w.npad || w.npad % nt || nt > nt_max) continue;
     if (m_tiles * (w.npad / nt) >= c->num_sms || nt == 64) return nt;
   }
   return w.npad <= 256 ? w.npad : 128;

@@ -105,7 +105,6 @@ struct Conv2Params {
   int s_ho, s_wo;              // output dims
   uint32_t fd_plane_mul, fd_wp_mul;   // fast_div multipliers for hp*wp and wp
   int fd_plane_shift, fd_wp_shift;
-  int desc_mode;   // 1 (product): base-offset 0; 0 (experiment): base-offset = (addr >> 7) & 7
   int stride;      // 1 | 2
   int hp_out, wp_out;
   int out_cp;      // channel stride of the P-layout output
@@ -180,6 +179,36 @@ __device__ __forceinline__ bool mbar_wait_t(uint64_t* bar, uint32_t parity, int*
   const long long t0 = clock64();
   const bool ok = mbar_wait(bar, parity, err, code);
   acc += clock64() - t0;
+  return ok;
+}
+// Address-based forms for the MMA issuers' loop (shared-memory addresses precomputed as 32-bit values).
+__device__ __forceinline__ bool mbar_try_wait_addr(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ bool mbar_wait_addr(uint32_t bar, uint32_t parity, int* err, int code, long long& acc, bool timed) {
+  if (mbar_try_wait_addr(bar, parity)) return true;
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  bool ok = true;
+  while (!mbar_try_wait_addr(bar, parity)) {
+    if ((++spins & 0x3ff) == 0) {
+      if (*(volatile int*)err != 0) { ok = false; break; }
+      if (clock64() - t0 > 600000000LL) {
+        atomicCAS(err, 0, code);
+        ok = false;
+        break;
+      }
+    }
+  }
+  if (timed) acc += clock64() - t0;
   return ok;
 }
 // One lane of a converged warp (the canonical single-issuer idiom: control flow stays warp-uniform, so the
@@ -266,6 +295,14 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   else
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+template <bool kPair>
+__device__ __forceinline__ void umma_commit_addr(uint32_t bar) {
+  if (kPair)
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+  else
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -282,20 +319,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart.  The start
-// address may sit on any 128-byte row (tap shifts).  Measured on B200 (tools/conv_check.py): the
-// tensor core applies the 128B swizzle to ABSOLUTE shared-memory address bits (the same rule TMA writes
-// with), so a row-shifted start needs base-offset 0; setting base-offset = (addr >> 7) & 7 double-counts
-// the phase and gives wrong sums (desc_mode 0 is kept only to reproduce that experiment).
-__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr, int desc_mode, bool sw64 = false) {
-  // sw64: rows of 64 bytes (32 fp16 of K), 64B swizzle, 8-row groups 512 bytes apart -- layers with <= 32 input channels
-  uint64_t lo = (uint64_t)((saddr >> 4) & 0x3fff);             // start address, LBO = 0
-  uint64_t hi = (uint64_t)((sw64 ? 512 : 1024) >> 4)            // SBO
-                | (1ull << 14)                                  // descriptor version 1 (sm_100)
-                | ((sw64 ? 4ull : 2ull) << 29);                 // layout type: SWIZZLE_64B / SWIZZLE_128B
-  if (desc_mode == 0) hi |= (uint64_t)((saddr >> 7) & 7) << 17; // base offset, bits 49-51
-  return lo | (hi << 32);
-}
+// UMMA shared-memory descriptors (built inline in the issuer loop): K-major, 128B-swizzled operand tile, rows of 128 bytes,
+// 8-row groups 1024 bytes apart (64-byte rows / SWIZZLE_64B / 512 bytes for layers with <= 32 input channels).  The start
+// address may sit on any row (tap shifts).  Measured on B200 (tools/conv_check.py): the tensor core applies the swizzle to
+// ABSOLUTE shared-memory address bits (the same rule TMA writes with), so a row-shifted start needs base-offset 0; setting
+// base-offset = (addr >> 7) & 7 double-counts the phase and gives wrong sums (that experiment: PCB_DESC_MODE=0 up to commit 9c41a29).
 
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint4& v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
@@ -562,6 +590,14 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // ===================== MMA issuers (whole warp loops, one elected lane issues; pair: the leader CTA only) =====================
     const int iss = warp == 1 ? 0 : 1;
     if (leader && iss < p.n_iss) {
+      // The loop below is what paces the tensor pipe (ncu: the issuer warps spent ~220 cycles per instruction where the
+      // pipe needs 64-128), so everything loop-invariant lives in registers: shared-memory addresses as 32-bit values
+      // computed once (re-deriving them from generic pointers cost an S2UR/ULEA/ULOP3 chain per use), barrier addresses as
+      // base + 8 * index, descriptors as a constant high word plus (address >> 4), parameters copied out of the constant
+      // bank (the asm memory clobbers made the compiler reload them every tap).
+      const int taps = p.taps, kchunks = p.kchunks, mt = p.mt, n_a = p.a_stages, n_b = p.b_stages;
+      const bool b_res = p.b_resident != 0, sw64 = p.kc == 32;
+      const int kfull = p.kc / 16, klast = p.kinstr_last;
       const int n_instr = p.split_n ? p.n_tile / 2 : p.n_tile;
       const uint32_t idesc = (1u << 4)                          // D format: F32
                              | (0u << 7) | (0u << 10)           // A, B format: F16
@@ -569,72 +605,89 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                              | ((uint32_t)((kPair ? 2 * kBlockM : kBlockM) >> 4) << 24);
       // my share of every K step: sub-tiles j0, j0 + jstep, ... and the weight rows / accumulator columns from b_off / d_off
       const int j0 = p.split_n ? 0 : iss, jstep = p.split_n ? 1 : p.n_iss;
-      const uint32_t b_off = p.split_n ? (uint32_t)(iss * (p.b_rows / 2) * p.row_bytes) : 0u;
       const uint32_t d_off = p.split_n ? (uint32_t)(iss * (p.n_tile / 2)) : 0u;
-      int a_stage = 0, b_stage = 0;
-      uint32_t a_phase = 0, b_phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
+      const uint32_t a_base = smem_u32(smem_a), a_bytes = (uint32_t)p.a_stage_bytes;
+      const uint32_t b_base = smem_u32(smem_b) + (p.split_n ? (uint32_t)(iss * (p.b_rows / 2) * p.row_bytes) : 0u), b_bytes = (uint32_t)p.b_bytes;
+      const uint32_t sub_bytes = (uint32_t)p.sub_bytes, sub_cols = (uint32_t)p.sub_cols;
+      const uint32_t bar_a_full = smem_u32(a_full), bar_a_empty = smem_u32(a_empty), bar_b_full = smem_u32(b_full),
+                     bar_b_empty = smem_u32(b_empty), bar_tfull = smem_u32(tfull_bar), bar_tempty = smem_u32(tempty_bar);
+      // descriptor = constant high word (SBO, version, swizzle mode) | start address >> 4 (LBO 0, base offset 0)
+      const uint64_t desc_hi = (uint64_t)((uint32_t)((sw64 ? 512 : 1024) >> 4) | (1u << 14) | ((sw64 ? 4u : 2u) << 29)) << 32;
+      const bool timed = p.dbg != nullptr;
+      uint32_t a_stage = 0, b_stage = 0, a_phase = 0, b_phase = 0, acc = 0, acc_phase = 0;
+      uint32_t sa = a_base;                // address of A stage a_stage
       bool ok = true;
       bool b_loaded = false;
       long long w_a = 0, w_b = 0, w_t = 0;
       for (int tile = tile0; ok && tile < total_tiles; tile += tile_step) {
-        ok = __all_sync(0xffffffffu, mbar_wait_t(&tempty_bar[acc], acc_phase ^ 1, p.err, 102, w_t, p.dbg != nullptr));
+        ok = __all_sync(0xffffffffu, mbar_wait_addr(bar_tempty + 8u * acc, acc_phase ^ 1, p.err, 102, w_t, timed));
         if (!ok) break;
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256) + d_off;
-        for (int kc = 0; ok && kc < p.kchunks; ++kc) {
+        const uint32_t d_tmem = tmem_base + acc * 256u + d_off;
+        uint32_t sb = b_base;              // resident weights: slot kc * taps + t, walked in order
+        for (int kc = 0; ok && kc < kchunks; ++kc) {
           if (!kStrided) {
-            ok = __all_sync(0xffffffffu, mbar_wait_t(&a_full[a_stage], a_phase, p.err, 103, w_a, p.dbg != nullptr));
+            ok = __all_sync(0xffffffffu, mbar_wait_addr(bar_a_full + 8u * a_stage, a_phase, p.err, 103, w_a, timed));
             if (!ok) break;
           }
-          uint32_t sa = smem_u32(smem_a + (size_t)a_stage * p.a_stage_bytes);
-          const int kinstr = (kc == p.kchunks - 1) ? p.kinstr_last : p.kc / 16;
-          for (int t = 0; t < p.taps; ++t) {
+          const int kinstr = (kc == kchunks - 1) ? klast : kfull;
+          for (int t = 0; t < taps; ++t) {
             if (kStrided) {
-              ok = __all_sync(0xffffffffu, mbar_wait_t(&a_full[a_stage], a_phase, p.err, 103, w_a, p.dbg != nullptr));
+              ok = __all_sync(0xffffffffu, mbar_wait_addr(bar_a_full + 8u * a_stage, a_phase, p.err, 103, w_a, timed));
               if (!ok) break;
-              sa = smem_u32(smem_a + (size_t)a_stage * p.a_stage_bytes);
             }
-            const int slot = p.b_resident ? kc * p.taps + t : b_stage;
-            if (!p.b_resident || !b_loaded) {
-              ok = __all_sync(0xffffffffu, mbar_wait_t(&b_full[slot], p.b_resident ? 0u : b_phase, p.err, 106, w_b, p.dbg != nullptr));
+            if (!b_res) sb = b_base + b_stage * b_bytes;
+            if (!b_res || !b_loaded) {
+              const uint32_t slot = b_res ? (uint32_t)(kc * taps + t) : b_stage;
+              ok = __all_sync(0xffffffffu, mbar_wait_addr(bar_b_full + 8u * slot, b_res ? 0u : b_phase, p.err, 106, w_b, timed));
               if (!ok) break;
             }
             tc_fence_after();
             if (elect_one()) {
-              const uint64_t db = make_desc_sw128(smem_u32(smem_b + (size_t)slot * p.b_bytes) + b_off, 1, p.kc == 32);
+              const uint64_t db = desc_hi | (uint64_t)((sb >> 4) & 0x3fffu);
               const uint32_t first = (kc | t) != 0 ? 1u : 0u;
-              for (int j = j0; j < p.mt; j += jstep) {
-                const uint64_t da = make_desc_sw128(sa + (kStrided ? 0u : (uint32_t)p.tap_off[t]) + (uint32_t)(j * p.sub_bytes), p.desc_mode, p.kc == 32);
-                const uint32_t d = d_tmem + (uint32_t)(j * p.sub_cols);
+              const uint32_t a_tap = sa + (kStrided ? 0u : (uint32_t)p.tap_off[t]);
+              for (int j = j0; j < mt; j += jstep) {
+                const uint64_t da = desc_hi | (uint64_t)(((a_tap + (uint32_t)j * sub_bytes) >> 4) & 0x3fffu);
+                const uint32_t d = d_tmem + (uint32_t)j * sub_cols;
                 // advance 16 elements (32 bytes) along K inside the swizzle atom; all-zero K slices are skipped
-                umma_f16<kPair>(d, da, db, idesc, first);
-                if (kinstr > 1) umma_f16<kPair>(d, da + 2, db + 2, idesc, 1u);
-                if (kinstr > 2) umma_f16<kPair>(d, da + 4, db + 4, idesc, 1u);
-                if (kinstr > 3) umma_f16<kPair>(d, da + 6, db + 6, idesc, 1u);
+                if (kinstr == 4) {
+                  umma_f16<kPair>(d, da, db, idesc, first);
+                  umma_f16<kPair>(d, da + 2, db + 2, idesc, 1u);
+                  umma_f16<kPair>(d, da + 4, db + 4, idesc, 1u);
+                  umma_f16<kPair>(d, da + 6, db + 6, idesc, 1u);
+                } else {
+                  umma_f16<kPair>(d, da, db, idesc, first);
+                  if (kinstr > 1) umma_f16<kPair>(d, da + 2, db + 2, idesc, 1u);
+                  if (kinstr > 2) umma_f16<kPair>(d, da + 4, db + 4, idesc, 1u);
+                }
               }
-              if (!p.b_resident) umma_commit<kPair>(&b_empty[b_stage]);
-              if (kStrided) umma_commit<kPair>(&a_empty[a_stage]);
+              if (!b_res) umma_commit_addr<kPair>(bar_b_empty + 8u * b_stage);
+              if (kStrided) umma_commit_addr<kPair>(bar_a_empty + 8u * a_stage);
             }
             __syncwarp();
-            if (!p.b_resident) {
-              if (++b_stage == p.b_stages) { b_stage = 0; b_phase ^= 1; }
+            if (b_res) {
+              sb += b_bytes;
+            } else if (++b_stage == (uint32_t)n_b) {
+              b_stage = 0;
+              b_phase ^= 1;
             }
             if (kStrided) {
-              if (++a_stage == p.a_stages) { a_stage = 0; a_phase ^= 1; }
+              sa += a_bytes;
+              if (++a_stage == (uint32_t)n_a) { a_stage = 0; a_phase ^= 1; sa = a_base; }
             }
           }
           if (!ok) break;
           if (!kStrided) {
-            if (elect_one()) umma_commit<kPair>(&a_empty[a_stage]);
+            if (elect_one()) umma_commit_addr<kPair>(bar_a_empty + 8u * a_stage);
             __syncwarp();
-            if (++a_stage == p.a_stages) { a_stage = 0; a_phase ^= 1; }
+            sa += a_bytes;
+            if (++a_stage == (uint32_t)n_a) { a_stage = 0; a_phase ^= 1; sa = a_base; }
           }
         }
         if (!ok) break;
         b_loaded = true;
-        if (elect_one()) umma_commit<kPair>(&tfull_bar[acc]);
+        if (elect_one()) umma_commit_addr<kPair>(bar_tfull + 8u * acc);
         __syncwarp();
         if (p.acc_bufs == 2) {
           acc ^= 1;
@@ -1042,7 +1095,6 @@ int pcb_conv_tc2(pcb_ctx* c, const ConvArgs& a) {
   p.bias = w.bias;
   p.slope = w.slope;
   p.err = c->d_err;
-  p.desc_mode = env_int("PCB_DESC_MODE", 1);
   {
     auto fd = [](int d, uint32_t* mul, int* shift) {
       int sft = 0;

@@ -62,5 +62,5 @@ for slot, name in ((L.MODEL_SCRFD, args.scrfd), (L.MODEL_ARCFACE, args.arcface))
                 print(f"{name} op kind={op['kind']} k={op['k']} cin={op['cin']} cout={op['cout']} stride={op['stride']} tensor={t} "
                       f"shape={a.shape} maxabs={d:.4g} scale={s:.4g} rel={rel:.3g} {flag}")
     print(f"{name}: impl {args.impl} vs validation kernel: worst relative diff {worst:.3g}")
-print("CONV_CHECK", "FAIL" if bad else "OK", f"desc_mode={os.environ.get('PCB_DESC_MODE','0')} mt={os.environ.get('PCB_CONV_MT','auto')}")
+print("CONV_CHECK", "FAIL" if bad else "OK", f"pair={os.environ.get('PCB_CONV_PAIR','1')} iss={os.environ.get('PCB_CONV_ISS','2')} mt={os.environ.get('PCB_CONV_MT','auto')}")
 sys.exit(1 if bad else 0)
