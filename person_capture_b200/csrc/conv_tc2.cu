@@ -606,9 +606,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       // my share of every K step: sub-tiles j0, j0 + jstep, ... and the weight rows / accumulator columns from b_off / d_off
       const int j0 = p.split_n ? 0 : iss, jstep = p.split_n ? 1 : p.n_iss;
       const uint32_t d_off = p.split_n ? (uint32_t)(iss * (p.n_tile / 2)) : 0u;
-      const uint32_t a_base = smem_u32(smem_a), a_bytes = (uint32_t)p.a_stage_bytes;
-      const uint32_t b_base = smem_u32(smem_b) + (p.split_n ? (uint32_t)(iss * (p.b_rows / 2) * p.row_bytes) : 0u), b_bytes = (uint32_t)p.b_bytes;
-      const uint32_t sub_bytes = (uint32_t)p.sub_bytes, sub_cols = (uint32_t)p.sub_cols;
+      // operand addresses in 16-byte units (what the descriptor's start-address field holds); the & 0x3fff drops the cluster
+      // rank bits of a shared::cluster-form address once, every later offset is a plain add (all offsets stay < 256 KB)
+      const uint32_t a_base = (smem_u32(smem_a) >> 4) & 0x3fffu, a_bytes = (uint32_t)p.a_stage_bytes >> 4;
+      const uint32_t b_base = ((smem_u32(smem_b) + (p.split_n ? (uint32_t)(iss * (p.b_rows / 2) * p.row_bytes) : 0u)) >> 4) & 0x3fffu,
+                     b_bytes = (uint32_t)p.b_bytes >> 4;
+      const uint32_t sub_bytes = (uint32_t)p.sub_bytes >> 4, sub_cols = (uint32_t)p.sub_cols;
       const uint32_t bar_a_full = smem_u32(a_full), bar_a_empty = smem_u32(a_empty), bar_b_full = smem_u32(b_full),
                      bar_b_empty = smem_u32(b_empty), bar_tfull = smem_u32(tfull_bar), bar_tempty = smem_u32(tempty_bar);
       // descriptor = constant high word (SBO, version, swizzle mode) | start address >> 4 (LBO 0, base offset 0)
@@ -644,11 +647,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
             tc_fence_after();
             if (elect_one()) {
-              const uint64_t db = desc_hi | (uint64_t)((sb >> 4) & 0x3fffu);
+              const uint64_t db = desc_hi | (uint64_t)sb;
               const uint32_t first = (kc | t) != 0 ? 1u : 0u;
-              const uint32_t a_tap = sa + (kStrided ? 0u : (uint32_t)p.tap_off[t]);
+              const uint32_t a_tap = sa + (kStrided ? 0u : (uint32_t)p.tap_off[t] >> 4);
               for (int j = j0; j < mt; j += jstep) {
-                const uint64_t da = desc_hi | (uint64_t)(((a_tap + (uint32_t)j * sub_bytes) >> 4) & 0x3fffu);
+                const uint64_t da = desc_hi | (uint64_t)(a_tap + (uint32_t)j * sub_bytes);
                 const uint32_t d = d_tmem + (uint32_t)j * sub_cols;
                 // advance 16 elements (32 bytes) along K inside the swizzle atom; all-zero K slices are skipped
                 if (kinstr == 4) {
