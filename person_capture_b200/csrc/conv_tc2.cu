@@ -21,7 +21,7 @@
 //   warp 0  A producer (TMA)    warp 1  MMA issuer 0 (+TMEM alloc)    warp 2  B producer (TMA)    warp 3  MMA issuer 1
 //   warps 4-11  epilogue: TMEM lane quarter = warp % 4, column half = (warp - 4) / 4.
 // Registers: the kernel is built for 168 per thread (384 threads); warps 0-3 (one warpgroup) give theirs back with
-// setmaxnreg.dec 56 and the two epilogue warpgroups take 224 each with setmaxnreg.inc.  At 168 the epilogue spilled loop
+// setmaxnreg.dec 72 and the two epilogue warpgroups take 216 each with setmaxnreg.inc.  At 168 the epilogue spilled loop
 // invariants to local memory, and with the L1 squeezed to ~28 KB by the operand rings every reload was a long-scoreboard
 // stall (ncu: 22 % of the epilogue's samples on the instruction after an LDL).
 // Two issuers: measured with tools/mma_rate.cu, ONE thread sustains a tcgen05.mma every ~65-85 cycles (59 + 0.2 N), so
@@ -480,7 +480,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
   // (setmaxnreg sits at the top of each role branch: ptxas bounds the registers of the code a setmaxnreg dominates)
   if (warp < kEpiWarp0) {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");     // one instruction for the whole warpgroup (warps 0-3)
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");     // one instruction for the whole warpgroup (warps 0-3)
   if (warp == 0) {
     // ===================== A producer (whole warp loops, one elected lane issues) =====================
     {
@@ -708,7 +708,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
   } else {
     // ===================== epilogue (warps 4..11) =====================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
     const int half = (warp - kEpiWarp0) >> 2;     // column half
     const int row_in_tile = q * 32 + lane;
