@@ -634,6 +634,40 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             if (!ok) break;
           }
           const int kinstr = (kc == kchunks - 1) ? klast : kfull;
+          if (!kStrided && b_res && b_loaded) {
+            // resident weights, already loaded: nothing to wait for inside the K chunk, so all taps go out in ONE elected block
+            // (per-tap elect / vote / reconvergence bookkeeping is what limits the N <= 64 layers: their instructions need
+            // only 16-32 tensor-pipe cycles each)
+            if (elect_one()) {
+              uint32_t sbt = sb;
+              for (int t = 0; t < taps; ++t) {
+                const uint64_t db = desc_hi | (uint64_t)sbt;
+                const uint32_t first = (kc | t) != 0 ? 1u : 0u;
+                const uint32_t a_tap = sa + ((uint32_t)p.tap_off[t] >> 4);
+                for (int j = j0; j < mt; j += jstep) {
+                  const uint64_t da = desc_hi | (uint64_t)(a_tap + (uint32_t)j * sub_bytes);
+                  const uint32_t d = d_tmem + (uint32_t)j * sub_cols;
+                  if (kinstr == 4) {
+                    umma_f16<kPair>(d, da, db, idesc, first);
+                    umma_f16<kPair>(d, da + 2, db + 2, idesc, 1u);
+                    umma_f16<kPair>(d, da + 4, db + 4, idesc, 1u);
+                    umma_f16<kPair>(d, da + 6, db + 6, idesc, 1u);
+                  } else {
+                    umma_f16<kPair>(d, da, db, idesc, first);
+                    if (kinstr > 1) umma_f16<kPair>(d, da + 2, db + 2, idesc, 1u);
+                    if (kinstr > 2) umma_f16<kPair>(d, da + 4, db + 4, idesc, 1u);
+                  }
+                }
+                sbt += b_bytes;
+              }
+              umma_commit_addr<kPair>(bar_a_empty + 8u * a_stage);
+            }
+            __syncwarp();
+            sb += (uint32_t)taps * b_bytes;
+            sa += a_bytes;
+            if (++a_stage == (uint32_t)n_a) { a_stage = 0; a_phase ^= 1; sa = a_base; }
+            continue;
+          }
           for (int t = 0; t < taps; ++t) {
             if (kStrided) {
               ok = __all_sync(0xffffffffu, mbar_wait_addr(bar_a_full + 8u * a_stage, a_phase, p.err, 103, w_a, timed));
