@@ -194,8 +194,8 @@ __device__ __forceinline__ bool mbar_try_wait_addr(uint32_t bar, uint32_t parity
   return ok != 0;
 }
 __device__ __forceinline__ bool mbar_wait_addr(uint32_t bar, uint32_t parity, int* err, int code, long long& acc, bool timed) {
-  if (mbar_try_wait_addr(bar, parity)) return true;
-  const long long t0 = clock64();
+  if (!timed && mbar_try_wait_addr(bar, parity)) return true;
+  const long long t0 = clock64();      // debug runs time the first try too: try_wait may suspend inside the instruction
   uint32_t spins = 0;
   bool ok = true;
   while (!mbar_try_wait_addr(bar, parity)) {
