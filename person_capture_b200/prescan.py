@@ -537,6 +537,9 @@ class FaceTable:
     # images per ArcFace graph run (pcb_embed chunk; half as many faces when both variants are computed).  444 fills the 148 SMs
     # to >= 95 % in every iResNet stage (14x14: 888 tiles = 6.0 waves, 28x28: 10.5, 56x56: 39.4)
     EMBED_RUN = int(os.environ.get("PCB_EMBED_RUN", "444"))
+    # images per EARLY flip run (FlipPredictor): small enough to fit into the slack of one frame batch (a 444-image run is 13 ms,
+    # the slack of a PCIe-bound batch ~3 ms), still whole waves in the 14x14 stage (148 images = 296 tiles = 2.0 waves)
+    EARLY_RUN = int(os.environ.get("PCB_EARLY_RUN", "148"))
 
     def __init__(self, lazy: bool = False):
         self.lazy = lazy
@@ -551,6 +554,16 @@ class FaceTable:
         self.a_parts: List[np.ndarray] = []
         self.encoded = None
         self.flip_passes = 0          # faces that went through the flip pass (bench: ArcFace image passes / s)
+        # lazy mode, flips computed while the superset is still running (see FlipPredictor): per flushed run its first row
+        # and its similarity to the initial bank, rows queued for an early flip pass, and the results until `finalize`
+        self.part_start: List[int] = []
+        self.sim_parts: List[tuple] = []          # (first row, rows, sim device tensor, event)
+        self.sim_fetched = 0                      # parts whose similarities are on the host
+        self.fd0_host = np.zeros((0,), np.float64)
+        self.flip_queue: List[np.ndarray] = []
+        self.flip_queue_n = 0
+        self.early: List[tuple] = []              # (rows, normalised flip features on the device)
+        self.embedded = 0                         # rows whose plain feature has been computed (flushed)
 
     def queue(self, eng, chips: torch.Tensor, k: int) -> np.ndarray:
         """Register k aligned chips; -> their row numbers.  Embedding happens in `flush`."""
@@ -577,9 +590,15 @@ class FaceTable:
         use = chips[:take].contiguous()
         if self.lazy:
             emb, _ = eng.embed(use, take, False)
-            fp, _, _ = eng.match(emb, None, None, take)           # normalise(e(x))
+            fp, sim, _ = eng.match(emb, None, None, take)         # normalise(e(x)); sim: against the bank on the device
             self.raw.append(emb[:take])
             self.chip_list.append(use)
+            ev = torch.cuda.Event() if use.is_cuda else None
+            if ev is not None:
+                ev.record(eng.stream)
+            self.part_start.append(self.embedded)
+            self.sim_parts.append((self.embedded, take, sim, ev))
+            self.embedded += take
         else:
             emb, emb_flip = eng.embed(use, take, True)
             fp, _, _ = eng.match(emb, None, None, take)           # normalise(e(x))
@@ -594,8 +613,53 @@ class FaceTable:
         else:
             self.pending, self.pending_n = [], 0
 
+    # ---- early flips (lazy mode): see FlipPredictor
+    def poll_fd0(self, block: bool = False) -> int:
+        """Fetch the similarities (to the bank that was on the device during the superset) of finished runs; -> number of
+        leading rows whose distance is on the host.  Never waits for the GPU unless `block`."""
+        while self.sim_fetched < len(self.sim_parts):
+            start, take, sim, ev = self.sim_parts[self.sim_fetched]
+            if ev is not None and not block and not ev.query():
+                break
+            if ev is not None and block:
+                ev.synchronize()
+            self.fd0_host = np.concatenate([self.fd0_host, 1.0 - sim[:take].cpu().numpy().astype(np.float64)])
+            self.sim_fetched += 1
+        return len(self.fd0_host)
+
+    def queue_flips(self, eng, rows: np.ndarray):
+        """Rows (already flushed) whose flip feature will most likely be needed: embed them in runs of EMBED_RUN images."""
+        if len(rows):
+            self.flip_queue.append(np.asarray(rows, np.int64))
+            self.flip_queue_n += len(rows)
+        while self.flip_queue_n >= self.EARLY_RUN:
+            self._run_flips(eng, self.EARLY_RUN)
+
+    def _run_flips(self, eng, n: int):
+        allr = np.concatenate(self.flip_queue)
+        rows, rest = allr[:n], allr[n:]
+        self.flip_queue = [rest] if len(rest) else []
+        self.flip_queue_n = len(rest)
+        starts = np.asarray(self.part_start, np.int64)
+        part = np.searchsorted(starts, rows, side="right") - 1
+        with torch.cuda.stream(eng.stream):
+            chips, raws = [], []
+            for pi in np.unique(part):
+                loc = torch.as_tensor(rows[part == pi] - starts[pi], device=self.chip_list[pi].device)
+                chips.append(self.chip_list[pi].index_select(0, loc))
+                raws.append(self.raw[pi].index_select(0, loc))
+            chips = torch.cat(chips, 0).contiguous()
+            raws = torch.cat(raws, 0).contiguous()
+        order = np.concatenate([rows[part == pi] for pi in np.unique(part)])
+        _, emb_flip = eng.embed(chips, len(order), "only")
+        ff, _, _ = eng.match(raws, emb_flip, None, len(order))
+        self.early.append((order, ff[:len(order)]))
+        self.flip_passes += len(order)
+
     def finalize(self, eng):
         self.flush(eng)
+        if self.lazy and self.flip_queue_n:
+            self._run_flips(eng, self.flip_queue_n)
         with torch.cuda.stream(eng.stream):
             if self.count:
                 self.plain = torch.cat(self.feat_plain, 0).contiguous()
@@ -610,6 +674,15 @@ class FaceTable:
                 self.flip = eng.empty((1, L.FEAT_DIM), torch.float32)
         self.flip_ready = np.zeros(self.count, bool) if self.lazy else np.ones(self.count, bool)
         self.flip_host = np.zeros((self.count, L.FEAT_DIM), np.float32) if self.lazy else None
+        for rows, ff in self.early:           # flips computed while the superset was running
+            with torch.cuda.stream(eng.stream):
+                self.flip.index_copy_(0, torch.as_tensor(rows, device=self.flip.device), ff)
+        if self.early:
+            eng.sync()
+            for rows, ff in self.early:
+                self.flip_host[rows] = ff.cpu().numpy()
+                self.flip_ready[rows] = True
+        self.early = []
         self.feat_plain, self.feat_flip, self.raw, self.chip_list = [], [], [], []
 
     def ensure_flip(self, eng, rows: np.ndarray) -> bool:
@@ -662,8 +735,45 @@ def _collect_variant(eng, frames, det, idx_list, records, key, table: FaceTable,
         off += k
 
 
+class FlipPredictor:
+    """`_predict_flip_rows` as an incremental state machine, run while the superset is still in progress: as soon as the plain
+    distances (to the initial bank) of a sample's faces are on the host, the sample is passed through the same rule and the rows
+    it selects are queued for an early flip pass (FaceTable.queue_flips).  The separate prediction after the superset still
+    runs over everything, so this only moves ArcFace work earlier -- into the time the SMs otherwise wait for frames to cross
+    PCIe when the clip is host-resident -- and never changes which rows are computed eagerly, let alone results."""
+
+    def __init__(self, cfg, fps: int, carry_in: bool, margin: float = 0.12):
+        self.thr = float(cfg.prescan_fd_enter) + margin
+        stride = max(1, int(cfg.prescan_stride))
+        exit_cool = int(round(max(0.0, float(getattr(cfg, "prescan_exit_cooldown_sec", 0.5))) * fps))
+        self.tail = (exit_cool + stride - 1) // stride + 1
+        self.remaining = self.tail if carry_in else 0
+        self.samples: List[List[np.ndarray]] = []      # per sample (in order): its row arrays
+        self.next = 0
+
+    def add(self, records, chunk):
+        for idx in chunk:
+            self.samples.append(_rows_of(records[idx]))
+
+    def advance(self, table: "FaceTable", eng, block: bool = False):
+        have = table.poll_fd0(block)
+        out: List[np.ndarray] = []
+        while self.next < len(self.samples):
+            rws = self.samples[self.next]
+            if rws and max(int(r.max()) for r in rws if len(r)) >= have:
+                break
+            if self.remaining > 0:
+                out += rws
+                self.remaining -= 1
+            if rws and min(float(table.fd0_host[r].min()) for r in rws if len(r)) <= self.thr:
+                self.remaining = self.tail
+            self.next += 1
+        if out:
+            table.queue_flips(eng, np.concatenate(out))
+
+
 def compute_superset(clip, idxs: Sequence[int], face: FaceEmbedder, cfg, batch: int = 32, max_faces: int = 4096,
-                     lazy_flip: bool = False):
+                     lazy_flip: bool = False, predictor: Optional["FlipPredictor"] = None):
     """GPU stage of the batched pre-scan for the samples `idxs` (fast pre-scan settings must be active).
     lazy_flip: compute e(flip x) later, only for the faces the replay evaluates while a span is active.
 
@@ -731,6 +841,10 @@ def compute_superset(clip, idxs: Sequence[int], face: FaceEmbedder, cfg, batch: 
 
     cur = issue(0) if chunks else None
     for ci in range(len(chunks)):
+        if predictor is not None:
+            # early flip passes go into the stream BEFORE the next batch's work, which may sit waiting for its frames to
+            # arrive over PCIe: that wait is the time these passes are meant to fill
+            predictor.advance(table, eng)
         nxt = issue(ci + 1) if ci + 1 < len(chunks) else None
         cur["done"].synchronize()
         chunk, frames, dyn, det0 = cur["chunk"], cur["frames"], cur["dyn"], cur["det0"]
@@ -744,6 +858,8 @@ def compute_superset(clip, idxs: Sequence[int], face: FaceEmbedder, cfg, batch: 
         cur = nxt
         if not empty:
             encode_chunk(chunk)
+            if predictor is not None:
+                predictor.add(records, chunk)
             continue
         with torch.cuda.stream(eng.stream):
             sub = frames.index_select(0, torch.as_tensor(empty, device=frames.device)).contiguous()
@@ -769,6 +885,10 @@ def compute_superset(clip, idxs: Sequence[int], face: FaceEmbedder, cfg, batch: 
                 records[sidx].heavy_raw[deg] = int(raw[j])
             _collect_variant(eng, sub2, hv, sel_idx, records, deg, table, max_faces)
         encode_chunk(chunk)
+        if predictor is not None:
+            predictor.add(records, chunk)
+    if predictor is not None:
+        predictor.advance(table, eng)
     table.finalize(eng)
     one = lambda parts, dt: np.concatenate(parts).astype(dt) if parts else np.zeros(1, dt)
     table.encoded = (np.concatenate(meta_parts, 0) if meta_parts else np.zeros((0, L.REPLAY_META), np.int32),
@@ -1122,7 +1242,16 @@ def prescan_batched(clip, fps: int, face: FaceEmbedder, ref_feat, cfg, batch: in
         per = (len(idxs) + world - 1) // world
         mine = idxs[rank * per:(rank + 1) * per]
         lazy = os.environ.get("PCB_EAGER_FLIP", "0") != "1"
-        records, table = compute_superset(clip, mine, face, cfg, batch=batch, lazy_flip=lazy)
+        predictor = None
+        # Early flip passes (FlipPredictor) are OFF by default: measured on B200 they move half of the predicted flips into the
+        # superset but lengthen it by as much, resident (52 -> 66 ms) and host-resident (75 -> 88 ms) alike, i.e. the superset
+        # has no idle SM time to fill even when it is PCIe-paced (4 430 -> 4 360-4 420 frames/s e2e); PCB_EARLY_FLIP=1 enables it.
+        if lazy and os.environ.get("PCB_EARLY_FLIP", "0") == "1":
+            bank0 = RefBank(cfg, ref_feat)
+            if len(bank0):
+                eng.set_bank(bank0.array())      # FaceTable.flush then gets the distances to the initial bank for free
+                predictor = FlipPredictor(cfg, fps, carry_in=rank > 0)
+        records, table = compute_superset(clip, mine, face, cfg, batch=batch, lazy_flip=lazy, predictor=predictor)
         eng.sync()
         mark("superset")
         if lazy and table.count:

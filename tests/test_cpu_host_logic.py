@@ -227,3 +227,49 @@ def test_cache_layout_is_the_references(tmp_path):
     cfg.prescan_cache_mode = "off"
     assert PS.save_cache(cfg, 23.976024, 1000, spans, bank, root=tmp_path / "c3") is None
     assert PS.load_cache(cfg, 23.976024, 1000, tmp_path / "cache")[0] is False
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+@pytest.mark.parametrize("carry", [False, True])
+def test_flip_predictor_matches_batch_rule(seed, carry):
+    """The incremental predictor that runs during the superset selects exactly the rows `_predict_flip_rows` selects afterwards,
+    however the plain distances trickle in (runs of arbitrary size, samples whose rows straddle runs, empty samples)."""
+    rng = np.random.default_rng(seed)
+    cfg = PrescanParams()
+    fps, n = 24, 160
+    records, rows_next = {}, 0
+    for i in range(n):
+        rec = PS.SampleRecord(i)
+        k = int(rng.integers(0, 4))
+        if k:
+            rec.up = PS._Variant(np.zeros((k, 4), np.int32), np.ones(k), np.arange(rows_next, rows_next + k))
+            rows_next += k
+        if rng.random() < 0.15:
+            rec.heavy[90] = PS._Variant(np.zeros((1, 4), np.int32), np.ones(1), np.arange(rows_next, rows_next + 1))
+            rows_next += 1
+        records[i] = rec
+    fd = rng.uniform(0.2, 1.2, rows_next)
+    want = np.sort(PS._predict_flip_rows(records, list(range(n)), fd, cfg, fps, carry_in=carry))
+
+    class Table:                       # the part of FaceTable the predictor touches
+        def __init__(self):
+            self.fd0_host = np.zeros((0,), np.float64)
+            self.avail = 0
+            self.queued = []
+
+        def poll_fd0(self, block=False):
+            self.fd0_host = fd[:rows_next if block else self.avail]
+            return len(self.fd0_host)
+
+        def queue_flips(self, eng, rows):
+            self.queued.append(np.asarray(rows))
+
+    table, pred = Table(), PS.FlipPredictor(cfg, fps, carry_in=carry)
+    for c0 in range(0, n, 16):
+        pred.add(records, list(range(c0, min(n, c0 + 16))))
+        table.avail = min(rows_next, table.avail + int(rng.integers(0, 40)))     # distances arrive late and in odd amounts
+        pred.advance(table, None)
+    pred.advance(table, None, block=True)
+    got = np.sort(np.concatenate(table.queued)) if table.queued else np.zeros((0,), np.int64)
+    assert pred.next == n
+    assert np.array_equal(got, want)
