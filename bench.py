@@ -329,9 +329,9 @@ def main():
         "roofline": {"kernel": "conv_tc2_kernel", "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": achieved / peak_tf if peak_tf else None,
                      # DRAM bytes per launch of the dominant layer shape (iResNet-100 stage 3, 14x14 256->256, 444 images) from the
-                     # round's ncu --set full capture (profiles/r01_ncu_conv_tc2_stage3_keymetrics.txt): 59.5 MB read + 9.8 MB
+                     # round's ncu --set full capture (profiles/r01_ncu_conv_tc2_stage3_keymetrics.txt): 59.5 MB read + 11.7 MB
                      # written for 59.4 MB of algorithmic input+weight bytes (the output stays in the 126 MB L2)
-                     "traffic": 69.2e6, "traffic_layer": "14x14 256->256 conv1, 444 images, 102.6 GFLOP/launch",
+                     "traffic": 71.2e6, "traffic_layer": "14x14 256->256 conv1, 444 images, 102.6 GFLOP/launch",
                      "peak_source": peak_src,
                      "conv_launches": conv_n, "conv_ms_per_step": conv_ms / args.steps,
                      "conv_share_of_step": (conv_ms / ms) if ms > 0 else None},
