@@ -98,6 +98,7 @@ struct Conv2Params {
   // each tap is its own TMA load through a 4-D map with element strides {1,2,2,1} (only the even input pixels of the tap
   // are fetched), so the GEMM runs on the OUTPUT grid instead of computing all input positions and dropping 3 of 4
   int strided;
+  int tma_store;   // 1: fp16 outputs leave through TMA stores of the staged 32-row x 32-channel chunk (stride-1 spatial layers)
   int pair;        // 1: 2-CTA cluster, cta_group::2 (m_tiles counts PAIR tiles of 2*mt*128 rows; b_bytes is this CTA's half stage)
   int s_bx, s_by, s_nb;        // output pixels / output rows / images per tile
   int s_tx, s_ty;              // tiles per output row / per image column of rows
@@ -250,6 +251,15 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t bar
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
         : "memory");
 }
+// TMA store of a staged chunk (shared -> global, bulk async group of the issuing thread)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -406,7 +416,8 @@ constexpr int kVarHalo = 0, kVarStrided = 1, kVarPair = 2;
 template <int kAct, bool kRes, bool kOut2, int kOutMode, int kVar>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
-                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ Conv2Params p) {
+                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO,
+                const __grid_constant__ CUtensorMap tmO2, const __grid_constant__ Conv2Params p) {
   constexpr bool kPair = kVar == kVarPair;
   constexpr bool kStrided = kVar == kVarStrided;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -414,7 +425,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + (size_t)p.a_stages * p.a_stage_bytes;
   float* vec = (float*)(smem_b + (size_t)p.b_stages * p.b_bytes);   // scale | bias | slope | scale2 | bias2
-  uint8_t* stage_buf = (uint8_t*)(vec + 5 * p.vec_n);                  // [8 warps][2 KB] epilogue transpose buffers
+  // [8 warps][2 KB] epilogue staging buffers, 1 KB aligned: the TMA store's 64B swizzle is a function of address bits 7-8
+  uint8_t* stage_buf = (uint8_t*)(((uintptr_t)(vec + 5 * p.vec_n) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = (uint64_t*)(stage_buf + kEpiWarps * 2048);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + kMaxA;
@@ -934,41 +946,79 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     if (ch + e * 4 < p.out_c_store) *(float4*)(o + e * 4) = make_float4(y[e * 4], y[e * 4 + 1], y[e * 4 + 2], y[e * 4 + 3]);
                 }
               } else {
-                // transpose through shared memory so that 4 lanes write one row's 64 contiguous bytes (full sectors)
-                const bool piece_ok = ch + rb_piece * 8 < p.out_c_store;
+                if (!kStrided && p.tma_store) {
+                  // The chunk (32 consecutive P-rows x 32 channels) is staged in the 64B-swizzled layout TMA expects and leaves
+                  // through ONE bulk tensor store per output: no read-back, no per-row address arithmetic, asynchronous.  Rows
+                  // that are not image pixels are staged as zeros, so the padding of the output stays zero; rows past the end of
+                  // the tensor and channels past its width are clipped by the tensor map.
+                  const int prow32 = (int)(row0 - row_in_tile) + j * kBlockM + q * 32;     // first P-row of this warp's 32 rows
+                  uint4 pk[4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) st_shared_v4(stg_w + (uint32_t)(((e ^ w_sw) & 3) * 16), pack_h8(y + e * 8));
-                __syncwarp();
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const int r = i * 8 + (lane >> 2);
-                  const uint4 o4 = ld_shared_v4(smem_u32(stg) + (uint32_t)(r * 64 + ((rb_piece ^ (r >> 1)) & 3) * 16));
-                  if (wvalid[i] && piece_ok) *(uint4*)(p.out + woff[i] + ch) = o4;
-                }
-                if (kOut2) {
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) {
-                    const float4 s4 = ld_shared_f4(v_scale2 + 4u * (uint32_t)(ch + e * 4));
-                    const float4 b4 = ld_shared_f4(v_bias2 + 4u * (uint32_t)(ch + e * 4));
-                    y[e * 4 + 0] = fmaf(y[e * 4 + 0], s4.x, b4.x);
-                    y[e * 4 + 1] = fmaf(y[e * 4 + 1], s4.y, b4.y);
-                    y[e * 4 + 2] = fmaf(y[e * 4 + 2], s4.z, b4.z);
-                    y[e * 4 + 3] = fmaf(y[e * 4 + 3], s4.w, b4.w);
-                  }
+                  for (int e = 0; e < 4; ++e) pk[e] = ri.valid ? pack_h8(y + e * 8) : make_uint4(0, 0, 0, 0);
+                  if (lane == 0) tma_store_wait_read();       // the previous store has finished reading the staging buffer
                   __syncwarp();
 #pragma unroll
+                  for (int e = 0; e < 4; ++e) st_shared_v4(stg_w + (uint32_t)(((e ^ w_sw) & 3) * 16), pk[e]);
+                  fence_proxy_async_smem();
+                  __syncwarp();
+                  if (lane == 0) tma_store_2d(&tmO, smem_u32(stg), ch, prow32);
+                  if (kOut2) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                      const float4 s4 = ld_shared_f4(v_scale2 + 4u * (uint32_t)(ch + e * 4));
+                      const float4 b4 = ld_shared_f4(v_bias2 + 4u * (uint32_t)(ch + e * 4));
+                      y[e * 4 + 0] = fmaf(y[e * 4 + 0], s4.x, b4.x);
+                      y[e * 4 + 1] = fmaf(y[e * 4 + 1], s4.y, b4.y);
+                      y[e * 4 + 2] = fmaf(y[e * 4 + 2], s4.z, b4.z);
+                      y[e * 4 + 3] = fmaf(y[e * 4 + 3], s4.w, b4.w);
+                    }
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) pk[e] = ri.valid ? pack_h8(y + e * 8) : make_uint4(0, 0, 0, 0);
+                    if (lane == 0) tma_store_wait_read();
+                    __syncwarp();
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) st_shared_v4(stg_w + (uint32_t)(((e ^ w_sw) & 3) * 16), pk[e]);
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) tma_store_2d(&tmO2, smem_u32(stg), ch, prow32);
+                  }
+                } else {
+                // transpose through shared memory so that 4 lanes write one row's 64 contiguous bytes (full sectors)
+                  const bool piece_ok = ch + rb_piece * 8 < p.out_c_store;
+  #pragma unroll
                   for (int e = 0; e < 4; ++e) st_shared_v4(stg_w + (uint32_t)(((e ^ w_sw) & 3) * 16), pack_h8(y + e * 8));
                   __syncwarp();
-#pragma unroll
+  #pragma unroll
                   for (int i = 0; i < 4; ++i) {
                     const int r = i * 8 + (lane >> 2);
                     const uint4 o4 = ld_shared_v4(smem_u32(stg) + (uint32_t)(r * 64 + ((rb_piece ^ (r >> 1)) & 3) * 16));
-                    if (wvalid[i] && piece_ok) *(uint4*)(p.out2 + woff2[i] + ch) = o4;
+                    if (wvalid[i] && piece_ok) *(uint4*)(p.out + woff[i] + ch) = o4;
+                  }
+                  if (kOut2) {
+  #pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                      const float4 s4 = ld_shared_f4(v_scale2 + 4u * (uint32_t)(ch + e * 4));
+                      const float4 b4 = ld_shared_f4(v_bias2 + 4u * (uint32_t)(ch + e * 4));
+                      y[e * 4 + 0] = fmaf(y[e * 4 + 0], s4.x, b4.x);
+                      y[e * 4 + 1] = fmaf(y[e * 4 + 1], s4.y, b4.y);
+                      y[e * 4 + 2] = fmaf(y[e * 4 + 2], s4.z, b4.z);
+                      y[e * 4 + 3] = fmaf(y[e * 4 + 3], s4.w, b4.w);
+                    }
+                    __syncwarp();
+  #pragma unroll
+                    for (int e = 0; e < 4; ++e) st_shared_v4(stg_w + (uint32_t)(((e ^ w_sw) & 3) * 16), pack_h8(y + e * 8));
+                    __syncwarp();
+  #pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                      const int r = i * 8 + (lane >> 2);
+                      const uint4 o4 = ld_shared_v4(smem_u32(stg) + (uint32_t)(r * 64 + ((rb_piece ^ (r >> 1)) & 3) * 16));
+                      if (wvalid[i] && piece_ok) *(uint4*)(p.out2 + woff2[i] + ch) = o4;
+                    }
                   }
                 }
               }
             }
-          }
+                }
           if (kRes) res_load(R[u]);     // this slot's next use: four chunks from now
           if (++c == nch) {
             c = 0;
@@ -982,6 +1032,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
       }
     }
+    if (lane == 0) tma_store_wait_all();     // every bulk store of this thread has been written before the CTA exits
     if (p.dbg && blockIdx.x == 0 && warp == kEpiWarp0 && lane == 0) {
       p.dbg[9] = (unsigned long long)w_full;
       p.dbg[10] = (unsigned long long)t_epi;
@@ -1170,7 +1221,7 @@ int pcb_conv_tc2(pcb_ctx* c, const ConvArgs& a) {
   if (w.n_tile % 16 || w.n_tile > 256 || w.n_tile < 16) return pcb_fail(c, PCB_ERR_ARG, "conv_tc2: bad n_tile");
   p.sub_cols = pcb_round_up(w.n_tile, 32);
   const int ksteps = p.taps * p.kchunks;
-  const int fixed = 5 * p.vec_n * 4 + kEpiWarps * 2048 + (2 * kMaxA + 2 * kMaxB + 4) * 8 + 16 + 1024;
+  const int fixed = 5 * p.vec_n * 4 + 1024 + kEpiWarps * 2048 + (2 * kMaxA + 2 * kMaxB + 4) * 8 + 16 + 1024;
   const int room = kSmemBudget - fixed;
 
   // stride-2 convolutions: GEMM on the output grid, one strided 4-D TMA load per tap (see Conv2Params::strided)
@@ -1273,7 +1324,7 @@ int pcb_conv_tc2(pcb_ctx* c, const ConvArgs& a) {
   if (p.a_stages > kMaxA) p.a_stages = kMaxA;
   const size_t smem = (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * p.b_bytes + fixed;
 
-  CUtensorMap tmA, tmA2, tmB;
+  CUtensorMap tmA, tmA2, tmB, tmO, tmO2;
   if (strided) {
     if (!make_map_4d_s2(&tmA, in.data, in.n, in.h + kPad, in.w + kPad, in.cp, p.kc, p.s_bx, p.s_by, p.s_nb))
       return pcb_fail(c, PCB_ERR_CUDA, "cuTensorMapEncodeTiled(A strided) failed");
@@ -1287,6 +1338,21 @@ int pcb_conv_tc2(pcb_ctx* c, const ConvArgs& a) {
   if (!make_map_2d(&tmB, w.w, (uint64_t)w.npad, (uint64_t)w.taps * w.cin_w, (uint64_t)w.taps * w.cin_w, (uint32_t)p.b_load_rows, p.kc))
     return pcb_fail(c, PCB_ERR_CUDA, "cuTensorMapEncodeTiled(B) failed");
 
+  // TMA stores for the fp16 outputs of stride-1 spatial layers (output P-rows = input P-rows).  PCB_CONV_TMA_STORE = 0 per-lane
+  // stores everywhere, 1 (default) TMA stores on maps at least 24 pixels wide, 2 wherever legal.  Measured (same library, same box):
+  // the epilogue-bound layers gain 3-10 % (28x28 +res+out2 -6.5 %, stem -10 %), the 14x14 / 7x7 layers LOSE ~2 %: there the
+  // padding rows the store also writes (as zeros) are 23-40 % of the tile and those layers are bound by TMA weight loads.
+  static const int tma_store_mode = env_int("PCB_CONV_TMA_STORE", 1);
+  p.tma_store = (tma_store_mode && (tma_store_mode == 2 || in.w >= 24) && !strided && !in.dense && p.stride == 1 && p.out &&
+                 !p.out_s32 && !p.out_f32) ? 1 : 0;
+  tmO = tmB;
+  tmO2 = tmB;
+  if (p.tma_store) {
+    if (!make_map_2d(&tmO, p.out, (uint64_t)a.out->rows(), (uint64_t)p.out_cp, (uint64_t)p.out_cp, 32, 32))
+      return pcb_fail(c, PCB_ERR_CUDA, "cuTensorMapEncodeTiled(out) failed");
+    if (p.out2 && !make_map_2d(&tmO2, p.out2, (uint64_t)a.out2->rows(), (uint64_t)p.out2_cp, (uint64_t)p.out2_cp, 32, 32))
+      return pcb_fail(c, PCB_ERR_CUDA, "cuTensorMapEncodeTiled(out2) failed");
+  }
   const int total = p.m_tiles * p.n_tiles;
   const int grid = p.pair ? 2 * (total < units ? total : units) : (total < c->num_sms ? total : c->num_sms);
   // algorithmic FLOPs of this layer: 2 * output pixels * cout * cin * taps (real, unpadded extents)
@@ -1331,9 +1397,9 @@ int pcb_conv_tc2(pcb_ctx* c, const ConvArgs& a) {
       at[0].val.clusterDim.z = 1;                                                                                      \
       cfg.attrs = at;                                                                                                  \
       cfg.numAttrs = 1;                                                                                                \
-      le = cudaLaunchKernelEx(&cfg, conv_tc2_kernel<ACT, RES, OUT2, MODE, VAR>, tmA, tmA2, tmB, p);                    \
+      le = cudaLaunchKernelEx(&cfg, conv_tc2_kernel<ACT, RES, OUT2, MODE, VAR>, tmA, tmA2, tmB, tmO, tmO2, p);                    \
     } else {                                                                                                           \
-      conv_tc2_kernel<ACT, RES, OUT2, MODE, VAR><<<grid, kThreads, smem, c->stream>>>(tmA, tmA2, tmB, p);              \
+      conv_tc2_kernel<ACT, RES, OUT2, MODE, VAR><<<grid, kThreads, smem, c->stream>>>(tmA, tmA2, tmB, tmO, tmO2, p);              \
       le = cudaSuccess;                                                                                                \
     }                                                                                                                  \
   }
