@@ -26,6 +26,17 @@ def test_header_symbols_are_exported():
     assert set(_lib.EXPORTS) == set(names)
 
 
+def test_layout_pad_is_reported_by_the_library():
+    """pcb_layout_pad needs no GPU: the host side takes the activation-layout padding from the library it loaded."""
+    import ctypes as C
+    from person_capture_b200 import _lib
+    lib = _lib.load()
+    lo, pad = C.c_int(-1), C.c_int(-1)
+    lib.pcb_layout_pad(C.byref(lo), C.byref(pad))
+    assert (lo.value, pad.value) == (_lib.P_PAD_LO, _lib.P_PAD)
+    assert (lo.value, pad.value) in ((1, 2), (0, 1))          # ring (product) or trailing pad (build-time experiment)
+
+
 def test_no_cpu_fallback_without_gpu():
     import torch
     if torch.cuda.is_available():
