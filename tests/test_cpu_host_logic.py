@@ -273,3 +273,76 @@ def test_flip_predictor_matches_batch_rule(seed, carry):
     got = np.sort(np.concatenate(table.queued)) if table.queued else np.zeros((0,), np.int64)
     assert pred.next == n
     assert np.array_equal(got, want)
+
+
+class _FakeEngine:
+    """CPU stand-in for Engine.embed / Engine.match: a fixed random projection of the chip (mirrored for the flip variant)."""
+    stream = None
+
+    def __init__(self, bank):
+        import torch
+        g = torch.Generator().manual_seed(7)
+        self.proj = torch.randn(8 * 8 * 3, 512, generator=g)
+        self.bank = torch.as_tensor(bank, dtype=torch.float32)
+
+    def _e(self, chips, flip):
+        import torch
+        x = chips.to(torch.float32)
+        if flip:
+            x = torch.flip(x, dims=[2])
+        return x.reshape(x.shape[0], -1) @ self.proj
+
+    def embed(self, chips, f, flip):
+        only = flip == "only"
+        return (None if only else self._e(chips[:f], False)), (self._e(chips[:f], True) if flip else None)
+
+    def match(self, emb, emb_flip, use_flip, f, want_feat=True):
+        import torch
+        v = emb[:f] + (emb_flip[:f] if emb_flip is not None else 0)
+        v = v / v.norm(dim=1, keepdim=True).clamp_min(1e-6)
+        sim = (v @ self.bank.T).max(dim=1).values
+        return v, sim, torch.zeros(f, dtype=torch.int32)
+
+    def sync(self):
+        pass
+
+
+def test_early_flip_passes_equal_on_demand_flips(monkeypatch):
+    """FaceTable.queue_flips (flip passes issued while chips are still being queued, rows spread over several flushed runs)
+    leaves exactly what ensure_flip computes afterwards: same features, same ready flags, same pass count."""
+    import torch
+    rng = np.random.default_rng(3)
+    bank = rng.standard_normal((3, 512)).astype(np.float32)
+    bank /= np.linalg.norm(bank, axis=1, keepdims=True)
+    monkeypatch.setattr(PS.FaceTable, "EMBED_RUN", 16)
+    monkeypatch.setattr(PS.FaceTable, "EARLY_RUN", 10)
+    batches = [torch.as_tensor(rng.integers(0, 256, (k, 8, 8, 3), dtype=np.uint8)) for k in (7, 13, 5, 22, 9)]
+    early_rows = [np.array([1, 5, 6]), np.array([0, 8, 14, 15, 17]), np.array([19, 20, 30, 2]), np.array([33, 40, 41])]
+
+    eng = _FakeEngine(bank)
+    ref = PS.FaceTable(lazy=True)
+    for b in batches:
+        ref.queue(eng, b, b.shape[0])
+    ref.finalize(eng)
+    want_rows = np.unique(np.concatenate(early_rows))
+    ref.ensure_flip(eng, want_rows)
+
+    tab = PS.FaceTable(lazy=True)
+    for i, b in enumerate(batches):
+        tab.queue(eng, b, b.shape[0])
+        have = tab.poll_fd0()
+        assert have == tab.embedded
+        if i < len(early_rows):
+            rows = early_rows[i][early_rows[i] < have]
+            tab.queue_flips(eng, rows)
+            early_rows[i] = rows
+    tab.finalize(eng)
+    done = np.unique(np.concatenate(early_rows))
+    assert tab.flip_ready[done].all() and tab.flip_ready.sum() == len(done)
+    assert tab.flip_passes == len(done)
+    np.testing.assert_allclose(tab.flip_host[done], ref.flip_host[done], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(tab.flip[torch.as_tensor(done)].numpy(), ref.flip[torch.as_tensor(done)].numpy(), rtol=0, atol=1e-6)
+    np.testing.assert_allclose(tab.plain.numpy(), ref.plain.numpy(), rtol=0, atol=0)
+    # distances to the bank that was "on the device" during the queueing (the last run is flushed by finalize)
+    assert tab.poll_fd0(block=True) == tab.count
+    np.testing.assert_allclose(tab.fd0_host, 1.0 - (ref.plain.numpy() @ bank.T).max(1), atol=1e-5)
