@@ -143,8 +143,16 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_oracle_rate(frames_u8, ref_img, cfg, sample: int, threads: int):
-    """Frames/s of the CPU oracle pre-scan loop over the first `sample` frames (bounded)."""
+def spans_digest(spans, bank) -> str:
+    """sha1 over the kept spans and the shape of the final bank: what must be identical on every rank and at every N."""
+    import hashlib
+    rows = 0 if bank is None else int(np.asarray(bank).reshape(-1, 512).shape[0])
+    return hashlib.sha1(json.dumps([[int(a), int(b)] for a, b in spans] + [rows]).encode()).hexdigest()[:16]
+
+
+def cpu_oracle_rate(frames_u8, ref_img, cfg, sample: int, threads: int, out: dict | None = None):
+    """Frames/s of the CPU oracle pre-scan loop over the first `sample` frames (bounded).  `out` receives the oracle's
+    per-sample log, spans and bank (the parity block of the bench line compares the GPU path with them)."""
     import torch
     torch.set_num_threads(threads)
     import cv2
@@ -157,10 +165,14 @@ def cpu_oracle_rate(frames_u8, ref_img, cfg, sample: int, threads: int):
     face = FaceEmbedderOracle(SCRFDOracle(FoldedSCRFD("scrfd_10g_bnkps", weights.load_params("scrfd_10g_bnkps"))),
                               FoldedIResNet("arcface_r100", weights.load_params("arcface_r100")), conf=cfg.face_det_conf)
     bank = OP.build_reference_bank(face, [ref_img], cfg)
-    sample = min(sample, len(frames_u8))
+    P = len(frames_u8)
+    OP.prescan(lambda i: frames_u8[i % P] if i < 4 else None, 24, 4, face, bank, cfg)     # untimed: thread pools, first-touch pages
+    log = []
     t0 = time.perf_counter()
-    OP.prescan(lambda i: frames_u8[i] if i < sample else None, 24, sample, face, bank, cfg)
+    spans, bank2 = OP.prescan(lambda i: frames_u8[i % P] if i < sample else None, 24, sample, face, bank, cfg, log=log)
     dt = time.perf_counter() - t0
+    if out is not None:
+        out.update(log=log, spans=spans, bank=bank2, bank0=bank)
     return sample / dt, dt
 
 
@@ -170,8 +182,8 @@ def run_reference_arm(args):
         return
     cfg = make_cfg()
     threads = os.cpu_count() or 1
-    sample = args.cpu_sample
-    frames, ref_img = make_pool(sample)
+    sample = args.ref_sample
+    frames, ref_img = make_pool(min(sample, args.pool))
     rates = []
     for s in range(args.warmup + args.steps):
         r, _ = cpu_oracle_rate(frames, ref_img, cfg, sample, threads)
@@ -198,7 +210,8 @@ def main():
     ap.add_argument("--frames-per-step", type=int, default=512, help="clip length per GPU per step")
     ap.add_argument("--pool", type=int, default=64, help="distinct 1080p frames resident in HBM")
     ap.add_argument("--batch", type=int, default=64)
-    ap.add_argument("--cpu-sample", type=int, default=12)
+    ap.add_argument("--cpu-sample", type=int, default=96, help="frames of the clip the CPU oracle is timed on (cpu_baseline + parity block)")
+    ap.add_argument("--ref-sample", type=int, default=48, help="frames per step of the --impl reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -234,7 +247,8 @@ def main():
 
     def step(clip):
         stats = {}
-        spans, _ = PS.prescan_batched(clip, 24, face, bank, cfg, batch=args.batch, stats=stats)
+        spans, bank_out = PS.prescan_batched(clip, 24, face, bank, cfg, batch=args.batch, stats=stats)
+        faces_seen["digest"] = spans_digest(spans, bank_out)
         faces_seen["n"] = stats.get("faces", 0)               # faces aligned + embedded by THIS rank in the step
         faces_seen["passes"] = stats.get("arcface_passes", 0)  # ArcFace image passes (e(x), plus e(flip x) where the span logic needs it)
         faces_seen["spans"] = [list(map(int, sp)) for sp in spans]
@@ -290,6 +304,21 @@ def main():
     e2e_value = total * e2e_steps / (ms_e / 1000.0)
     h2d = clip_host.h2d_bytes // e2e_steps
 
+    # every rank must have replayed to the same spans / bank; rank 0 additionally repeats the whole clip ALONE (no collective)
+    # and the N-rank result must equal it
+    digest = faces_seen.get("digest")
+    multi = None
+    if world > 1:
+        mine = torch.tensor([int(digest, 16) & 0x7fffffffffffffff], dtype=torch.int64, device=eng.tdev)
+        allv = torch.empty((world,), dtype=torch.int64, device=eng.tdev)
+        dist.all_gather_into_tensor(allv, mine)
+        ranks_agree = bool((allv == allv[0]).all().item())
+        single = None
+        if rank == 0:
+            s1, b1 = PS.prescan_batched(clip_dev, 24, face, bank, cfg, batch=args.batch, single_rank=True)
+            single = spans_digest(s1, b1)
+        multi = {"ranks_agree": ranks_agree, "single_rank_digest": single, "equals_single_rank": single == digest if rank == 0 else None}
+        dist.barrier()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -313,7 +342,7 @@ def main():
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": args.frames_per_step, "batch": args.batch,
                    "pool_frames": args.pool, "l2_policy": "inputs larger than L2 (pool 398 MB of 1080p frames, cycled)",
-                   "detector_input": 512, "kept_spans": faces_seen.get("spans"), "faces_per_step_per_gpu": faces_seen["n"], "arcface_passes_per_step_per_gpu": faces_seen["passes"],
+                   "detector_input": 512, "kept_spans": faces_seen.get("spans"), "spans_sha": digest, "faces_per_step_per_gpu": faces_seen["n"], "arcface_passes_per_step_per_gpu": faces_seen["passes"],
                    "flip_tta": "e(flip x) only for faces evaluated while a span is active (as the reference); N>1 ranks embed both variants before the all-gather",
                    "weights": "SCRFD trained on synthetic faces; ArcFace seeded random + calibrated affine (no checkpoints offline)",
                    "scrfd_gflop_per_frame": 2e-9 * graphs.graph_macs(g_s, 256, 256),
@@ -336,12 +365,29 @@ def main():
                      "conv_launches": conv_n, "conv_ms_per_step": conv_ms / args.steps,
                      "conv_share_of_step": (conv_ms / ms) if ms > 0 else None},
     }
+    if multi is not None:
+        line["multi_gpu_check"] = multi
     if not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        rate, dt = cpu_oracle_rate(frames_np, ref_img, cfg, args.cpu_sample, threads)
+        ora = {}
+        rate, dt = cpu_oracle_rate(frames_np, ref_img, cfg, args.cpu_sample, threads, out=ora)
         line["cpu_baseline"] = {"value": rate, "unit": "frames/s", "cores": threads, "kind": "port",
-                                "sample": f"first {min(args.cpu_sample, len(frames_np))} frames of the same clip, CPU oracle "
-                                          f"(torch-CPU fp32 + cv2), {dt:.1f} s"}
+                                "sample": f"first {args.cpu_sample} frames of the same clip, CPU oracle "
+                                          f"(torch-CPU fp32 + cv2), {dt:.1f} s after a 4-frame warm-up"}
+        # parity on the bench configuration itself: the GPU path over the SAME sample clip vs the oracle run just timed
+        ns = args.cpu_sample
+        glog = []
+        gspans, gbank = PS.prescan_batched(PooledDeviceClip(pool_dev, ns), 24, face, bank, cfg, batch=args.batch, log=glog, single_rank=True)
+        olog = ora["log"]
+        same = len(glog) == len(olog) and all(g["idx"] == o["idx"] and g["skip"] == o["skip"] and g["nfaces"] == o["nfaces"]
+                                              for g, o in zip(glog, olog))
+        dfd = [abs(g["best"] - o["best"]) for g, o in zip(glog, olog) if g["nfaces"] == o["nfaces"] and o["nfaces"] > 0]
+        cosb = [float(np.dot(a, b) / (np.linalg.norm(a) * np.linalg.norm(b))) for a, b in zip(np.asarray(bank), np.asarray(ora["bank0"]))]
+        line["parity"] = {"oracle": "CPU restatement (torch fp32 + cv2), same weights, same frames", "samples": ns,
+                          "decisions_equal": bool(same), "max_abs_dfd": float(max(dfd)) if dfd else None,
+                          "spans_equal": [list(map(int, sp)) for sp in gspans] == [list(map(int, sp)) for sp in ora["spans"]],
+                          "bank_rows_equal": int(np.asarray(gbank).shape[0]) == int(np.asarray(ora["bank"]).shape[0]),
+                          "ref_bank_min_cos": min(cosb) if cosb else None, "tolerance_dfd": 3e-3}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -176,6 +176,38 @@ int pcb_set_bank(pcb_ctx* ctx, const float* bank_host /* [rows][512] */, int row
 int pcb_match(pcb_ctx* ctx, const float* emb_dev, const float* emb_flip_dev, const uint8_t* use_flip_dev,
               int f, float* feat_dev, float* sim_dev, int32_t* argmax_dev);
 
+/* ---- live reference bank (replaces Processor._stream_ref_bank_update, gui_app.py:922-986, for the replay below) ----
+ * Host object: rows are unit fp32 vectors.  pcb_bank_offer applies the reference's streaming rule -- skip a zero vector,
+ * "dup" when max cosine >= dedup, append while rows < cap, else replace the worst row when
+ * s_new > s_worst + margin with s = wa*(1-fd_anchor) + wd*(1-nn_sim) (+ wq*min(max(q,0),1000)/300 for the candidate). */
+typedef struct pcb_bank pcb_bank;
+typedef struct pcb_bank_cfg {
+  int32_t cap;                 /* prescan_bank_max */
+  double dedup, margin;        /* prescan_diversity_dedup_cos, prescan_replace_margin */
+  double wa, wd, wq;           /* prescan_weights */
+} pcb_bank_cfg;
+enum { PCB_BANK_SKIP = 0, PCB_BANK_ADDED = 1, PCB_BANK_DUP = 2, PCB_BANK_REPLACED = 3 };
+pcb_bank* pcb_bank_create(const pcb_bank_cfg* cfg, const float* rows_host /* [n][512] unit rows or NULL */, int n);
+void pcb_bank_destroy(pcb_bank* b);
+/* -> PCB_BANK_*; *slot_out (may be NULL) = the row that was written for ADDED / REPLACED */
+int pcb_bank_offer(pcb_bank* b, const float* vec /* [512], any norm */, double quality, int32_t* slot_out);
+int pcb_bank_rows(const pcb_bank* b);
+long long pcb_bank_version(const pcb_bank* b);      /* number of ADDED + REPLACED so far */
+const float* pcb_bank_data(const pcb_bank* b);      /* [rows][512], valid until the next offer */
+
+/* ---- live distances: the cosine of every face-table row to the live bank, kept current on the GPU while the replay
+ *      changes the bank (the per-face Processor._fd_min calls of gui_app.py:1512-1549, batched).  Arithmetic per
+ *      (row, bank row) pair is pcb_match's, so distances equal what pcb_match returns for the same bank. ---- */
+/* feats_dev: [rows][512] unit features (pcb_match's feat output); copied in normalised form, so the caller may free it. */
+int pcb_live_begin(pcb_ctx* ctx, const float* feats_dev, int rows);
+/* Brings sim[r] = max_j bank_j . feat_r up to date for r >= row_lo of each of the `segments` equal parts of the table
+ * (the replay keeps [plain; flip] halves and only ever needs rows of samples it has not passed yet) and copies them to
+ * the host: synchronous.  changed_slot >= 0: only that bank row differs from the previous call (one dot product per
+ * face row; rows whose argmax was that slot are recomputed in full); -1: the whole bank is new.
+ * *sim_host_out: pinned [rows] float, entries outside the refreshed range are stale.  Empty bank: sim = -8 (fd 9.0). */
+int pcb_live_refresh(pcb_ctx* ctx, const float* bank_host, int bank_rows, int changed_slot, int row_lo, int segments,
+                     const float** sim_host_out);
+
 /* ---- host replay of the pre-scan state machine (replaces the per-sample body of Processor._prescan,
  *      gui_app.py:1468-1655, for samples whose detections / features were precomputed in batches) -------- */
 #define PCB_REPLAY_META 10
@@ -190,15 +222,31 @@ typedef struct pcb_replay_state {      /* FaceEmbedder counters the reference ad
   int64_t frame_idx, last_face_idx;
   int32_t no_face_streak, rot_cycle, prescan_rr, trk_active;
 } pcb_replay_state;
-/* offer: a face qualifies for the bank (gui_app.py:1519-1549); returns 1 if the bank changed (the callee has then
- * rewritten fd_plain / fd_flip in place).  need_flip: flip-TTA features of sample s are missing (callee fills them). */
-typedef int (*pcb_replay_offer_cb)(void* user, int sample, int row, double quality, int active);
+/* refresh: the bank changed (changed_slot >= 0: that row only; -1: everything, e.g. after new flip features) -- the callee
+ * rewrites fd_plain / fd_flip for rows >= row_lo in place.  Used when ctx is NULL (CPU tests, custom matchers); with a
+ * context the library refreshes through pcb_live_refresh itself and the callback may be NULL.
+ * need_flip: flip-TTA features of sample s (and a look-ahead the callee chooses) are missing; the callee computes them,
+ * sets flip_ready and the host features, and -- with a context -- calls pcb_live_begin again.
+ * Both return 0 on success; a negative value aborts the replay (pcb_replay then returns PCB_REPLAY_ABORTED = 5). */
+typedef int (*pcb_replay_refresh_cb)(void* user, const float* bank_rows, int n_rows, int changed_slot, int row_lo);
 typedef int (*pcb_replay_flip_cb)(void* user, int sample);
-int pcb_replay(const pcb_replay_cfg* cfg, const int32_t* meta, const int64_t* frame_idx, int n_samples,
-               const double* quality, const int64_t* area, const uint8_t* flip_ready /* NULL: all present */,
-               const double* fd_plain, const double* fd_flip, pcb_replay_state* st, pcb_replay_offer_cb offer,
-               pcb_replay_flip_cb need_flip, void* user, double* best_out, uint8_t* skip_out, uint8_t* active_out,
-               int32_t* nfaces_out, int64_t* spans_out /* [max_spans][2] */, int max_spans, int32_t* n_spans_out);
+#define PCB_REPLAY_ABORTED 5
+typedef struct pcb_replay_io {
+  const int32_t* meta; const int64_t* frame_idx; int32_t n_samples;
+  int32_t n_rows;                          /* face-table rows */
+  const double* quality; const int64_t* area;
+  const uint8_t* flip_ready;               /* [n_rows] or NULL: all flip features present */
+  const float* feat_plain; const float* feat_flip;   /* host [n_rows][512]: what a bank offer appends (flip while a span is active) */
+  double* fd_plain; double* fd_flip;       /* [n_rows] host distances, kept current by the refresh */
+  pcb_replay_refresh_cb refresh; pcb_replay_flip_cb need_flip; void* user;
+  /* outputs */
+  double* best_out; uint8_t* skip_out; uint8_t* active_out; int32_t* nfaces_out;
+  int64_t* spans_out; int32_t max_spans; int32_t* n_spans_out;
+  int64_t* refreshes_out;                  /* may be NULL: distance refreshes performed */
+} pcb_replay_io;
+/* ctx may be NULL (no GPU: distances come from io->refresh).  With ctx, pcb_live_begin must have been called on the
+ * [plain; flip] table (2 * n_rows rows) and fd_plain / fd_flip are filled by the library before the first sample. */
+int pcb_replay(pcb_ctx* ctx, const pcb_replay_cfg* cfg, pcb_bank* bank, const pcb_replay_io* io, pcb_replay_state* st);
 
 #ifdef __cplusplus
 }

@@ -30,6 +30,8 @@ EXPORTS = (
     "pcb_create", "pcb_destroy", "pcb_last_error", "pcb_sync", "pcb_layout_pad", "pcb_set_conv_impl", "pcb_launch_count",
     "pcb_reset_launch_count", "pcb_set_profile", "pcb_profile_read", "pcb_model_load", "pcb_model_get_tensor", "pcb_resize_area", "pcb_resize_linear", "pcb_resize_factor",
     "pcb_detect", "pcb_letterbox", "pcb_decode_nms", "pcb_align", "pcb_embed", "pcb_set_bank", "pcb_match", "pcb_replay",
+    "pcb_bank_create", "pcb_bank_destroy", "pcb_bank_offer", "pcb_bank_rows", "pcb_bank_version", "pcb_bank_data",
+    "pcb_live_begin", "pcb_live_refresh",
 )
 
 
@@ -75,8 +77,26 @@ class ReplayState(C.Structure):
                 ("rot_cycle", C.c_int32), ("prescan_rr", C.c_int32), ("trk_active", C.c_int32)]
 
 
-REPLAY_OFFER_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_int)
+REPLAY_REFRESH_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int)
 REPLAY_FLIP_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int)
+REPLAY_ABORTED = 5
+BANK_SKIP, BANK_ADDED, BANK_DUP, BANK_REPLACED = 0, 1, 2, 3
+BANK_ACTIONS = ("skip", "added", "dup", "replaced")
+
+
+class BankCfg(C.Structure):
+    _fields_ = [("cap", C.c_int32), ("dedup", C.c_double), ("margin", C.c_double), ("wa", C.c_double), ("wd", C.c_double),
+                ("wq", C.c_double)]
+
+
+class ReplayIO(C.Structure):
+    _fields_ = [("meta", C.c_void_p), ("frame_idx", C.c_void_p), ("n_samples", C.c_int32), ("n_rows", C.c_int32),
+                ("quality", C.c_void_p), ("area", C.c_void_p), ("flip_ready", C.c_void_p),
+                ("feat_plain", C.c_void_p), ("feat_flip", C.c_void_p), ("fd_plain", C.c_void_p), ("fd_flip", C.c_void_p),
+                ("refresh", REPLAY_REFRESH_CB), ("need_flip", REPLAY_FLIP_CB), ("user", C.c_void_p),
+                ("best_out", C.c_void_p), ("skip_out", C.c_void_p), ("active_out", C.c_void_p), ("nfaces_out", C.c_void_p),
+                ("spans_out", C.c_void_p), ("max_spans", C.c_int32), ("n_spans_out", C.POINTER(C.c_int32)),
+                ("refreshes_out", C.POINTER(C.c_int64))]
 
 
 class PcbError(RuntimeError):
@@ -123,8 +143,19 @@ def load():
     lib.pcb_embed.argtypes = [vp, vp, i32, vp, vp]
     lib.pcb_set_bank.argtypes = [vp, vp, i32]
     lib.pcb_match.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp]
-    lib.pcb_replay.argtypes = [C.POINTER(ReplayCfg), vp, vp, i32, vp, vp, vp, vp, vp, C.POINTER(ReplayState), REPLAY_OFFER_CB,
-                               REPLAY_FLIP_CB, vp, vp, vp, vp, vp, vp, i32, C.POINTER(C.c_int32)]
+    lib.pcb_replay.argtypes = [vp, C.POINTER(ReplayCfg), vp, C.POINTER(ReplayIO), C.POINTER(ReplayState)]
+    lib.pcb_bank_create.restype = vp
+    lib.pcb_bank_create.argtypes = [C.POINTER(BankCfg), vp, i32]
+    lib.pcb_bank_destroy.restype = None
+    lib.pcb_bank_destroy.argtypes = [vp]
+    lib.pcb_bank_offer.argtypes = [vp, vp, C.c_double, C.POINTER(C.c_int32)]
+    lib.pcb_bank_rows.argtypes = [vp]
+    lib.pcb_bank_version.restype = C.c_longlong
+    lib.pcb_bank_version.argtypes = [vp]
+    lib.pcb_bank_data.restype = C.POINTER(C.c_float)
+    lib.pcb_bank_data.argtypes = [vp]
+    lib.pcb_live_begin.argtypes = [vp, vp, i32]
+    lib.pcb_live_refresh.argtypes = [vp, vp, i32, i32, i32, i32, C.POINTER(C.POINTER(C.c_float))]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int:

@@ -265,18 +265,21 @@ __global__ void __launch_bounds__(256) chip_kernel(const RenderParams p) {
 
 extern "C" int pcb_align(pcb_ctx* c, const pcb_align_args* a) {
   if (!a || a->n <= 0 || a->max_det <= 0 || a->max_faces <= 0) return pcb_fail(c, PCB_ERR_ARG, "align: bad arguments");
-  // context-owned scratch: kept_idx [n][max_det], face_off [n], plans [max_faces], roll allocator + buffer
-  static std::map<pcb_ctx*, std::vector<size_t>> sizes;
-  static std::map<pcb_ctx*, std::vector<void*>> bufs;
-  auto& sz = sizes[c];
-  auto& bf = bufs[c];
+  PCB_ENTER(c);
+  // context-owned scratch (freed with the context): kept_idx [n][max_det], face_off [n], plans [max_faces], roll allocator + buffer
+  size_t* sz = c->align_sz;
+  void** bf = c->align_buf;
   const size_t want[4] = {(size_t)a->n * a->max_det * sizeof(int), (size_t)a->n * sizeof(int), (size_t)a->max_faces * sizeof(FacePlan),
                           (size_t)256 << 20};
-  if (sz.empty()) { sz.assign(5, 0); bf.assign(5, nullptr); }
   for (int i = 0; i < 4; ++i) {
     if (sz[i] < want[i]) {
-      bf[i] = pcb_dev_alloc(c, want[i], false);
-      if (!bf[i]) return pcb_fail(c, PCB_ERR_CUDA, "align: scratch alloc failed");
+      void* nb = pcb_dev_alloc(c, want[i], false);
+      if (!nb) return pcb_fail(c, PCB_ERR_CUDA, "align: scratch alloc failed");
+      if (bf[i]) {                        // kernels of earlier calls may still read the old buffer
+        PCB_CUDA(c, cudaStreamSynchronize(c->stream));
+        pcb_dev_free(c, bf[i]);
+      }
+      bf[i] = nb;
       sz[i] = want[i];
     }
   }

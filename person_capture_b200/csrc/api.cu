@@ -89,6 +89,8 @@ extern "C" void pcb_destroy(pcb_ctx* c) {
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
   if (c->h_err) cudaFreeHost(c->h_err);
   if (c->bank_stage) cudaFreeHost(c->bank_stage);
+  if (c->live_sim_host) cudaFreeHost(c->live_sim_host);
+  if (c->live_row_stage) cudaFreeHost(c->live_row_stage);
   if (c->bank_ev) cudaEventDestroy(c->bank_ev);
   for (int i = 0; i < 4; ++i) delete c->models[i];
   if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -98,6 +100,7 @@ extern "C" void pcb_destroy(pcb_ctx* c) {
 extern "C" const char* pcb_last_error(pcb_ctx* c) { return c ? c->last_error.c_str() : "null context"; }
 
 extern "C" int pcb_sync(pcb_ctx* c) {
+  PCB_ENTER(c);
   PCB_CUDA(c, cudaMemcpyAsync(c->h_err, c->d_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   PCB_CUDA(c, cudaStreamSynchronize(c->stream));
   if (*c->h_err != 0) {
@@ -153,6 +156,7 @@ extern "C" int pcb_set_profile(pcb_ctx* c, int on) {
 
 // Folds all recorded conv launches into the running totals and returns them (synchronises).
 extern "C" int pcb_profile_read(pcb_ctx* c, double* conv_ms, double* conv_flops, long long* conv_launches, int reset) {
+  PCB_ENTER(c);
   PCB_CUDA(c, cudaStreamSynchronize(c->stream));
   FILE* dump = nullptr;
   if (const char* path = getenv("PCB_PROFILE_DUMP")) dump = fopen(path, "a");
@@ -194,8 +198,8 @@ static float* upload_f32_padded(pcb_ctx* c, const float* src, int n, int npad, f
 
 extern "C" int pcb_model_load(pcb_ctx* c, int slot, const pcb_op* ops, int n_ops, int n_tensors, const void* blob_host,
                               size_t blob_bytes, const int32_t* outputs, int n_outputs, const float* reg_scale3) {
+  PCB_ENTER(c);
   if (slot < 0 || slot >= 4 || !ops || n_ops <= 0 || !blob_host) return pcb_fail(c, PCB_ERR_ARG, "model_load: bad arguments");
-  PCB_CUDA(c, cudaSetDevice(c->device));
   Model* m = new Model();
   m->ops.assign(ops, ops + n_ops);
   m->conv.resize(n_ops);
@@ -262,7 +266,18 @@ extern "C" int pcb_model_load(pcb_ctx* c, int slot, const pcb_op* ops, int n_ops
       if (!m->aff_scale[i] || !m->aff_bias[i]) { delete m; return pcb_fail(c, PCB_ERR_CUDA, "model_load: param upload failed"); }
     }
   }
-  delete c->models[slot];
+  if (Model* old = c->models[slot]) {
+    // the replaced graph's weights, vectors and activation sets go back to the device now, not at pcb_destroy
+    PCB_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (auto& w : old->conv) { pcb_dev_free(c, w.w); pcb_dev_free(c, w.scale); pcb_dev_free(c, w.bias); pcb_dev_free(c, w.slope); }
+    for (float* q : old->aff_scale) pcb_dev_free(c, q);
+    for (float* q : old->aff_bias) pcb_dev_free(c, q);
+    for (auto& kv : old->runs) {
+      for (auto& t : kv.second.t) pcb_dev_free(c, t.data);
+      pcb_dev_free(c, kv.second.fc_out);
+    }
+    delete old;
+  }
   c->models[slot] = m;
   return PCB_OK;
 }
@@ -275,7 +290,7 @@ static int alloc_tensor(pcb_ctx* c, PTensor& t) {
   return t.data ? PCB_OK : pcb_fail(c, PCB_ERR_CUDA, "activation alloc failed (batch too large for HBM?)");
 }
 
-static void pcb_dev_free(pcb_ctx* c, void* p) {
+void pcb_dev_free(pcb_ctx* c, void* p) {
   if (!p) return;
   for (size_t i = 0; i < c->allocs.size(); ++i)
     if (c->allocs[i] == p) { c->allocs.erase(c->allocs.begin() + i); break; }
@@ -422,6 +437,7 @@ __global__ void gather_nchw_kernel(const __half* __restrict__ in, float* __restr
 }
 
 extern "C" int pcb_model_get_tensor(pcb_ctx* c, int slot, int tid, float* out_host, int* n, int* ch, int* h, int* w) {
+  PCB_ENTER(c);
   if (slot < 0 || slot >= 4 || !c->models[slot] || !c->models[slot]->last) return pcb_fail(c, PCB_ERR_STATE, "get_tensor: model has not run");
   Model::Run* r = c->models[slot]->last;
   if (tid < 0 || tid >= (int)r->t.size() || !r->t[tid].data) return pcb_fail(c, PCB_ERR_ARG, "get_tensor: bad tensor id");
@@ -448,15 +464,18 @@ extern "C" int pcb_model_get_tensor(pcb_ctx* c, int slot, int tid, float* out_ho
 // ---------------------------------------------------------------------------------------
 extern "C" int pcb_letterbox(pcb_ctx* c, const uint8_t* frames_dev, int n, int h, int w, int S, int rot_deg, int pad_replicate,
                              void* out_dev, uint8_t* det_img_dev) {
+  PCB_ENTER(c);
   return pcb_letterbox_impl(c, frames_dev, n, h, w, S, rot_deg, pad_replicate, (__half*)out_dev, det_img_dev, nullptr);
 }
 
 extern "C" int pcb_decode_nms(pcb_ctx* c, const void* h8, const void* h16, const void* h32, const float* reg_scale3_host,
                               const pcb_detect_args* a, float det_scale) {
+  PCB_ENTER(c);
   return pcb_decode_nms_impl(c, (const float*)h8, (const float*)h16, (const float*)h32, reg_scale3_host, a, det_scale);
 }
 
 extern "C" int pcb_detect(pcb_ctx* c, const pcb_detect_args* a) {
+  PCB_ENTER(c);
   if (!a || !a->frames_dev || a->n <= 0) return pcb_fail(c, PCB_ERR_ARG, "detect: bad arguments");
   Model* m = c->models[PCB_MODEL_SCRFD];
   if (!m) return pcb_fail(c, PCB_ERR_STATE, "detect: no SCRFD graph loaded");
@@ -478,6 +497,7 @@ extern "C" int pcb_detect(pcb_ctx* c, const pcb_detect_args* a) {
 }
 
 extern "C" int pcb_embed(pcb_ctx* c, const uint8_t* chips_dev, int f, float* emb_dev, float* emb_flip_dev) {
+  PCB_ENTER(c);
   if (f < 0 || (f > 0 && (!chips_dev || (!emb_dev && !emb_flip_dev)))) return pcb_fail(c, PCB_ERR_ARG, "embed: bad arguments");
   Model* m = c->models[PCB_MODEL_ARCFACE];
   if (!m) return pcb_fail(c, PCB_ERR_STATE, "embed: no ArcFace graph loaded");

@@ -462,11 +462,9 @@ int pcb_conv_tc(pcb_ctx* c, const ConvArgs& a) {
   if (!make_map_2d(&tmB, w.w, (uint64_t)w.npad, (uint64_t)w.taps * w.cin_w, (uint64_t)w.taps * w.cin_w, (uint32_t)w.n_tile))
     return pcb_fail(c, PCB_ERR_CUDA, "cuTensorMapEncodeTiled(B) failed");
 
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_devs = 0;     // the opt-in is per device
+  if (pcb_attr_needed(&attr_devs, c->device))
     PCB_CUDA(c, cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
   const int total = p.m_tiles * p.n_tiles;
   const int grid = total < c->num_sms ? total : c->num_sms;
   // algorithmic FLOPs of this layer: 2 * output pixels * cout * cin * taps (real, unpadded extents)

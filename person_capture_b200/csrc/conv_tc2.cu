@@ -1366,7 +1366,7 @@ int pcb_conv_tc2(pcb_ctx* c, const ConvArgs& a) {
              (a.out && a.out->f32) ? 1 : 0, a.out2 ? 1 : 0, p.a_stages, p.b_stages, p.b_resident, p.strided ? p.s_nb : 0,
              p.strided ? p.s_by : 0, p.strided ? p.s_bx : 0, p.pair, p.n_iss + p.split_n * 10);
   static const int debug = env_int("PCB_CONV_DEBUG", 0);
-  static unsigned long long* dbg_dev = nullptr;
+  static unsigned long long* dbg_dev = nullptr;    // debug builds of the stall counters assume one context
   if (debug && c->profile) {
     if (!dbg_dev) dbg_dev = (unsigned long long*)pcb_dev_alloc(c, 16 * sizeof(unsigned long long), true);
     p.dbg = dbg_dev;
@@ -1379,11 +1379,9 @@ int pcb_conv_tc2(pcb_ctx* c, const ConvArgs& a) {
     cudaError_t le = cudaErrorInvalidValue;
 #define PCB_TC2_LAUNCH(ACT, RES, OUT2, MODE, VAR)                                                                       \
   {                                                                                                                    \
-    static bool attr = false;                                                                                          \
-    if (!attr) {                                                                                                       \
+    static unsigned long long attr_devs = 0; /* the opt-in is per device */                                            \
+    if (pcb_attr_needed(&attr_devs, c->device))                                                                        \
       cudaFuncSetAttribute(conv_tc2_kernel<ACT, RES, OUT2, MODE, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
-      attr = true;                                                                                                     \
-    }                                                                                                                  \
     if (VAR == kVarPair) {                                                                                             \
       cudaLaunchConfig_t cfg = {};                                                                                     \
       cfg.gridDim = dim3(grid);                                                                                        \

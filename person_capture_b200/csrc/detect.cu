@@ -260,7 +260,11 @@ static int ensure_scratch(pcb_ctx* c, size_t bytes) {
   if (c->scratch_bytes >= bytes) return PCB_OK;
   void* p = pcb_dev_alloc(c, bytes, false);
   if (!p) return pcb_fail(c, PCB_ERR_CUDA, "scratch alloc failed");
-  c->scratch = p;   // the old block stays owned by the context until destroy
+  if (c->scratch) {
+    cudaStreamSynchronize(c->stream);
+    pcb_dev_free(c, c->scratch);
+  }
+  c->scratch = p;
   c->scratch_bytes = bytes;
   return PCB_OK;
 }
@@ -298,11 +302,9 @@ int pcb_decode_nms_impl(pcb_ctx* c, const float* h8, const float* h16, const flo
   np.acc_box = a->acc_box_dev; np.acc_kps = a->acc_kps_dev; np.acc_score = a->acc_score_dev; np.acc_count = a->acc_count_dev; np.acc_unfiltered = a->acc_unfiltered_dev;
   np.err = c->d_err;
   const size_t nms_smem_bytes = (size_t)kCandCap * (8 + 2 + 1) + 1024 * 4;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_devs = 0;     // the opt-in is per device
+  if (pcb_attr_needed(&attr_devs, c->device))
     PCB_CUDA(c, cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nms_smem_bytes));
-    attr_set = true;
-  }
   nms_kernel<<<a->n, 256, nms_smem_bytes, c->stream>>>(np);
   PCB_LAUNCH_CHECK(c, "nms_kernel");
   return PCB_OK;

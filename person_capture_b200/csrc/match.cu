@@ -1,13 +1,19 @@
-// K5: fused (sum flip pair) + L2-normalise + bank cosine + max/argmax.
+// K5: fused (sum flip pair) + L2-normalise + bank cosine + max/argmax, and the live distance table of the pre-scan replay.
 // Replaces person_capture/face_embedder.py:1383-1389 (f = e(x) [+ e(flip x)]; f /= max(|f|, 1e-6))
 // and Processor._fd_min, person_capture/gui_app.py:660-674 (vec / max(|vec|, 1e-6); 1 - max(bank @ vec)).
 // HBM/L2-bound on the bank read (B*512*4 bytes per face block); no tensor cores: 2*F*B*512 FLOP
 // is negligible next to the convolutions.
+//
+// One arithmetic for every path: a (face row, bank row) cosine is always computed by ONE warp with `row_dot` below
+// (explicit fma chain per lane, xor-butterfly sum), so pcb_match, the full live refresh and the one-row incremental
+// refresh give bit-identical similarities -- max(old, dot(new row)) IS the full recomputation.
 #include <string.h>
 
 #include "pcb_common.cuh"
 
 namespace {
+
+constexpr int kD = PCB_FEAT_DIM;
 
 __device__ __forceinline__ float block_sum(float v, float* red) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -19,51 +25,49 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
   return t;
 }
 
-__global__ void __launch_bounds__(256) match_kernel(const float* __restrict__ emb, const float* __restrict__ emb_flip,
-                                                    const uint8_t* __restrict__ use_flip, int f, const float* __restrict__ bank,
-                                                    int rows, float* __restrict__ feat_out, float* __restrict__ sim_out,
-                                                    int* __restrict__ arg_out) {
-  __shared__ __align__(16) float v[PCB_FEAT_DIM];
-  __shared__ float red[8];
-  __shared__ float wmax[8];
-  __shared__ int warg[8];
-  const int face = blockIdx.x;
-  if (face >= f) return;
-  const bool fl = emb_flip != nullptr && (use_flip == nullptr || use_flip[face] != 0);
-  float x0 = emb[(size_t)face * PCB_FEAT_DIM + threadIdx.x];
-  float x1 = emb[(size_t)face * PCB_FEAT_DIM + 256 + threadIdx.x];
-  if (fl) {
-    x0 += emb_flip[(size_t)face * PCB_FEAT_DIM + threadIdx.x];
-    x1 += emb_flip[(size_t)face * PCB_FEAT_DIM + 256 + threadIdx.x];
+// cosine of one bank row and one (normalised) face row: lane l owns elements 4*(l + 32*j) .. +3, j = 0..3
+__device__ __forceinline__ float row_dot(const float4* __restrict__ b4, const float4* v4, int lane) {
+  float acc = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float4 a = __ldg(b4 + lane + 32 * j);
+    const float4 q = v4[lane + 32 * j];
+    acc = __fmaf_rn(a.x, q.x, acc);
+    acc = __fmaf_rn(a.y, q.y, acc);
+    acc = __fmaf_rn(a.z, q.z, acc);
+    acc = __fmaf_rn(a.w, q.w, acc);
   }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  return acc;
+}
+
+// 256 threads: x0/x1 are this thread's two elements of the face vector.  Normalises as the reference does twice
+// (_arcface_encode, then _fd_min on the already-unit feature) and leaves the result in v[512] (shared).
+__device__ __forceinline__ void normalise_twice(float x0, float x1, float* v, float* red, float* feat_out_row) {
   float nrm = sqrtf(block_sum(x0 * x0 + x1 * x1, red));
   nrm = fmaxf(nrm, 1e-6f);
   x0 /= nrm; x1 /= nrm;
-  if (feat_out) {
-    feat_out[(size_t)face * PCB_FEAT_DIM + threadIdx.x] = x0;
-    feat_out[(size_t)face * PCB_FEAT_DIM + 256 + threadIdx.x] = x1;
+  if (feat_out_row) {
+    feat_out_row[threadIdx.x] = x0;
+    feat_out_row[256 + threadIdx.x] = x1;
   }
-  // _fd_min renormalises the (already unit) feature
   float n2 = sqrtf(block_sum(x0 * x0 + x1 * x1, red));
   n2 = fmaxf(n2, 1e-6f);
   v[threadIdx.x] = x0 / n2;
   v[256 + threadIdx.x] = x1 / n2;
   __syncthreads();
+}
+
+// best bank row for the face vector in shared memory: 8 warps take rows r = warp, warp + 8, ...; first occurrence wins
+__device__ __forceinline__ void bank_scan(const float* v, const float* __restrict__ bank, int rows, float* wmax, int* warg,
+                                          float* sim_out, int* arg_out) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float best = -3.0e38f;
   int barg = -1;
   const float4* v4 = (const float4*)v;
   for (int r = warp; r < rows; r += 8) {
-    const float4* b4 = (const float4*)(bank + (size_t)r * PCB_FEAT_DIM);
-    float acc = 0.f;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float4 a = __ldg(b4 + lane + 32 * j);
-      const float4 q = v4[lane + 32 * j];
-      acc += a.x * q.x + a.y * q.y + a.z * q.z + a.w * q.w;
-    }
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (acc > best) { best = acc; barg = r; }   // first occurrence wins within a warp (rows ascending)
+    const float acc = row_dot((const float4*)(bank + (size_t)r * kD), v4, lane);
+    if (acc > best) { best = acc; barg = r; }   // rows ascending within a warp
   }
   if (lane == 0) { wmax[warp] = best; warg[warp] = barg; }
   __syncthreads();
@@ -73,44 +77,204 @@ __global__ void __launch_bounds__(256) match_kernel(const float* __restrict__ em
     for (int i = 0; i < 8; ++i)
       if (warg[i] >= 0 && (wmax[i] > m || (wmax[i] == m && warg[i] < a))) { m = wmax[i]; a = warg[i]; }
     // empty bank: sim = -8 so that fd = 1 - sim = 9.0, the reference's sentinel (gui_app.py:662-673)
-    sim_out[face] = a >= 0 ? m : -8.0f;
-    if (arg_out) arg_out[face] = a;
+    *sim_out = a >= 0 ? m : -8.0f;
+    if (arg_out) *arg_out = a;
   }
+}
+
+__global__ void __launch_bounds__(256) match_kernel(const float* __restrict__ emb, const float* __restrict__ emb_flip,
+                                                    const uint8_t* __restrict__ use_flip, int f, const float* __restrict__ bank,
+                                                    int rows, float* __restrict__ feat_out, float* __restrict__ sim_out,
+                                                    int* __restrict__ arg_out) {
+  __shared__ __align__(16) float v[kD];
+  __shared__ float red[8];
+  __shared__ float wmax[8];
+  __shared__ int warg[8];
+  const int face = blockIdx.x;
+  if (face >= f) return;
+  const bool fl = emb_flip != nullptr && (use_flip == nullptr || use_flip[face] != 0);
+  float x0 = emb[(size_t)face * kD + threadIdx.x];
+  float x1 = emb[(size_t)face * kD + 256 + threadIdx.x];
+  if (fl) {
+    x0 += emb_flip[(size_t)face * kD + threadIdx.x];
+    x1 += emb_flip[(size_t)face * kD + 256 + threadIdx.x];
+  }
+  normalise_twice(x0, x1, v, red, feat_out ? feat_out + (size_t)face * kD : nullptr);
+  bank_scan(v, bank, rows, wmax, warg, sim_out + face, arg_out ? arg_out + face : nullptr);
+}
+
+// live table: V[r] = the vector match_kernel would hold in shared memory for feature row r
+__global__ void __launch_bounds__(256) live_prepare_kernel(const float* __restrict__ feats, float* __restrict__ V, int rows) {
+  __shared__ __align__(16) float v[kD];
+  __shared__ float red[8];
+  const int r = blockIdx.x;
+  if (r >= rows) return;
+  normalise_twice(feats[(size_t)r * kD + threadIdx.x], feats[(size_t)r * kD + 256 + threadIdx.x], v, red, nullptr);
+  V[(size_t)r * kD + threadIdx.x] = v[threadIdx.x];
+  V[(size_t)r * kD + 256 + threadIdx.x] = v[256 + threadIdx.x];
+}
+
+// rows [row_lo, seg) of each of `segments` parts of V; block b handles row index b of that compacted range
+__device__ __forceinline__ int live_row(int b, int row_lo, int seg) {
+  const int per = seg - row_lo;
+  return (b / per) * seg + row_lo + (b % per);
+}
+
+__global__ void __launch_bounds__(256) live_full_kernel(const float* __restrict__ V, const float* __restrict__ bank, int bank_rows,
+                                                        int row_lo, int seg, float* __restrict__ sim, int* __restrict__ arg) {
+  __shared__ __align__(16) float v[kD];
+  __shared__ float wmax[8];
+  __shared__ int warg[8];
+  const int r = live_row(blockIdx.x, row_lo, seg);
+  v[threadIdx.x] = V[(size_t)r * kD + threadIdx.x];
+  v[256 + threadIdx.x] = V[(size_t)r * kD + 256 + threadIdx.x];
+  __syncthreads();
+  bank_scan(v, bank, bank_rows, wmax, warg, sim + r, arg + r);
+}
+
+// one bank row (slot k) changed: sim = max(sim, dot(row k)) -- unless k WAS the argmax (replaced row), then rescan.
+// One warp per face row.
+__global__ void __launch_bounds__(256) live_update_kernel(const float* __restrict__ V, const float* __restrict__ bank, int bank_rows,
+                                                          int k, int row_lo, int seg, int n_work, float* __restrict__ sim,
+                                                          int* __restrict__ arg) {
+  const int w = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (w >= n_work) return;
+  const int r = live_row(w, row_lo, seg);
+  const float4* v4 = (const float4*)(V + (size_t)r * kD);
+  const int a0 = arg[r];
+  float m;
+  int a;
+  if (a0 == k || a0 < 0) {
+    m = -3.0e38f;
+    a = -1;
+    for (int j = 0; j < bank_rows; ++j) {
+      const float d = row_dot((const float4*)(bank + (size_t)j * kD), v4, lane);
+      if (d > m) { m = d; a = j; }
+    }
+  } else {
+    m = sim[r];
+    a = a0;
+    const float d = row_dot((const float4*)(bank + (size_t)k * kD), v4, lane);
+    if (d > m || (d == m && k < a)) { m = d; a = k; }
+  }
+  if (lane == 0) {
+    sim[r] = a >= 0 ? m : -8.0f;
+    arg[r] = a;
+  }
+}
+
+// device bank with room for `rows` rows (geometric growth; the old buffer is released once the stream has drained)
+int bank_reserve(pcb_ctx* c, int rows) {
+  if (rows <= c->bank_cap) return PCB_OK;
+  int cap = c->bank_cap < 64 ? 64 : c->bank_cap;
+  while (cap < rows) cap *= 2;
+  float* nb = (float*)pcb_dev_alloc(c, (size_t)cap * kD * sizeof(float), false);
+  if (!nb) return pcb_fail(c, PCB_ERR_CUDA, "set_bank: alloc failed");
+  PCB_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (c->bank_rows > 0 && c->bank)
+    PCB_CUDA(c, cudaMemcpyAsync(nb, c->bank, (size_t)c->bank_rows * kD * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+  PCB_CUDA(c, cudaStreamSynchronize(c->stream));
+  pcb_dev_free(c, c->bank);
+  if (c->bank_stage) cudaFreeHost(c->bank_stage);
+  c->bank_stage = nullptr;
+  PCB_CUDA(c, cudaMallocHost((void**)&c->bank_stage, (size_t)cap * kD * sizeof(float)));
+  if (!c->bank_ev) PCB_CUDA(c, cudaEventCreateWithFlags(&c->bank_ev, cudaEventDisableTiming));
+  c->bank = nb;
+  c->bank_cap = cap;
+  return PCB_OK;
 }
 
 }  // namespace
 
 extern "C" int pcb_set_bank(pcb_ctx* c, const float* bank_host, int rows) {
+  PCB_ENTER(c);
   if (rows < 0 || (rows > 0 && !bank_host)) return pcb_fail(c, PCB_ERR_ARG, "set_bank: bad arguments");
-  if (rows > c->bank_cap) {
-    int cap = rows < 64 ? 64 : rows;
-    float* nb = (float*)pcb_dev_alloc(c, (size_t)cap * PCB_FEAT_DIM * sizeof(float), false);
-    if (!nb) return pcb_fail(c, PCB_ERR_CUDA, "set_bank: alloc failed");
-    if (c->bank_ev) PCB_CUDA(c, cudaEventSynchronize(c->bank_ev));
-    if (c->bank_stage) cudaFreeHost(c->bank_stage);
-    c->bank_stage = nullptr;
-    PCB_CUDA(c, cudaMallocHost((void**)&c->bank_stage, (size_t)cap * PCB_FEAT_DIM * sizeof(float)));
-    if (!c->bank_ev) PCB_CUDA(c, cudaEventCreateWithFlags(&c->bank_ev, cudaEventDisableTiming));
-    c->bank = nb;
-    c->bank_cap = cap;
-  }
+  int rc = bank_reserve(c, rows);
+  if (rc) return rc;
   if (rows > 0) {
-    // the live bank changes every few samples during a replay: stage through pinned memory so the upload is asynchronous
-    // (the caller may reuse its buffer immediately) and only wait for the PREVIOUS upload before overwriting the stage
+    // stage through pinned memory so the upload is asynchronous (the caller may reuse its buffer immediately); only
+    // the PREVIOUS upload is waited for before the stage is overwritten
     PCB_CUDA(c, cudaEventSynchronize(c->bank_ev));
-    memcpy(c->bank_stage, bank_host, (size_t)rows * PCB_FEAT_DIM * sizeof(float));
-    PCB_CUDA(c, cudaMemcpyAsync(c->bank, c->bank_stage, (size_t)rows * PCB_FEAT_DIM * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    memcpy(c->bank_stage, bank_host, (size_t)rows * kD * sizeof(float));
+    PCB_CUDA(c, cudaMemcpyAsync(c->bank, c->bank_stage, (size_t)rows * kD * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     PCB_CUDA(c, cudaEventRecord(c->bank_ev, c->stream));
   }
   c->bank_rows = rows;
+  c->live_bank_rows = -1;      // the live table's similarities no longer describe the device bank
   return PCB_OK;
 }
 
 extern "C" int pcb_match(pcb_ctx* c, const float* emb_dev, const float* emb_flip_dev, const uint8_t* use_flip_dev, int f,
                          float* feat_dev, float* sim_dev, int32_t* argmax_dev) {
+  PCB_ENTER(c);
   if (f < 0 || (f > 0 && (!emb_dev || !sim_dev))) return pcb_fail(c, PCB_ERR_ARG, "match: bad arguments");
   if (f == 0) return PCB_OK;
   match_kernel<<<f, 256, 0, c->stream>>>(emb_dev, emb_flip_dev, use_flip_dev, f, c->bank, c->bank_rows, feat_dev, sim_dev, argmax_dev);
   PCB_LAUNCH_CHECK(c, "match_kernel");
+  return PCB_OK;
+}
+
+extern "C" int pcb_live_begin(pcb_ctx* c, const float* feats_dev, int rows) {
+  PCB_ENTER(c);
+  if (rows < 0 || (rows > 0 && !feats_dev)) return pcb_fail(c, PCB_ERR_ARG, "live_begin: bad arguments");
+  if (rows > c->live_cap) {
+    int cap = c->live_cap < 1024 ? 1024 : c->live_cap;
+    while (cap < rows) cap *= 2;
+    PCB_CUDA(c, cudaStreamSynchronize(c->stream));
+    pcb_dev_free(c, c->live_v); pcb_dev_free(c, c->live_sim); pcb_dev_free(c, c->live_arg);
+    if (c->live_sim_host) cudaFreeHost(c->live_sim_host);
+    c->live_sim_host = nullptr;
+    c->live_cap = 0;
+    c->live_v = (float*)pcb_dev_alloc(c, (size_t)cap * kD * sizeof(float), false);
+    c->live_sim = (float*)pcb_dev_alloc(c, (size_t)cap * sizeof(float), false);
+    c->live_arg = (int*)pcb_dev_alloc(c, (size_t)cap * sizeof(int), false);
+    if (!c->live_v || !c->live_sim || !c->live_arg) return pcb_fail(c, PCB_ERR_CUDA, "live_begin: alloc failed");
+    PCB_CUDA(c, cudaMallocHost((void**)&c->live_sim_host, (size_t)cap * sizeof(float)));
+    c->live_cap = cap;
+  }
+  if (!c->live_row_stage) PCB_CUDA(c, cudaMallocHost((void**)&c->live_row_stage, kD * sizeof(float)));
+  c->live_rows = rows;
+  c->live_bank_rows = -1;
+  if (rows > 0) {
+    live_prepare_kernel<<<rows, 256, 0, c->stream>>>(feats_dev, c->live_v, rows);
+    PCB_LAUNCH_CHECK(c, "live_prepare_kernel");
+  }
+  return PCB_OK;
+}
+
+extern "C" int pcb_live_refresh(pcb_ctx* c, const float* bank_host, int bank_rows, int changed_slot, int row_lo, int segments,
+                                const float** sim_host_out) {
+  PCB_ENTER(c);
+  if (bank_rows < 0 || (bank_rows > 0 && !bank_host) || segments < 1 || c->live_rows % segments || changed_slot >= bank_rows)
+    return pcb_fail(c, PCB_ERR_ARG, "live_refresh: bad arguments");
+  if (sim_host_out) *sim_host_out = c->live_sim_host;
+  const int seg = c->live_rows / segments;
+  if (row_lo < 0) row_lo = 0;
+  if (seg == 0 || row_lo >= seg) return PCB_OK;
+  const int n_work = (seg - row_lo) * segments;
+  // the incremental form needs the previous state to describe exactly the bank minus this row
+  const bool incremental = changed_slot >= 0 && c->live_bank_rows >= 0 &&
+                           (c->live_bank_rows == bank_rows || (c->live_bank_rows == bank_rows - 1 && changed_slot == bank_rows - 1));
+  if (incremental) {
+    int rc = bank_reserve(c, bank_rows);
+    if (rc) return rc;
+    // one 2 KB row; the previous refresh ended with a stream synchronisation, so the stage is free
+    memcpy(c->live_row_stage, bank_host + (size_t)changed_slot * kD, kD * sizeof(float));
+    PCB_CUDA(c, cudaMemcpyAsync(c->bank + (size_t)changed_slot * kD, c->live_row_stage, kD * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    c->bank_rows = bank_rows;
+    live_update_kernel<<<(n_work + 7) / 8, 256, 0, c->stream>>>(c->live_v, c->bank, bank_rows, changed_slot, row_lo, seg, n_work,
+                                                                 c->live_sim, c->live_arg);
+    PCB_LAUNCH_CHECK(c, "live_update_kernel");
+  } else {
+    int rc = pcb_set_bank(c, bank_host, bank_rows);
+    if (rc) return rc;
+    live_full_kernel<<<n_work, 256, 0, c->stream>>>(c->live_v, c->bank, bank_rows, row_lo, seg, c->live_sim, c->live_arg);
+    PCB_LAUNCH_CHECK(c, "live_full_kernel");
+  }
+  for (int s = 0; s < segments; ++s)
+    PCB_CUDA(c, cudaMemcpyAsync(c->live_sim_host + (size_t)s * seg + row_lo, c->live_sim + (size_t)s * seg + row_lo,
+                                (size_t)(seg - row_lo) * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  PCB_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->live_bank_rows = bank_rows;
   return PCB_OK;
 }

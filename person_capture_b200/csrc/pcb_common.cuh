@@ -101,6 +101,20 @@ struct pcb_ctx {
   cudaEvent_t bank_ev = nullptr; // completion of the last bank upload
   void* scratch = nullptr;
   size_t scratch_bytes = 0;
+  // per-context scratch that used to live in function-static maps keyed by the context pointer (a recreated context
+  // could inherit freed device pointers): K4 align buffers and the letterbox coefficient tables
+  size_t align_sz[5] = {0, 0, 0, 0, 0};
+  void* align_buf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  std::map<std::vector<int>, std::pair<void*, void*>> lin_tabs;
+  // live distance table of the pre-scan replay (match.cu): normalised face rows, their best cosine / argmax against
+  // the live bank on the device, and the pinned host mirror pcb_live_refresh hands to the replay
+  float* live_v = nullptr;
+  float* live_sim = nullptr;
+  int* live_arg = nullptr;
+  float* live_sim_host = nullptr;
+  float* live_row_stage = nullptr;   // pinned [512]: the one bank row that changed
+  int live_rows = 0, live_cap = 0;
+  int live_bank_rows = 0;            // bank rows the device-side sims are current for (-1: never refreshed)
   // profiling (bench.py roofline): CUDA events around every conv launch + algorithmic FLOPs
   bool profile = false;
   std::vector<cudaEvent_t> ev_pool;
@@ -120,6 +134,21 @@ struct PcbConvTimer {
 };
 
 int pcb_fail(pcb_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess);
+// Every extern "C" entry point that touches the device starts with this: a process may hold contexts on several GPUs
+// (Engine(device=k) is public API) and the calling thread's current device is whatever the last call left behind.
+#define PCB_ENTER(ctx)                                                           \
+  do {                                                                           \
+    if (!(ctx)) return PCB_ERR_ARG;                                              \
+    cudaError_t _e0 = cudaSetDevice((ctx)->device);                              \
+    if (_e0 != cudaSuccess) return pcb_fail((ctx), PCB_ERR_CUDA, "cudaSetDevice", _e0); \
+  } while (0)
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-device setting: remember it per (function, device)
+static inline bool pcb_attr_needed(unsigned long long* mask, int device) {
+  const unsigned long long bit = 1ull << (device & 63);
+  if (*mask & bit) return false;
+  *mask |= bit;
+  return true;
+}
 #define PCB_CUDA(ctx, call)                                                      \
   do {                                                                           \
     cudaError_t _e = (call);                                                     \
@@ -133,6 +162,7 @@ int pcb_fail(pcb_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess
   } while (0)
 
 void* pcb_dev_alloc(pcb_ctx* c, size_t bytes, bool zero);
+void pcb_dev_free(pcb_ctx* c, void* p);   // cudaFree + forget; the caller orders it after the last use on the stream
 
 // conv_tc.cu / conv_simple.cu
 int pcb_conv_tc2(pcb_ctx* c, const ConvArgs& a);   // product kernel: pixels on UMMA M, couts on N, operand reuse in shared memory

@@ -193,6 +193,7 @@ inline int grid_for(long long total, pcb_ctx* c, int per_block = 256) {
 
 int resize_common(pcb_ctx* c, const uint8_t* src, int n, int h, int w, uint8_t* dst, int nh, int nw, bool area, double fx = 0.0,
                   double fy = 0.0) {
+  PCB_ENTER(c);
   if (!src || !dst || n <= 0 || h <= 0 || w <= 0 || nh <= 0 || nw <= 0) return pcb_fail(c, PCB_ERR_ARG, "resize: bad arguments");
   PcbResizePlan plan = pcb_resize_plan(h, w, nh, nw, area, fx, fy);
   if (plan.mode == PCB_RS_AREA_INT && plan.isx == 2 && plan.isy == 2 && (nw % 16) == 0 && ((uintptr_t)src % 16) == 0 &&
@@ -236,11 +237,6 @@ void pcb_letterbox_geometry(int vh, int vw, int S, int* new_h, int* new_w, doubl
   *det_scale = (double)(*new_h) / (double)vh;
 }
 
-struct LinTabCacheEntry { void* x; void* y; };
-static std::map<std::vector<int>, LinTabCacheEntry>& lin_cache(pcb_ctx* c) {
-  static std::map<pcb_ctx*, std::map<std::vector<int>, LinTabCacheEntry>> caches;
-  return caches[c];
-}
 
 int pcb_letterbox_impl(pcb_ctx* c, const uint8_t* frames, int n, int h, int w, int S, int rot, int pad, __half* out,
                        uint8_t* det_img, double* det_scale_out) {
@@ -257,21 +253,20 @@ int pcb_letterbox_impl(pcb_ctx* c, const uint8_t* frames, int n, int h, int w, i
   p.mode = p.plan.mode;
   if (p.mode == PCB_RS_LINEAR) {
     std::vector<int> key = {v.vh, v.vw, p.new_h, p.new_w};
-    auto& cache = lin_cache(c);
+    auto& cache = c->lin_tabs;          // owned by the context: freed (with every other allocation) by pcb_destroy
     auto it = cache.find(key);
     if (it == cache.end()) {
-      LinTabCacheEntry e;
-      e.x = pcb_dev_alloc(c, sizeof(LinTab) * p.new_w, false);
-      e.y = pcb_dev_alloc(c, sizeof(LinTab) * p.new_h, false);
-      if (!e.x || !e.y) return pcb_fail(c, PCB_ERR_CUDA, "letterbox: table alloc");
-      lin_table_kernel<<<(p.new_w + 127) / 128, 128, 0, c->stream>>>((LinTab*)e.x, v.vw, p.new_w, 1);
+      void* ex = pcb_dev_alloc(c, sizeof(LinTab) * p.new_w, false);
+      void* ey = pcb_dev_alloc(c, sizeof(LinTab) * p.new_h, false);
+      if (!ex || !ey) return pcb_fail(c, PCB_ERR_CUDA, "letterbox: table alloc");
+      lin_table_kernel<<<(p.new_w + 127) / 128, 128, 0, c->stream>>>((LinTab*)ex, v.vw, p.new_w, 1);
       PCB_LAUNCH_CHECK(c, "lin_table_kernel");
-      lin_table_kernel<<<(p.new_h + 127) / 128, 128, 0, c->stream>>>((LinTab*)e.y, v.vh, p.new_h, 0);
+      lin_table_kernel<<<(p.new_h + 127) / 128, 128, 0, c->stream>>>((LinTab*)ey, v.vh, p.new_h, 0);
       PCB_LAUNCH_CHECK(c, "lin_table_kernel");
-      it = cache.emplace(key, e).first;
+      it = cache.emplace(key, std::make_pair(ex, ey)).first;
     }
-    p.xtab = (const LinTab*)it->second.x;
-    p.ytab = (const LinTab*)it->second.y;
+    p.xtab = (const LinTab*)it->second.first;
+    p.ytab = (const LinTab*)it->second.second;
   }
   p.out = out;
   p.det_img = det_img;

@@ -466,12 +466,20 @@ def _refine_edges_batched(spans, clip, fps, face, bank: RefBank, ref_feat, cfg, 
                         break
             res[j] = bool(chosen is not None and (fdf[chosen.rows] <= trk.enter).any())
         if shard is not None:
+            # every rank knows which probe frames every other rank owns: one all_gather of padded hit bytes
             import torch.distributed as dist
-            parts = [None] * shard["world"]
-            dist.all_gather_object(parts, res, group=shard["group"])
-            res = {}
-            for part in parts:
-                res.update(part)
+            world = shard["world"]
+            owned = [[j for j in all_ids if shard["owner"](j) == r] for r in range(world)]
+            cap = max(max(len(o) for o in owned), 1)
+            cuda = dist.get_backend(shard["group"]) == "nccl"
+            dev = face.engine.tdev if cuda else torch.device("cpu")
+            mine = torch.zeros((cap,), dtype=torch.uint8)
+            for k, j in enumerate(owned[shard["rank"]]):
+                mine[k] = 1 if res[j] else 0
+            recv = torch.empty((world, cap), dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(recv.view(-1), mine.to(dev), group=shard["group"])
+            hits = recv.cpu().numpy()
+            res = {j: bool(hits[r, k]) for r in range(world) for k, j in enumerate(owned[r])}
         return res
 
     left_ids = []
@@ -537,9 +545,6 @@ class FaceTable:
     # images per ArcFace graph run (pcb_embed chunk; half as many faces when both variants are computed).  444 fills the 148 SMs
     # to >= 95 % in every iResNet stage (14x14: 888 tiles = 6.0 waves, 28x28: 10.5, 56x56: 39.4)
     EMBED_RUN = int(os.environ.get("PCB_EMBED_RUN", "444"))
-    # images per EARLY flip run (FlipPredictor): small enough to fit into the slack of one frame batch (a 444-image run is 13 ms,
-    # the slack of a PCIe-bound batch ~3 ms), still whole waves in the 14x14 stage (148 images = 296 tiles = 2.0 waves)
-    EARLY_RUN = int(os.environ.get("PCB_EARLY_RUN", "148"))
 
     def __init__(self, lazy: bool = False):
         self.lazy = lazy
@@ -554,16 +559,6 @@ class FaceTable:
         self.a_parts: List[np.ndarray] = []
         self.encoded = None
         self.flip_passes = 0          # faces that went through the flip pass (bench: ArcFace image passes / s)
-        # lazy mode, flips computed while the superset is still running (see FlipPredictor): per flushed run its first row
-        # and its similarity to the initial bank, rows queued for an early flip pass, and the results until `finalize`
-        self.part_start: List[int] = []
-        self.sim_parts: List[tuple] = []          # (first row, rows, sim device tensor, event)
-        self.sim_fetched = 0                      # parts whose similarities are on the host
-        self.fd0_host = np.zeros((0,), np.float64)
-        self.flip_queue: List[np.ndarray] = []
-        self.flip_queue_n = 0
-        self.early: List[tuple] = []              # (rows, normalised flip features on the device)
-        self.embedded = 0                         # rows whose plain feature has been computed (flushed)
 
     def queue(self, eng, chips: torch.Tensor, k: int) -> np.ndarray:
         """Register k aligned chips; -> their row numbers.  Embedding happens in `flush`."""
@@ -590,15 +585,9 @@ class FaceTable:
         use = chips[:take].contiguous()
         if self.lazy:
             emb, _ = eng.embed(use, take, False)
-            fp, sim, _ = eng.match(emb, None, None, take)         # normalise(e(x)); sim: against the bank on the device
+            fp, _, _ = eng.match(emb, None, None, take)           # normalise(e(x))
             self.raw.append(emb[:take])
             self.chip_list.append(use)
-            ev = torch.cuda.Event() if use.is_cuda else None
-            if ev is not None:
-                ev.record(eng.stream)
-            self.part_start.append(self.embedded)
-            self.sim_parts.append((self.embedded, take, sim, ev))
-            self.embedded += take
         else:
             emb, emb_flip = eng.embed(use, take, True)
             fp, _, _ = eng.match(emb, None, None, take)           # normalise(e(x))
@@ -613,53 +602,8 @@ class FaceTable:
         else:
             self.pending, self.pending_n = [], 0
 
-    # ---- early flips (lazy mode): see FlipPredictor
-    def poll_fd0(self, block: bool = False) -> int:
-        """Fetch the similarities (to the bank that was on the device during the superset) of finished runs; -> number of
-        leading rows whose distance is on the host.  Never waits for the GPU unless `block`."""
-        while self.sim_fetched < len(self.sim_parts):
-            start, take, sim, ev = self.sim_parts[self.sim_fetched]
-            if ev is not None and not block and not ev.query():
-                break
-            if ev is not None and block:
-                ev.synchronize()
-            self.fd0_host = np.concatenate([self.fd0_host, 1.0 - sim[:take].cpu().numpy().astype(np.float64)])
-            self.sim_fetched += 1
-        return len(self.fd0_host)
-
-    def queue_flips(self, eng, rows: np.ndarray):
-        """Rows (already flushed) whose flip feature will most likely be needed: embed them in runs of EMBED_RUN images."""
-        if len(rows):
-            self.flip_queue.append(np.asarray(rows, np.int64))
-            self.flip_queue_n += len(rows)
-        while self.flip_queue_n >= self.EARLY_RUN:
-            self._run_flips(eng, self.EARLY_RUN)
-
-    def _run_flips(self, eng, n: int):
-        allr = np.concatenate(self.flip_queue)
-        rows, rest = allr[:n], allr[n:]
-        self.flip_queue = [rest] if len(rest) else []
-        self.flip_queue_n = len(rest)
-        starts = np.asarray(self.part_start, np.int64)
-        part = np.searchsorted(starts, rows, side="right") - 1
-        with torch.cuda.stream(eng.stream):
-            chips, raws = [], []
-            for pi in np.unique(part):
-                loc = torch.as_tensor(rows[part == pi] - starts[pi], device=self.chip_list[pi].device)
-                chips.append(self.chip_list[pi].index_select(0, loc))
-                raws.append(self.raw[pi].index_select(0, loc))
-            chips = torch.cat(chips, 0).contiguous()
-            raws = torch.cat(raws, 0).contiguous()
-        order = np.concatenate([rows[part == pi] for pi in np.unique(part)])
-        _, emb_flip = eng.embed(chips, len(order), "only")
-        ff, _, _ = eng.match(raws, emb_flip, None, len(order))
-        self.early.append((order, ff[:len(order)]))
-        self.flip_passes += len(order)
-
     def finalize(self, eng):
         self.flush(eng)
-        if self.lazy and self.flip_queue_n:
-            self._run_flips(eng, self.flip_queue_n)
         with torch.cuda.stream(eng.stream):
             if self.count:
                 self.plain = torch.cat(self.feat_plain, 0).contiguous()
@@ -674,15 +618,6 @@ class FaceTable:
                 self.flip = eng.empty((1, L.FEAT_DIM), torch.float32)
         self.flip_ready = np.zeros(self.count, bool) if self.lazy else np.ones(self.count, bool)
         self.flip_host = np.zeros((self.count, L.FEAT_DIM), np.float32) if self.lazy else None
-        for rows, ff in self.early:           # flips computed while the superset was running
-            with torch.cuda.stream(eng.stream):
-                self.flip.index_copy_(0, torch.as_tensor(rows, device=self.flip.device), ff)
-        if self.early:
-            eng.sync()
-            for rows, ff in self.early:
-                self.flip_host[rows] = ff.cpu().numpy()
-                self.flip_ready[rows] = True
-        self.early = []
         self.feat_plain, self.feat_flip, self.raw, self.chip_list = [], [], [], []
 
     def ensure_flip(self, eng, rows: np.ndarray) -> bool:
@@ -735,45 +670,8 @@ def _collect_variant(eng, frames, det, idx_list, records, key, table: FaceTable,
         off += k
 
 
-class FlipPredictor:
-    """`_predict_flip_rows` as an incremental state machine, run while the superset is still in progress: as soon as the plain
-    distances (to the initial bank) of a sample's faces are on the host, the sample is passed through the same rule and the rows
-    it selects are queued for an early flip pass (FaceTable.queue_flips).  The separate prediction after the superset still
-    runs over everything, so this only moves ArcFace work earlier -- into the time the SMs otherwise wait for frames to cross
-    PCIe when the clip is host-resident -- and never changes which rows are computed eagerly, let alone results."""
-
-    def __init__(self, cfg, fps: int, carry_in: bool, margin: float = 0.12):
-        self.thr = float(cfg.prescan_fd_enter) + margin
-        stride = max(1, int(cfg.prescan_stride))
-        exit_cool = int(round(max(0.0, float(getattr(cfg, "prescan_exit_cooldown_sec", 0.5))) * fps))
-        self.tail = (exit_cool + stride - 1) // stride + 1
-        self.remaining = self.tail if carry_in else 0
-        self.samples: List[List[np.ndarray]] = []      # per sample (in order): its row arrays
-        self.next = 0
-
-    def add(self, records, chunk):
-        for idx in chunk:
-            self.samples.append(_rows_of(records[idx]))
-
-    def advance(self, table: "FaceTable", eng, block: bool = False):
-        have = table.poll_fd0(block)
-        out: List[np.ndarray] = []
-        while self.next < len(self.samples):
-            rws = self.samples[self.next]
-            if rws and max(int(r.max()) for r in rws if len(r)) >= have:
-                break
-            if self.remaining > 0:
-                out += rws
-                self.remaining -= 1
-            if rws and min(float(table.fd0_host[r].min()) for r in rws if len(r)) <= self.thr:
-                self.remaining = self.tail
-            self.next += 1
-        if out:
-            table.queue_flips(eng, np.concatenate(out))
-
-
 def compute_superset(clip, idxs: Sequence[int], face: FaceEmbedder, cfg, batch: int = 32, max_faces: int = 4096,
-                     lazy_flip: bool = False, predictor: Optional["FlipPredictor"] = None):
+                     lazy_flip: bool = False):
     """GPU stage of the batched pre-scan for the samples `idxs` (fast pre-scan settings must be active).
     lazy_flip: compute e(flip x) later, only for the faces the replay evaluates while a span is active.
 
@@ -841,10 +739,6 @@ def compute_superset(clip, idxs: Sequence[int], face: FaceEmbedder, cfg, batch: 
 
     cur = issue(0) if chunks else None
     for ci in range(len(chunks)):
-        if predictor is not None:
-            # early flip passes go into the stream BEFORE the next batch's work, which may sit waiting for its frames to
-            # arrive over PCIe: that wait is the time these passes are meant to fill
-            predictor.advance(table, eng)
         nxt = issue(ci + 1) if ci + 1 < len(chunks) else None
         cur["done"].synchronize()
         chunk, frames, dyn, det0 = cur["chunk"], cur["frames"], cur["dyn"], cur["det0"]
@@ -858,8 +752,6 @@ def compute_superset(clip, idxs: Sequence[int], face: FaceEmbedder, cfg, batch: 
         cur = nxt
         if not empty:
             encode_chunk(chunk)
-            if predictor is not None:
-                predictor.add(records, chunk)
             continue
         with torch.cuda.stream(eng.stream):
             sub = frames.index_select(0, torch.as_tensor(empty, device=frames.device)).contiguous()
@@ -885,10 +777,6 @@ def compute_superset(clip, idxs: Sequence[int], face: FaceEmbedder, cfg, batch: 
                 records[sidx].heavy_raw[deg] = int(raw[j])
             _collect_variant(eng, sub2, hv, sel_idx, records, deg, table, max_faces)
         encode_chunk(chunk)
-        if predictor is not None:
-            predictor.add(records, chunk)
-    if predictor is not None:
-        predictor.advance(table, eng)
     table.finalize(eng)
     one = lambda parts, dt: np.concatenate(parts).astype(dt) if parts else np.zeros(1, dt)
     table.encoded = (np.concatenate(meta_parts, 0) if meta_parts else np.zeros((0, L.REPLAY_META), np.int32),
@@ -1061,22 +949,41 @@ def encode_records(records: Dict[int, SampleRecord], idxs: Sequence[int], n_rows
     return meta, quality, area
 
 
+class _BankView:
+    """What a `distances.get(bank)` implementation sees of the native bank: array() / version / len()."""
+
+    def __init__(self, rows: Optional[np.ndarray], version: int):
+        self._rows, self.version = rows, version
+
+    def array(self):
+        return self._rows
+
+    def __len__(self):
+        return 0 if self._rows is None else len(self._rows)
+
+
+def bank_cfg_of(cfg) -> "L.BankCfg":
+    wa, wd, wq = _weights3(cfg)
+    return L.BankCfg(cap=max(1, int(getattr(cfg, "prescan_bank_max", 64))), dedup=float(getattr(cfg, "prescan_diversity_dedup_cos", 0.968)),
+                     margin=float(getattr(cfg, "prescan_replace_margin", 0.010)), wa=wa, wd=wd, wq=wq)
+
+
 def replay(records: Dict[int, SampleRecord], table, feats_host, idxs: Sequence[int], fps: int, total_frames: int,
            face: FaceEmbedder, ref_feat, cfg, log: Optional[list] = None, distances=None, native: Optional[bool] = None,
            encoded=None):
-    """Replay of the reference's sequential loop over precomputed superset records.  The per-sample loop runs in
-    libpcb200 (pcb_replay); bank offers and missing flip features come back here through callbacks.  `native=False`
-    (or PCB_PY_REPLAY=1) runs the pure-Python statement of the same loop (`_replay_python`), which the tests hold the
-    native one against."""
+    """Replay of the reference's sequential loop over precomputed superset records.  The per-sample loop AND the live
+    bank run in libpcb200 (pcb_replay / pcb_bank_offer); distances of the rows still ahead are refreshed on the GPU by
+    the library itself (pcb_live_refresh: one short launch per bank change, no Python in between).  The only callback
+    left is "flip features missing".  `distances` (tests, no GPU) supplies the distances through a callback instead;
+    `native=False` (or PCB_PY_REPLAY=1) runs the pure-Python statement of the same loop (`_replay_python`), which the
+    tests hold the native one against."""
     import ctypes as C
     if native is None:
         native = os.environ.get("PCB_PY_REPLAY", "0") != "1"
     if not native:
         return _replay_python(records, table, feats_host, idxs, fps, total_frames, face, ref_feat, cfg, log, distances)
     lib = L.load()
-    bank = RefBank(cfg, ref_feat)
     trk = SpanTracker(cfg, fps, total_frames)
-    dist = distances if distances is not None else _LiveDistances(face.engine, table)
     plain_h, flip_h = feats_host
     lazy = table is not None and getattr(table, "lazy", False)
     if lazy:
@@ -1085,65 +992,112 @@ def replay(records: Dict[int, SampleRecord], table, feats_host, idxs: Sequence[i
     idxs = list(idxs)
     meta, quality, area = encoded if encoded is not None else encode_records(records, idxs, n_rows)
     meta = np.ascontiguousarray(meta, np.int32)
+    quality = np.ascontiguousarray(quality, np.float64)
+    area = np.ascontiguousarray(area, np.int64)
     frame_idx = np.asarray(idxs, np.int64)
     fdp = np.full(max(n_rows, 1), FD_NONE, np.float64)
     fdf = np.full(max(n_rows, 1), FD_NONE, np.float64)
+    plain_c = np.ascontiguousarray(plain_h, np.float32) if n_rows else np.zeros((1, L.FEAT_DIM), np.float32)
+    flip_c = np.ascontiguousarray(flip_h, np.float32) if (n_rows and flip_h is not None and len(flip_h)) else np.zeros((max(n_rows, 1), L.FEAT_DIM), np.float32)
+    if lazy and n_rows:
+        flip_c = table.flip_host            # filled in place by ensure_flip: the library must see the same memory
+        assert flip_c.flags["C_CONTIGUOUS"] and flip_c.dtype == np.float32
+    ref_rows = None
+    if ref_feat is not None:
+        ref_rows = np.ascontiguousarray(np.asarray(ref_feat, np.float32).reshape(-1, L.FEAT_DIM))
+    bcfg = bank_cfg_of(cfg)
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+    nb = lib.pcb_bank_create(C.byref(bcfg), ptr(ref_rows) if ref_rows is not None and len(ref_rows) else None,
+                             0 if ref_rows is None else len(ref_rows))
+    if not nb:
+        raise L.PcbError("pcb_bank_create failed")
+    eng = getattr(face, "engine", None)
+    use_gpu = distances is None
+    failure: List[BaseException] = []        # an exception inside a ctypes callback would be printed and swallowed: keep it, abort, re-raise
 
-    def refresh():
-        a, b = dist.get(bank)
-        if n_rows:
-            fdp[:n_rows] = a
-            fdf[:n_rows] = b
+    def arm_live():
+        with torch.cuda.stream(eng.stream):
+            both = torch.cat([table.plain[:n_rows], table.flip[:n_rows]], 0).contiguous()
+        eng._check(lib.pcb_live_begin(eng.ctx, both.data_ptr(), 2 * n_rows), "pcb_live_begin")
 
-    refresh()
+    def on_refresh(_user, bank_rows, n_bank, _slot, _row_lo):
+        try:
+            rows = np.ctypeslib.as_array(bank_rows, shape=(n_bank, L.FEAT_DIM)).copy() if n_bank else None
+            a, b = distances.get(_BankView(rows, int(lib.pcb_bank_version(nb))))
+            if n_rows:
+                fdp[:n_rows] = a
+                fdf[:n_rows] = b
+            return 0
+        except BaseException as exc:      # noqa: BLE001
+            failure.append(exc)
+            return -1
+
     lookahead = 96
 
-    def on_offer(_user, s_i, row, q, active):
-        vec = (flip_h if active else plain_h)[row]
-        if bank.offer(vec, q) in ("added", "replaced"):
-            refresh()
-            return 1
-        return 0
-
     def on_flip(_user, s_i):
-        want = []
-        for m in meta[s_i:s_i + lookahead]:
-            for c0 in (0, 6, 8):
-                if m[c0] >= 0:
-                    want.append(np.arange(m[c0], m[c0] + m[c0 + 1]))
-        if want and table.ensure_flip(getattr(face, "engine", None), np.concatenate(want)):
-            dist.invalidate()
-            refresh()
-        return 1
+        try:
+            want = []
+            for m in meta[s_i:s_i + lookahead]:
+                for c0 in (0, 6, 8):
+                    if m[c0] >= 0:
+                        want.append(np.arange(m[c0], m[c0] + m[c0 + 1]))
+            if want and table.ensure_flip(eng, np.concatenate(want)):
+                if use_gpu:
+                    arm_live()
+                elif hasattr(distances, "invalidate"):
+                    distances.invalidate()
+            return 0
+        except BaseException as exc:      # noqa: BLE001
+            failure.append(exc)
+            return -1
 
-    rc = L.ReplayCfg(enter=trk.enter, exit_thr=trk.exit, fd_add=float(getattr(cfg, "prescan_fd_add", trk.enter)),
-                     quality_min=float(cfg.face_quality_min), total_frames=trk.total, pad=trk.pad, min_len=trk.min_len,
-                     exit_cool=trk.exit_cool, stride=trk.stride, cooldown=int(getattr(cfg, "prescan_add_cooldown_samples", 5)),
-                     fd9_skip=int(trk._fd9_skip), fd9_grace=trk._fd9_grace, fd9_period=trk._fd9_period)
-    st = L.ReplayState(frame_idx=int(face._frame_idx), last_face_idx=int(max(face._last_face_idx, -2 ** 62)),
-                       no_face_streak=int(face._no_face_streak), rot_cycle=int(face._rot_cycle), prescan_rr=int(face._prescan_rr),
-                       trk_active=0)
-    n = len(idxs)
-    best = np.zeros(max(n, 1), np.float64)
-    skip = np.zeros(max(n, 1), np.uint8)
-    act = np.zeros(max(n, 1), np.uint8)
-    nf = np.zeros(max(n, 1), np.int32)
-    max_spans = n + 2
-    spans = np.zeros((max_spans, 2), np.int64)
-    n_spans = C.c_int32(0)
-    ready = table.flip_ready.view(np.uint8) if lazy else None
-    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
-    cb_o, cb_f = L.REPLAY_OFFER_CB(on_offer), L.REPLAY_FLIP_CB(on_flip)
-    err = lib.pcb_replay(C.byref(rc), ptr(meta), ptr(frame_idx), n, ptr(quality), ptr(area), ptr(ready) if ready is not None else None,
-                         ptr(fdp), ptr(fdf), C.byref(st), cb_o, cb_f, None, ptr(best), ptr(skip), ptr(act), ptr(nf), ptr(spans),
-                         max_spans, C.byref(n_spans))
-    if err:
-        raise L.PcbError(f"pcb_replay failed (code {err})")
+    try:
+        if use_gpu and n_rows:
+            arm_live()
+        rc = L.ReplayCfg(enter=trk.enter, exit_thr=trk.exit, fd_add=float(getattr(cfg, "prescan_fd_add", trk.enter)),
+                         quality_min=float(cfg.face_quality_min), total_frames=trk.total, pad=trk.pad, min_len=trk.min_len,
+                         exit_cool=trk.exit_cool, stride=trk.stride, cooldown=int(getattr(cfg, "prescan_add_cooldown_samples", 5)),
+                         fd9_skip=int(trk._fd9_skip), fd9_grace=trk._fd9_grace, fd9_period=trk._fd9_period)
+        st = L.ReplayState(frame_idx=int(face._frame_idx), last_face_idx=int(max(face._last_face_idx, -2 ** 62)),
+                           no_face_streak=int(face._no_face_streak), rot_cycle=int(face._rot_cycle), prescan_rr=int(face._prescan_rr),
+                           trk_active=0)
+        n = len(idxs)
+        best = np.zeros(max(n, 1), np.float64)
+        skip = np.zeros(max(n, 1), np.uint8)
+        act = np.zeros(max(n, 1), np.uint8)
+        nf = np.zeros(max(n, 1), np.int32)
+        max_spans = n + 2
+        spans = np.zeros((max_spans, 2), np.int64)
+        n_spans = C.c_int32(0)
+        n_refresh = C.c_int64(0)
+        ready = table.flip_ready.view(np.uint8) if lazy else None
+        cb_r, cb_f = L.REPLAY_REFRESH_CB(on_refresh), L.REPLAY_FLIP_CB(on_flip)
+        io = L.ReplayIO(meta=ptr(meta), frame_idx=ptr(frame_idx), n_samples=n, n_rows=n_rows, quality=ptr(quality), area=ptr(area),
+                        flip_ready=ptr(ready) if ready is not None else None, feat_plain=ptr(plain_c), feat_flip=ptr(flip_c),
+                        fd_plain=ptr(fdp), fd_flip=ptr(fdf), refresh=cb_r, need_flip=cb_f, user=None, best_out=ptr(best),
+                        skip_out=ptr(skip), active_out=ptr(act), nfaces_out=ptr(nf), spans_out=ptr(spans), max_spans=max_spans,
+                        n_spans_out=C.pointer(n_spans), refreshes_out=C.pointer(n_refresh))
+        err = lib.pcb_replay(eng.ctx if use_gpu else None, C.byref(rc), nb, C.byref(io), C.byref(st))
+        if failure:
+            raise failure[0]
+        if err:
+            msg = lib.pcb_last_error(eng.ctx).decode() if (use_gpu and eng is not None) else ""
+            raise L.PcbError(f"pcb_replay failed (code {err}) {msg}")
+        n_bank = int(lib.pcb_bank_rows(nb))
+        bank = RefBank(cfg)
+        if n_bank:
+            arr = np.ctypeslib.as_array(lib.pcb_bank_data(nb), shape=(n_bank, L.FEAT_DIM)).copy()
+            bank.rows = [r for r in arr]
+        bank.version = int(lib.pcb_bank_version(nb))
+    finally:
+        lib.pcb_bank_destroy(nb)
+        if use_gpu and eng is not None:
+            eng._bank_token = None          # the library rewrote the device bank behind Engine.set_bank's cache
     face._frame_idx, face._last_face_idx = int(st.frame_idx), int(st.last_face_idx)
     face._no_face_streak, face._rot_cycle, face._prescan_rr = int(st.no_face_streak), int(st.rot_cycle), int(st.prescan_rr)
     trk.spans = [(int(a), int(b)) for a, b in spans[:n_spans.value]]
     trk.active = False          # pcb_replay already closed the open span (gui_app.py:1648-1655)
-    trk.distance_refreshes = getattr(dist, "refreshes", None)
+    trk.distance_refreshes = int(n_refresh.value)
     if log is not None:
         for i, idx in enumerate(idxs):
             log.append(dict(idx=idx, skip=bool(skip[i]), best=float(best[i]), active_before=bool(act[i]), nfaces=int(nf[i])))
@@ -1192,26 +1146,43 @@ class _ShardedTable:
         need = np.unique(np.asarray(rows)[~self.flip_ready[rows]])
         if not len(need):
             return False
-        lo, hi = self.base[self.rank], self.base[self.rank + 1]
-        mine = need[(need >= lo) & (need < hi)] - lo
+        world = len(self.counts)
+        # every rank derives the same `need`, so it also knows how many rows each owner contributes: one all_gather of the
+        # padded feature blocks is the whole exchange (no pickled objects, no size negotiation)
+        owned = [need[(need >= self.base[r]) & (need < self.base[r + 1])] for r in range(world)]
+        mine = owned[self.rank] - self.base[self.rank]
         self.local.ensure_flip(eng, mine)
-        parts = [None] * len(self.counts)
-        dist.all_gather_object(parts, (mine + lo, self.local.flip_host[mine] if len(mine) else np.zeros((0, L.FEAT_DIM), np.float32)),
-                               group=self.group)
-        for rows_g, feats in parts:
-            if len(rows_g):
-                self.flip_host[rows_g] = feats
-                self.flip_ready[rows_g] = True
-                if self.flip.is_cuda:
-                    with torch.cuda.stream(eng.stream):
-                        self.flip.index_copy_(0, torch.as_tensor(rows_g, device=self.flip.device), torch.from_numpy(feats).to(self.flip.device))
-                else:
-                    self.flip[torch.as_tensor(rows_g)] = torch.from_numpy(feats)
+        cap = max(max(len(o) for o in owned), 1)
+        cuda = self.flip.is_cuda
+        send = torch.zeros((cap, L.FEAT_DIM), dtype=torch.float32, device=self.flip.device)
+        if len(mine):
+            if cuda:
+                with torch.cuda.stream(eng.stream):
+                    send[:len(mine)] = self.local.flip.index_select(0, torch.as_tensor(mine, device=self.flip.device))
+                torch.cuda.current_stream().wait_stream(eng.stream)
+            else:
+                send[:len(mine)] = torch.from_numpy(self.local.flip_host[mine])
+        recv = torch.empty((world, cap, L.FEAT_DIM), dtype=torch.float32, device=self.flip.device)
+        dist.all_gather_into_tensor(recv.view(-1), send.view(-1), group=self.group)
+        if cuda:
+            eng.stream.wait_stream(torch.cuda.current_stream())
+        host = recv.cpu().numpy()
+        for r in range(world):
+            rows_g = owned[r]
+            if not len(rows_g):
+                continue
+            self.flip_host[rows_g] = host[r, :len(rows_g)]
+            self.flip_ready[rows_g] = True
+            if cuda:
+                with torch.cuda.stream(eng.stream):
+                    self.flip.index_copy_(0, torch.as_tensor(rows_g, device=self.flip.device), recv[r, :len(rows_g)])
+            else:
+                self.flip[torch.as_tensor(rows_g)] = recv[r, :len(rows_g)]
         return True
 
 
 def prescan_batched(clip, fps: int, face: FaceEmbedder, ref_feat, cfg, batch: int = 32, log: Optional[list] = None,
-                    dist_group=None, stats: Optional[dict] = None):
+                    dist_group=None, stats: Optional[dict] = None, single_rank: bool = False):
     """Throughput pre-scan.  With torch.distributed initialised (dist_group or the default group), the
     sample list is split into contiguous chunks per rank, per-face records are all-gathered and every
     rank replays the same sequence.
@@ -1224,7 +1195,7 @@ def prescan_batched(clip, fps: int, face: FaceEmbedder, ref_feat, cfg, batch: in
     stride = max(1, int(cfg.prescan_stride))
     idxs = sample_indices(total, stride)
     world, rank = 1, 0
-    if dist.is_available() and dist.is_initialized():
+    if dist.is_available() and dist.is_initialized() and not single_rank:     # single_rank: this process scans the whole clip alone
         world, rank = dist.get_world_size(dist_group), dist.get_rank(dist_group)
     if int(getattr(cfg, "prescan_probe_imgsz", 512)) > int(face.fast_no_face_imgsz):
         raise RuntimeError("prescan_batched requires prescan_probe_imgsz <= fast_no_face_imgsz (the upright size would "
@@ -1242,16 +1213,7 @@ def prescan_batched(clip, fps: int, face: FaceEmbedder, ref_feat, cfg, batch: in
         per = (len(idxs) + world - 1) // world
         mine = idxs[rank * per:(rank + 1) * per]
         lazy = os.environ.get("PCB_EAGER_FLIP", "0") != "1"
-        predictor = None
-        # Early flip passes (FlipPredictor) are OFF by default: measured on B200 they move half of the predicted flips into the
-        # superset but lengthen it by as much, resident (52 -> 66 ms) and host-resident (75 -> 88 ms) alike, i.e. the superset
-        # has no idle SM time to fill even when it is PCIe-paced (4 430 -> 4 360-4 420 frames/s e2e); PCB_EARLY_FLIP=1 enables it.
-        if lazy and os.environ.get("PCB_EARLY_FLIP", "0") == "1":
-            bank0 = RefBank(cfg, ref_feat)
-            if len(bank0):
-                eng.set_bank(bank0.array())      # FaceTable.flush then gets the distances to the initial bank for free
-                predictor = FlipPredictor(cfg, fps, carry_in=rank > 0)
-        records, table = compute_superset(clip, mine, face, cfg, batch=batch, lazy_flip=lazy, predictor=predictor)
+        records, table = compute_superset(clip, mine, face, cfg, batch=batch, lazy_flip=lazy)
         eng.sync()
         mark("superset")
         if lazy and table.count:
@@ -1293,54 +1255,99 @@ def prescan_batched(clip, fps: int, face: FaceEmbedder, ref_feat, cfg, batch: in
 
 
 def _gather_shards(eng, enc_local, table, plain_h, flip_h, world, group):
-    """All-gather the per-face features (NCCL on device tensors) and the flat sample records (pcb_replay form; three
-    numpy arrays per rank).  -> (merged table, plain_h, flip_h, (meta, quality, area) of all ranks in sample order)."""
+    """All-gather of everything the replicated replay needs from the other ranks, as TWO tensor collectives: a 2-word
+    header (face rows, samples) and one packed byte buffer per rank
+
+        [ meta int32 [S,10] | quality f64 [F] | area i64 [F] | flip_ready u8 [F] | plain f32 [F,512] | flip f32 [F,512] ]
+
+    padded to the largest rank.  On NCCL the features never leave the device before the collective; the small records
+    ride in the same buffer.  -> (merged table, plain_h, flip_h, (meta, quality, area) of all ranks in sample order)."""
     import torch.distributed as dist
     rank = dist.get_rank(group)
     lazy = bool(getattr(table, "lazy", False))
     meta_l, q_l, a_l = enc_local
-    parts = [None] * world
-    ready_l = getattr(table, "flip_ready", np.ones(table.count, bool)) if table.count else np.zeros((0,), bool)
-    dist.all_gather_object(parts, (int(table.count), meta_l, q_l[:table.count], a_l[:table.count], ready_l), group=group)
-    counts = [p[0] for p in parts]
-    cap = max(max(counts), 1)
+    count = int(table.count)
+    n_s = int(len(meta_l))
     backend_cuda = dist.get_backend(group) == "nccl"
     dev = eng.tdev if (backend_cuda and eng is not None) else torch.device("cpu")
-    send = torch.zeros((2, cap, L.FEAT_DIM), dtype=torch.float32, device=dev)
-    if table.count:
-        if lazy:
-            flip_src = table.flip[:table.count] if backend_cuda else torch.from_numpy(table.flip_host)
-        else:
-            flip_src = table.flip[:table.count] if backend_cuda else torch.from_numpy(flip_h)
-        send[0, :table.count] = table.plain[:table.count] if backend_cuda else torch.from_numpy(plain_h)
-        send[1, :table.count] = flip_src
-    recv = [torch.empty_like(send) for _ in range(world)]
+    head = torch.tensor([count, n_s], dtype=torch.int64, device=dev)
+    heads = torch.empty((world, 2), dtype=torch.int64, device=dev)
     if backend_cuda:
         torch.cuda.current_stream().wait_stream(eng.stream)
-    dist.all_gather(recv, send, group=group)
-    metas, quals, areas, plains, flips = [], [], [], [], []
-    base = 0
-    for r in range(world):
-        m = parts[r][1].copy()
-        for c0 in (0, 6, 8):
-            m[:, c0] = np.where(m[:, c0] >= 0, m[:, c0] + base, -1)
-        metas.append(m)
-        quals.append(parts[r][2])
-        areas.append(parts[r][3])
-        plains.append(recv[r][0, :counts[r]])
-        flips.append(recv[r][1, :counts[r]])
-        base += counts[r]
-    allp = torch.cat(plains, 0) if base else torch.zeros((1, L.FEAT_DIM))
-    allf = torch.cat(flips, 0) if base else torch.zeros((1, L.FEAT_DIM))
+    dist.all_gather_into_tensor(heads.view(-1), head, group=group)
+    heads_h = heads.cpu().numpy()
+    counts = [int(c) for c in heads_h[:, 0]]
+    n_samples = [int(c) for c in heads_h[:, 1]]
+    cap, scap = max(max(counts), 1), max(max(n_samples), 1)
+    r16 = lambda x: (x + 15) // 16 * 16
+    o_meta = 0
+    o_q = r16(o_meta + scap * L.REPLAY_META * 4)
+    o_a = r16(o_q + cap * 8)
+    o_r = r16(o_a + cap * 8)
+    o_p = r16(o_r + cap)
+    o_f = o_p + cap * L.FEAT_DIM * 4
+    nbytes = o_f + cap * L.FEAT_DIM * 4
+    small = np.zeros(o_p, np.uint8)
+    small[o_meta:o_meta + n_s * L.REPLAY_META * 4] = np.ascontiguousarray(meta_l, np.int32).view(np.uint8).reshape(-1)
+    small[o_q:o_q + count * 8] = np.ascontiguousarray(q_l[:count], np.float64).view(np.uint8)
+    small[o_a:o_a + count * 8] = np.ascontiguousarray(a_l[:count], np.int64).view(np.uint8)
+    ready_l = np.asarray(getattr(table, "flip_ready", np.ones(count, bool))[:count], bool) if count else np.zeros((0,), bool)
+    small[o_r:o_r + count] = ready_l.view(np.uint8)
+    send = torch.zeros((nbytes,), dtype=torch.uint8, device=dev)
+    fview = lambda buf, off, n: buf[off:off + n * L.FEAT_DIM * 4].view(torch.float32).view(n, L.FEAT_DIM)
     if backend_cuda:
+        with torch.cuda.stream(eng.stream):
+            send[:o_p].copy_(torch.from_numpy(small).pin_memory(), non_blocking=True)
+            if count:
+                fview(send, o_p, count).copy_(table.plain[:count])
+                fview(send, o_f, count).copy_(table.flip[:count])
+        torch.cuda.current_stream().wait_stream(eng.stream)
+    else:
+        send[:o_p] = torch.from_numpy(small)
+        if count:
+            fview(send, o_p, count).copy_(torch.from_numpy(np.ascontiguousarray(plain_h[:count], np.float32)))
+            flip_src = table.flip_host if lazy else flip_h
+            fview(send, o_f, count).copy_(torch.from_numpy(np.ascontiguousarray(flip_src[:count], np.float32)))
+    recv = torch.empty((world, nbytes), dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(recv.view(-1), send, group=group)
+    base = sum(counts)
+    plain_all = torch.cat([fview(recv[r], o_p, counts[r]) for r in range(world)], 0) if base else torch.zeros((1, L.FEAT_DIM), device=dev)
+    flip_all = torch.cat([fview(recv[r], o_f, counts[r]) for r in range(world)], 0) if base else torch.zeros((1, L.FEAT_DIM), device=dev)
+    if backend_cuda:
+        # host copies (the replay hands bank offers a host vector): pinned, one copy per array
+        small_h = torch.empty((world, o_p), dtype=torch.uint8).pin_memory()
+        small_h.copy_(recv[:, :o_p], non_blocking=True)
+        ph = torch.empty((max(base, 1), L.FEAT_DIM), dtype=torch.float32).pin_memory()
+        fh = torch.empty((max(base, 1), L.FEAT_DIM), dtype=torch.float32).pin_memory()
+        if base:
+            ph[:base].copy_(plain_all, non_blocking=True)
+            fh[:base].copy_(flip_all, non_blocking=True)
         torch.cuda.current_stream().synchronize()
-    plain_all = allp.to(eng.tdev).contiguous() if eng is not None else allp
-    flip_all = allf.to(eng.tdev).contiguous() if eng is not None else allf.clone()
-    plain_host = allp[:base].cpu().numpy()
-    flip_host = allf[:base].cpu().numpy().copy()
+        eng.stream.wait_stream(torch.cuda.current_stream())
+        plain_all, flip_all = plain_all.contiguous(), flip_all.contiguous()
+        small_np, plain_host, flip_host = small_h.numpy(), ph[:base].numpy(), fh[:base].numpy()
+    else:
+        small_np = recv[:, :o_p].numpy()
+        plain_host, flip_host = plain_all[:base].numpy().copy(), flip_all[:base].numpy().copy()
+        if eng is not None:
+            plain_all, flip_all = plain_all.to(eng.tdev).contiguous(), flip_all.to(eng.tdev).contiguous()
+        else:
+            flip_all = flip_all.clone()
+    metas, quals, areas, readies = [], [], [], []
+    row0 = 0
+    for r in range(world):
+        row = np.ascontiguousarray(small_np[r])
+        m = row[o_meta:o_meta + n_samples[r] * L.REPLAY_META * 4].view(np.int32).reshape(-1, L.REPLAY_META).copy()
+        for c0 in (0, 6, 8):
+            m[:, c0] = np.where(m[:, c0] >= 0, m[:, c0] + row0, -1)
+        metas.append(m)
+        quals.append(row[o_q:o_q + counts[r] * 8].view(np.float64).copy())
+        areas.append(row[o_a:o_a + counts[r] * 8].view(np.int64).copy())
+        readies.append(row[o_r:o_r + counts[r]].astype(bool))
+        row0 += counts[r]
     if lazy:
-        ready = np.concatenate([np.asarray(p[4], bool) for p in parts]) if base else np.zeros((0,), bool)
-        new = _ShardedTable(table, counts, rank, group, plain_all, flip_all, ready, flip_host)
+        ready = np.concatenate(readies) if base else np.zeros((0,), bool)
+        new = _ShardedTable(table, counts, rank, group, plain_all, flip_all, ready, np.ascontiguousarray(flip_host, np.float32))
     else:
         new = FaceTable()
         new.count = base

@@ -28,3 +28,12 @@ def engine_25g_r50():
     eng = Engine(0, scrfd="scrfd_2.5g_bnkps", arcface="arcface_r50")
     yield eng
     eng.close()
+
+
+@pytest.fixture(scope="session")
+def engine_10g_r100():
+    """SCRFD-10G + ArcFace R100: the models BASELINE configs 2-5 (and bench.py) are quoted on."""
+    from person_capture_b200.engine import Engine
+    eng = Engine(0, scrfd="scrfd_10g_bnkps", arcface="arcface_r100")
+    yield eng
+    eng.close()

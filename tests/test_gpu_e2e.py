@@ -132,19 +132,27 @@ def _band(log, cfg, tol=FD_TOL_E2E):
     return False
 
 
+_ORACLE_RUNS = {}
+
+
 @pytest.mark.parametrize("driver", ["sequential", "batched"])
-@pytest.mark.parametrize("seed,stride", [(1001, 6), (1002, 3)])
+@pytest.mark.parametrize("seed,stride", [(1005, 6), (1006, 3), (1008, 3)])
 def test_prescan_spans_match_oracle(engine_25g_r50, driver, seed, stride):
-    """Kept spans and bank size identical to the oracle's sequential pre-scan; per-sample best fd within 1e-3."""
+    """Kept spans, bank size and every per-sample decision identical to the oracle's sequential pre-scan; per-sample best fd
+    within the end-to-end tolerance.  The seeds were chosen with the CPU oracle so that NO sample's best fd lies within
+    the tolerance band of a threshold (margins 0.017 / 0.032 / 0.046, asserted below): nothing in this test is conditional."""
     from oracle import prescan as OP
     from person_capture_b200 import prescan as PS
     from person_capture_b200.face_embedder import FaceEmbedder
     cfg, clip, ref_img = _make_case(seed, 640, 360, 144, stride)
     frames = [clip.frame(i) for i in range(clip.n_frames)]
-    ora = H.oracle_embedder("scrfd_2.5g_bnkps", "arcface_r50", conf=cfg.face_det_conf)
-    obank = OP.build_reference_bank(ora, [ref_img], cfg)
-    olog = []
-    ospans, obank2 = OP.prescan(lambda i: frames[i] if i < len(frames) else None, 24, len(frames), ora, obank, cfg, log=olog)
+    if (seed, stride) not in _ORACLE_RUNS:       # the CPU oracle run is shared by the two drivers
+        ora = H.oracle_embedder("scrfd_2.5g_bnkps", "arcface_r50", conf=cfg.face_det_conf)
+        obank = OP.build_reference_bank(ora, [ref_img], cfg)
+        olog = []
+        ospans, obank2 = OP.prescan(lambda i: frames[i] if i < len(frames) else None, 24, len(frames), ora, obank, cfg, log=olog)
+        _ORACLE_RUNS[(seed, stride)] = (obank, olog, ospans, obank2)
+    obank, olog, ospans, obank2 = _ORACLE_RUNS[(seed, stride)]
 
     face = FaceEmbedder("cuda:0", "scrfd_2.5g_bnkps", conf=cfg.face_det_conf, engine=engine_25g_r50)
     gbank = PS.build_reference_bank(face, [ref_img], cfg)
@@ -158,16 +166,13 @@ def test_prescan_spans_match_oracle(engine_25g_r50, driver, seed, stride):
     gspans, gbank2 = fn(src, 24, face, gbank, cfg, log=glog, **kw)
 
     assert [r["idx"] for r in glog] == [r["idx"] for r in olog]
-    near = _band(olog, cfg)
+    assert not _band(olog, cfg), "seed puts an oracle sample inside the tolerance band of a threshold: pick another seed"
     for g, o in zip(glog, olog):
-        if not near:
-            assert g["skip"] == o["skip"] and g["nfaces"] == o["nfaces"], (g, o)
-        if g["skip"] == o["skip"] and g["nfaces"] == o["nfaces"]:
-            assert abs(g["best"] - o["best"]) <= FD_TOL_E2E, (g, o)
-    if not near:
-        assert gspans == ospans, (gspans, ospans)
-        assert np.asarray(gbank2).shape == np.asarray(obank2).shape
-    assert len(ospans) >= 1      # the case must actually exercise span building
+        assert g["skip"] == o["skip"] and g["nfaces"] == o["nfaces"] and g["active_before"] == o["active_before"], (g, o)
+        assert abs(g["best"] - o["best"]) <= FD_TOL_E2E, (g, o)
+    assert gspans == ospans, (gspans, ospans)
+    assert np.asarray(gbank2).shape == np.asarray(obank2).shape
+    assert len(ospans) >= 2 and np.asarray(obank2).shape[0] > np.asarray(obank).shape[0]   # spans were built and the bank grew
 
 
 def test_arcface_distance_same_chips(engine_25g_r50):

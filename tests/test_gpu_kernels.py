@@ -94,8 +94,8 @@ def _scrfd_heads(eng, name, blob_img, S, impl):
 @pytest.mark.parametrize("name,fix,S", [("scrfd_2.5g_bnkps", "engine_25g_r50", 320), ("scrfd_10g_bnkps", "engine_10g_r50", 512)])
 @pytest.mark.parametrize("impl", [1, 2, 0])
 def test_scrfd_heads_match_oracle(request, name, fix, S, impl):
-    """fp16 conv path vs fp32 oracle on identical weights: head maps agree to 2e-2 absolute on logits
-    / distances (values are O(1..10)); impl 1 = CUDA-core validation kernel, 2 = first tcgen05 formulation,
+    """fp16 conv path (fp16 storage, fp32 accumulate, ~40 layers) vs fp32 oracle on identical weights: head maps agree to
+    0.06 absolute in the worst element and 4e-3 on average on logits / distances (values are O(1..10)); impl 1 = CUDA-core validation kernel, 2 = first tcgen05 formulation,
     0 = product tcgen05 kernel (operand reuse in shared memory)."""
     eng = request.getfixturevalue(fix)
     from person_capture_b200 import synth, _lib as L
@@ -331,3 +331,34 @@ def test_match_against_numpy(engine_25g_r50):
     _, sim0, _ = eng.match(_dev(eng, emb), None, None, f)
     eng.sync()
     assert np.all(1.0 - sim0.cpu().numpy() == 9.0)                      # reference sentinel fd = 9.0
+
+
+# ---------------------------------------------------------------- context lifecycle
+def test_engine_recreate_keeps_results_bit_exact():
+    """The reference app rebuilds its FaceEmbedder on every run: destroy + create must not inherit scratch (K4 buffers,
+    letterbox coefficient tables) of the freed context.  Three generations of engines, same inputs, identical bytes."""
+    from person_capture_b200 import synth
+    from person_capture_b200.engine import Engine
+    rng = np.random.default_rng(17)
+    clip = synth.ClipSpec(416, 234, 12, seed=5, target_segments=[(0, 11)])
+    frames = np.stack([clip.frame(i) for i in (1, 4, 7)])
+    outs = []
+    for gen in range(3):
+        eng = Engine(0, scrfd="scrfd_2.5g_bnkps", arcface=None)
+        if gen == 1:
+            # churn the allocator between generations so a stale pointer would land in live data
+            junk = [eng.zeros((1 << 20,), torch.float32) for _ in range(8)]
+            del junk
+        dev = eng.to_device(frames)
+        patches, det_img = eng.letterbox(dev, 416, want_det_img=True)
+        det = eng.detect(dev, 416, 0.5)
+        al = eng.align(dev, det, max_faces=32)
+        eng.sync()
+        n = int(al.face_total.cpu()[0])
+        outs.append((det_img.cpu().numpy().copy(), patches.cpu().numpy().copy(), n, al.chips[:n].cpu().numpy().copy(),
+                     al.quality[:n].cpu().numpy().copy(), al.face_box[:n].cpu().numpy().copy()))
+        eng.close()
+    assert outs[0][2] >= 3
+    for o in outs[1:]:
+        for a, b in zip(outs[0], o):
+            assert np.array_equal(a, b)
