@@ -362,3 +362,81 @@ def test_engine_recreate_keeps_results_bit_exact():
     for o in outs[1:]:
         for a, b in zip(outs[0], o):
             assert np.array_equal(a, b)
+
+
+# ---------------------------------------------------------------- K4: eye-roll fallback (a10)
+def _planted_fallback_points(rng, side, roll, mode):
+    """Five landmarks of a face rolled by `roll` degrees inside a side x side crop that _canon_5pts REJECTS.  _canon_5pts
+    re-labels the points by (y, x) order, so it only fails on ties; mode "tie": the two lowest points get the same x
+    (they separate again once the crop is rotated upright -> rotate + align), "twin": the two lowest points coincide (still
+    tied after any rotation -> rotate + plain resize), "eyes": the detector's two eye points coincide (the roll then comes
+    from the mouth corners)."""
+    from person_capture_b200 import synth
+    pts = (synth.ARC_DST / 112.0 * side).astype(np.float64)
+    a = np.deg2rad(roll)
+    R = np.array([[np.cos(a), -np.sin(a)], [np.sin(a), np.cos(a)]])
+    pts = ((pts - side / 2.0) @ R.T + side / 2.0 + rng.normal(0, 0.01 * side, (5, 2))).astype(np.float32)
+    lo = np.argsort(pts[:, 1])[3:]
+    if mode == "tie":
+        pts[lo[1], 0] = pts[lo[0], 0]
+    elif mode == "twin":
+        pts[lo[1]] = pts[lo[0]]
+    elif mode == "eyes":
+        pts[1] = pts[0]
+    return pts
+
+
+def test_eye_roll_branches_bit_exact(engine_25g_r50):
+    """_upright_by_eye_roll (face_embedder.py:1571-1647) with planted NON-canonical landmarks: rolled faces (|angle| >= 8 deg ->
+    rotate the crop, re-canonicalise, align: kind 1), rolled with coincident points (rotate, then plain resize: kind 2), small
+    rolls (plain resize: kind 3), crops larger than 256 px (rotation with scale < 1), angles beyond 80 deg (snapped to 90) and
+    the mouth-vector fallback.  Chips must equal the oracle's cv2 calls bit for bit wherever the similarity fit agrees (same
+    rule as test_align_chips_bit_exact)."""
+    from oracle import face_embedder as OF
+    from person_capture_b200 import synth
+    from person_capture_b200.engine import DetectResult
+    eng = engine_25g_r50
+    rng = np.random.default_rng(23)
+    Hh, Ww, max_det = 700, 1100, 16
+    cases = [(120, 25.0, "tie"), (90, -40.0, "tie"), (150, 85.0, "tie"), (200, 120.0, "tie"), (330, 30.0, "tie"), (300, -100.0, "tie"),
+             (140, 35.0, "twin"), (100, -20.0, "twin"), (160, 50.0, "eyes"), (64, 9.0, "tie"), (180, 1.0, "twin"), (110, 170.0, "tie")]
+    n = 2
+    frames = np.stack([synth.background(rng, Hh, Ww) for _ in range(n)])
+    acc_box = np.zeros((n, max_det, 4), np.int32)
+    acc_kps = np.zeros((n, max_det, 10), np.float32)
+    acc_score = np.zeros((n, max_det), np.float32)
+    acc_count = np.zeros((n,), np.int32)
+    slots = [(10, 10), (350, 10), (10, 350), (350, 350), (690, 10), (690, 350)]      # non-overlapping top-left corners
+    per = len(cases) // n
+    for i in range(n):
+        for k, (side, roll, mode) in enumerate(cases[i * per:(i + 1) * per]):
+            x1, y1 = slots[k]
+            acc_box[i, k] = (x1, y1, x1 + side, y1 + side)
+            acc_kps[i, k] = _planted_fallback_points(rng, side, roll, mode).reshape(-1)
+            acc_score[i, k] = np.float32(0.9 - 0.01 * k)
+        acc_count[i] = per
+    det = DetectResult(None, None, None, _dev(eng, acc_box), _dev(eng, acc_kps), _dev(eng, acc_score), _dev(eng, acc_count), None)
+    al = eng.align(_dev(eng, frames), det, max_faces=64)
+    eng.sync()
+    total = int(al.face_total.cpu()[0])
+    assert total == len(cases)
+    kinds = al.face_kind[:total].cpu().numpy()
+    gi = exact = 0
+    for i in range(n):
+        for k in range(per):
+            x1, y1, x2, y2 = [int(v) for v in acc_box[i, k]]
+            pts = acc_kps[i, k].reshape(5, 2)
+            crop = frames[i][y1:y2, x1:x2]
+            assert OF.canon_5pts(pts) is None, (i, k)           # every planted case takes the fallback
+            chip = OF.upright_by_eye_roll(crop, pts)
+            got = al.chips[gi].cpu().numpy()
+            assert tuple(al.face_box[gi].cpu().numpy()) == (x1, y1, x2, y2)
+            if np.array_equal(got, chip):
+                exact += 1
+            else:
+                assert np.abs(got.astype(int) - chip.astype(int)).max() <= 2 and (got != chip).mean() < 0.02, (i, k, int(kinds[gi]))
+            q = OF.face_quality(got)
+            assert abs(float(al.quality[gi].cpu()) - q) <= 1e-9 * max(1.0, q)
+            gi += 1
+    assert set(int(v) for v in kinds) >= {1, 2, 3}, kinds          # rotate+align, rotate+resize and plain resize all occurred
+    assert exact >= total - 1, (exact, total)
