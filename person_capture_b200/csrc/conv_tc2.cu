@@ -99,6 +99,7 @@ struct Conv2Params {
   // are fetched), so the GEMM runs on the OUTPUT grid instead of computing all input positions and dropping 3 of 4
   int strided;
   int tma_store;   // 1: fp16 outputs leave through TMA stores of the staged 32-row x 32-channel chunk (stride-1 spatial layers)
+  int epi_row_split;   // 1: the two epilogue warps of a TMEM lane quarter take one 128-row sub-tile each (all columns); 0: one column half each
   int pair;        // 1: 2-CTA cluster, cta_group::2 (m_tiles counts PAIR tiles of 2*mt*128 rows; b_bytes is this CTA's half stage)
   int s_bx, s_by, s_nb;        // output pixels / output rows / images per tile
   int s_tx, s_ty;              // tiles per output row / per image column of rows
@@ -325,6 +326,25 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
         "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
         "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t (&v)[64]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,"
+      "%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,"
+      "%48,%49,%50,%51,%52,%53,%54,%55,%56,%57,%58,%59,%60,%61,%62,%63}, [%64];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]),
+        "=r"(v[32]), "=r"(v[33]), "=r"(v[34]), "=r"(v[35]), "=r"(v[36]), "=r"(v[37]), "=r"(v[38]), "=r"(v[39]),
+        "=r"(v[40]), "=r"(v[41]), "=r"(v[42]), "=r"(v[43]), "=r"(v[44]), "=r"(v[45]), "=r"(v[46]), "=r"(v[47]),
+        "=r"(v[48]), "=r"(v[49]), "=r"(v[50]), "=r"(v[51]), "=r"(v[52]), "=r"(v[53]), "=r"(v[54]), "=r"(v[55]),
+        "=r"(v[56]), "=r"(v[57]), "=r"(v[58]), "=r"(v[59]), "=r"(v[60]), "=r"(v[61]), "=r"(v[62]), "=r"(v[63])
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
@@ -754,25 +774,39 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
   } else {
     // ===================== epilogue (warps 4..11) =====================
+    // Work split: TMEM lane quarter q = warp % 4 (hardware rule), h = the other bit.  Layers with n_tile <= 64 and two
+    // sub-tiles give sub-tile h to the warp (all columns); otherwise h selects a column half.  A warp's columns are walked
+    // in chunks of 64 (one tcgen05.ld.x64) with a trailing 32-column chunk where the span needs it; everything per chunk
+    // that does not depend on the data (tile decode, row decode, accumulator hand-shake) is hoisted to the tile / sub-tile
+    // level: ncu showed ~240 of the ~340 instructions per 32-column chunk of the previous flat loop were such overhead, and
+    // with two epilogue warps per scheduler the layers with N <= 128 ran at the latency of that instruction stream.
     asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
-    const int half = (warp - kEpiWarp0) >> 2;     // column half
+    const int half = (warp - kEpiWarp0) >> 2;
     const int row_in_tile = q * 32 + lane;
-    // column range of this warp inside an n-tile, in 32-column chunks
+    const bool row_split = p.epi_row_split != 0;
     const int split = ((p.n_tile / 2 + 31) / 32) * 32;
-    const int col_lo = half ? split : 0;
-    const int col_hi = half ? p.n_tile : (split < p.n_tile ? split : p.n_tile);
-    const int nch = col_hi > col_lo ? (col_hi - col_lo + 31) / 32 : 0;     // chunks per 128-row sub-tile for this warp
+    const int col_lo = row_split ? 0 : (half ? split : 0);
+    const int col_hi = row_split ? p.n_tile : (half ? p.n_tile : (split < p.n_tile ? split : p.n_tile));
+    const int span = col_hi > col_lo ? col_hi - col_lo : 0;
+    const int n64 = span >> 6;                                  // 64-column chunks per sub-tile
+    const int nch = n64 + (((span & 63) + 31) >> 5);            // + one 32-column chunk for the rest
+    const int j_lo = row_split ? half : 0, j_n = row_split ? 1 : p.mt;
     // per-channel vectors, as shared-memory byte addresses (explicit ld.shared: through a generic pointer these were LD.E)
     const uint32_t v_scale = smem_u32(vec), v_bias = v_scale + 4u * p.vec_n, v_slope = v_scale + 8u * p.vec_n,
                    v_scale2 = v_scale + 12u * p.vec_n, v_bias2 = v_scale + 16u * p.vec_n;
     // this warp's 2 KB transpose buffer: 32 rows x 64 B (32 fp16 channels), 16-byte pieces XOR-swizzled by
     // (row >> 1) & 3 so that both the row-wise writes and the 4-lanes-per-row read-back are conflict-free
     uint8_t* stg = stage_buf + (warp - kEpiWarp0) * 2048;
-    const uint32_t stg_w = smem_u32(stg) + (uint32_t)(lane * 64);          // my row, as writer
+    const uint32_t stg_a = smem_u32(stg);
+    const uint32_t stg_w = stg_a + (uint32_t)(lane * 64);                  // my row, as writer
     const int w_sw = (lane >> 1) & 3;
     const int rb_piece = lane & 3;                                          // as reader: piece rb_piece of row i*8 + lane/4
     const uint32_t tempty_l0 = kPair ? leader_addr(&tempty_bar[0]) : 0u, tempty_l1 = kPair ? leader_addr(&tempty_bar[1]) : 0u;
+    const bool use_tma_store = !kStrided && p.tma_store != 0;
+    const int n_tiles = p.n_tiles, n_tile = p.n_tile, sub_cols = p.sub_cols;
+    const int out_c_store = p.out_c_store;
+    const int step_q = tile_step / n_tiles, step_r = tile_step - step_q * n_tiles;      // tile -> (m tile, n tile) without divisions
     int acc = 0;
     uint32_t acc_phase = 0;
     bool ok = true;
@@ -794,90 +828,210 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
     };
     if (nch == 0) {
-      // no columns for this warp (n_tile <= 32, upper half): it only takes part in the accumulator hand-shake
+      // no columns for this warp: it only takes part in the accumulator hand-shake
       for (int ti = 0; ti < my_tiles; ++ti) {
         ok = __all_sync(0xffffffffu, mbar_wait(&tfull_bar[acc], acc_phase, p.err, 104));
         if (!ok) break;
         tile_done();
       }
     } else {
-      // The warp's work is the flat sequence g = 0 .. my_tiles*S-1 of 32-column chunks, S = mt*nch per tile, in the order
-      // (tile, sub-tile j, chunk c).  Residual rows are fetched FOUR chunks ahead of their use into a ring of four register
-      // sets (static slot = g & 3 through the 4x unrolled inner loop), i.e. at least one whole tile ahead: with the fetch
-      // issued at the start of the tile that needs it, the narrow residual layers (one or two chunks per tile and warp)
-      // exposed a global-memory latency per chunk and ran epilogue-bound (MMA warp waiting on TMEM 14-27 % of the time).
-      const int S = p.mt * nch;
-      const int G = my_tiles * S;
-      uint4 R[4][4];
-      // the prefetch stream runs four chunks ahead of the consumer; (p_tile, p_j, p_c) is its position, p_row its row
-      int p_g = 0, p_tile = tile0, p_j = 0, p_c = 0;
-      RowInfo p_row;
-      p_row.valid = false;
-      p_row.orow = 0;
-      int p_n0 = 0;
-      auto res_load = [&](uint4 (&dst)[4]) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) dst[e] = make_uint4(0, 0, 0, 0);
-        if (p_g >= G) return;
-        if (p_c == 0) {
-          const int mt_idx = p_tile / p.n_tiles;
-          p_n0 = (p_tile - mt_idx * p.n_tiles) * p.n_tile;
-          p_row = row_info<kStrided>(p, (long long)(kPair ? 2 * mt_idx + cta_rank : mt_idx) * tile_rows + p_j * kBlockM + row_in_tile);
-        }
-        const int ch = p_n0 + col_lo + p_c * 32;
-        if (p_row.valid) {
-          const __half* src = p.residual + p_row.orow * p.res_cp + ch;
-          if (ch + 32 <= p.out_c_store) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) dst[e] = *(const uint4*)(src + e * 8);
-          } else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-              if (ch + e * 8 < p.out_c_store) dst[e] = *(const uint4*)(src + e * 8);
-          }
-        }
-        ++p_g;
-        if (++p_c == nch) {
-          p_c = 0;
-          if (++p_j == p.mt) {
-            p_j = 0;
-            p_tile += tile_step;
+      // position in this warp's chunk sequence: (tile, sub-tile, chunk), with the tile decoded incrementally
+      struct Pos {
+        int j, c, mt_idx, nt;
+      };
+      auto advance = [&](Pos& s) {
+        if (++s.c == nch) {
+          s.c = 0;
+          if (++s.j == j_n) {
+            s.j = 0;
+            s.mt_idx += step_q;
+            s.nt += step_r;
+            if (s.nt >= n_tiles) { s.nt -= n_tiles; ++s.mt_idx; }
           }
         }
       };
-      if (kRes) {
+      auto first_row = [&](const Pos& s) {
+        return (long long)(kPair ? 2 * s.mt_idx + cta_rank : s.mt_idx) * tile_rows + (j_lo + s.j) * kBlockM + row_in_tile;
+      };
+      auto chunk_col = [&](int c) { return col_lo + (c < n64 ? c * 64 : n64 * 64 + (c - n64) * 32); };
+      const int G = my_tiles * j_n * nch;
+      const int t0_m = tile0 / n_tiles;
+      // residual rows are fetched TWO chunks ahead of their use (64-column chunks: the same bytes in flight as the four
+      // 32-column chunks of the previous loop) into two register sets, static slot through the 2x unrolled loop
+      uint4 R[2][8];
+      Pos pf{0, 0, t0_m, tile0 - t0_m * n_tiles};
+      int pf_g = 0;
+      RowInfo pf_row;
+      pf_row.valid = false;
+      pf_row.orow = 0;
+      auto res_load = [&](uint4 (&dst)[8]) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) res_load(R[u]);
+        for (int e = 0; e < 8; ++e) dst[e] = make_uint4(0, 0, 0, 0);
+        if (pf_g >= G) return;
+        if (pf.c == 0) pf_row = row_info<kStrided>(p, first_row(pf));
+        const int ch = pf.nt * n_tile + chunk_col(pf.c);
+        const int wpieces = pf.c < n64 ? 8 : 4;
+        if (pf_row.valid) {
+          const __half* src = p.residual + pf_row.orow * p.res_cp + ch;
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            if (e < wpieces && ch + e * 8 < out_c_store) dst[e] = *(const uint4*)(src + e * 8);
+        }
+        ++pf_g;
+        advance(pf);
+      };
+      if (kRes) {
+        res_load(R[0]);
+        res_load(R[1]);
       }
-      int ti = 0, j = 0, c = 0;            // decode of g, advanced incrementally
+      Pos cur{0, 0, t0_m, tile0 - t0_m * n_tiles};
       int n0 = 0;
       long long row0 = 0;
       RowInfo ri;
       ri.valid = false;
       ri.orow = 0;
-      // rows this lane writes back after the transpose: i*8 + lane/4, i = 0..3, as element offsets of piece rb_piece
+      // rows this lane writes back after the transpose (per-lane store path): i*8 + lane/4, i = 0..3, as element offsets of piece rb_piece
       long long woff[4] = {0, 0, 0, 0}, woff2[4] = {0, 0, 0, 0};
       bool wvalid[4] = {false, false, false, false};
+      int prow32 = 0;
       long long te0 = 0;
-      for (int g0 = 0; ok && g0 < G; g0 += 4) {
+
+      // one 32-column piece of a chunk: y = acc*scale+bias (+residual) -> activation -> store (+ second output)
+      auto piece = [&](const uint32_t* v, const uint4* res4, int ch) {
+        float y[32];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int g = g0 + u;
-          if (g >= G) break;
-          if (j == 0 && c == 0) {
+        for (int e = 0; e < 8; ++e) {
+          const float4 s4 = ld_shared_f4(v_scale + 4u * (uint32_t)(ch + e * 4));
+          const float4 b4 = ld_shared_f4(v_bias + 4u * (uint32_t)(ch + e * 4));
+          y[e * 4 + 0] = fmaf(__uint_as_float(v[e * 4 + 0]), s4.x, b4.x);
+          y[e * 4 + 1] = fmaf(__uint_as_float(v[e * 4 + 1]), s4.y, b4.y);
+          y[e * 4 + 2] = fmaf(__uint_as_float(v[e * 4 + 2]), s4.z, b4.z);
+          y[e * 4 + 3] = fmaf(__uint_as_float(v[e * 4 + 3]), s4.w, b4.w);
+        }
+        if (kOutMode == 2) {
+          if (ri.valid) {
+            float* o = p.out_f32 + ri.orow * p.out_f32_stride + ch;
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              if (ch + e * 4 < p.out_f32_cols) *(float4*)(o + e * 4) = make_float4(y[e * 4], y[e * 4 + 1], y[e * 4 + 2], y[e * 4 + 3]);
+          }
+          return;
+        }
+        if (kRes) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float f[8];
+            unpack_h8(res4[e], f);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) y[e * 8 + k] += f[k];
+          }
+        }
+        if (kAct == PCB_ACT_RELU) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) y[e] = fmaxf(y[e], 0.f);
+        } else if (kAct == PCB_ACT_PRELU) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float4 a4 = ld_shared_f4(v_slope + 4u * (uint32_t)(ch + e * 4));
+            y[e * 4 + 0] = y[e * 4 + 0] >= 0.f ? y[e * 4 + 0] : y[e * 4 + 0] * a4.x;
+            y[e * 4 + 1] = y[e * 4 + 1] >= 0.f ? y[e * 4 + 1] : y[e * 4 + 1] * a4.y;
+            y[e * 4 + 2] = y[e * 4 + 2] >= 0.f ? y[e * 4 + 2] : y[e * 4 + 2] * a4.z;
+            y[e * 4 + 3] = y[e * 4 + 3] >= 0.f ? y[e * 4 + 3] : y[e * 4 + 3] * a4.w;
+          }
+        }
+        if (kOutMode == 1) {
+          if (ri.valid) {
+            float* o = p.out_s32 + ri.orow * p.out_cp + ch;
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              if (ch + e * 4 < out_c_store) *(float4*)(o + e * 4) = make_float4(y[e * 4], y[e * 4 + 1], y[e * 4 + 2], y[e * 4 + 3]);
+          }
+          return;
+        }
+        auto second = [&]() {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float4 s4 = ld_shared_f4(v_scale2 + 4u * (uint32_t)(ch + e * 4));
+            const float4 b4 = ld_shared_f4(v_bias2 + 4u * (uint32_t)(ch + e * 4));
+            y[e * 4 + 0] = fmaf(y[e * 4 + 0], s4.x, b4.x);
+            y[e * 4 + 1] = fmaf(y[e * 4 + 1], s4.y, b4.y);
+            y[e * 4 + 2] = fmaf(y[e * 4 + 2], s4.z, b4.z);
+            y[e * 4 + 3] = fmaf(y[e * 4 + 3], s4.w, b4.w);
+          }
+        };
+        if (use_tma_store) {
+          // The piece (32 consecutive P-rows x 32 channels) is staged in the 64B-swizzled layout TMA expects and leaves
+          // through ONE bulk tensor store per output: no read-back, no per-row address arithmetic, asynchronous.  Rows
+          // that are not image pixels are staged as zeros, so the padding of the output stays zero; rows past the end of
+          // the tensor and channels past its width are clipped by the tensor map.
+          uint4 pk[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) pk[e] = ri.valid ? pack_h8(y + e * 8) : make_uint4(0, 0, 0, 0);
+          if (lane == 0) tma_store_wait_read();       // the previous store has finished reading the staging buffer
+          __syncwarp();
+#pragma unroll
+          for (int e = 0; e < 4; ++e) st_shared_v4(stg_w + (uint32_t)(((e ^ w_sw) & 3) * 16), pk[e]);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) tma_store_2d(&tmO, stg_a, ch, prow32);
+          if (kOut2) {
+            second();
+#pragma unroll
+            for (int e = 0; e < 4; ++e) pk[e] = ri.valid ? pack_h8(y + e * 8) : make_uint4(0, 0, 0, 0);
+            if (lane == 0) tma_store_wait_read();
+            __syncwarp();
+#pragma unroll
+            for (int e = 0; e < 4; ++e) st_shared_v4(stg_w + (uint32_t)(((e ^ w_sw) & 3) * 16), pk[e]);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) tma_store_2d(&tmO2, stg_a, ch, prow32);
+          }
+        } else {
+          // transpose through shared memory so that 4 lanes write one row's 64 contiguous bytes (full sectors)
+          const bool piece_ok = ch + rb_piece * 8 < out_c_store;
+          __syncwarp();      // the previous piece's read-back is done before the buffer is rewritten
+#pragma unroll
+          for (int e = 0; e < 4; ++e) st_shared_v4(stg_w + (uint32_t)(((e ^ w_sw) & 3) * 16), pack_h8(y + e * 8));
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = i * 8 + (lane >> 2);
+            const uint4 o4 = ld_shared_v4(stg_a + (uint32_t)(r * 64 + ((rb_piece ^ (r >> 1)) & 3) * 16));
+            if (wvalid[i] && piece_ok) *(uint4*)(p.out + woff[i] + ch) = o4;
+          }
+          if (kOut2) {
+            second();
+            __syncwarp();
+#pragma unroll
+            for (int e = 0; e < 4; ++e) st_shared_v4(stg_w + (uint32_t)(((e ^ w_sw) & 3) * 16), pack_h8(y + e * 8));
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int r = i * 8 + (lane >> 2);
+              const uint4 o4 = ld_shared_v4(stg_a + (uint32_t)(r * 64 + ((rb_piece ^ (r >> 1)) & 3) * 16));
+              if (wvalid[i] && piece_ok) *(uint4*)(p.out2 + woff2[i] + ch) = o4;
+            }
+          }
+        }
+      };
+
+      for (int g0 = 0; ok && g0 < G; g0 += 2) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          if (g0 + u >= G) break;
+          if (cur.j == 0 && cur.c == 0) {
             // first chunk of a tile: wait for its accumulator
-            const int tile = tile0 + ti * tile_step;
-            const int mt_idx = tile / p.n_tiles, nt = tile - mt_idx * p.n_tiles;
-            n0 = nt * p.n_tile;
-            row0 = (long long)(kPair ? 2 * mt_idx + cta_rank : mt_idx) * tile_rows + row_in_tile;
-            ok = __all_sync(0xffffffffu, mbar_wait_t(&tfull_bar[acc], acc_phase, p.err, 104, w_full, p.dbg != nullptr));
+            n0 = cur.nt * n_tile;
+            ok = __all_sync(0xffffffffu, mbar_wait_t(&tfull_bar[acc], acc_phase, p.err, 104, w_full, timed));
             if (!ok) break;
             tc_fence_after();
-            if (timed) te0 = clock64();
           }
-          if (c == 0) {
-            ri = row_info<kStrided>(p, row0 + (long long)j * kBlockM);
-            if (kOutMode == 0) {
+          if (timed) te0 = clock64();
+          if (cur.c == 0) {
+            row0 = first_row(cur);
+            ri = row_info<kStrided>(p, row0);
+            prow32 = (int)(row0 - lane);                      // first P-row of this warp's 32 rows (TMA store coordinate)
+            if (kOutMode == 0 && !use_tma_store) {
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 const int src = i * 8 + (lane >> 2);
@@ -888,147 +1042,31 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               }
             }
           }
-          const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256 + j * p.sub_cols);
-          const int col = col_lo + c * 32;
-          {
-            uint32_t v[32];
-            __syncwarp();   // tcgen05.ld is .sync.aligned; also orders the previous read-back before this chunk's staging writes
-            long long tl0 = 0;
-            if (timed) tl0 = clock64();
-            tmem_ld32(t_row + col, v);
+          const bool wide = cur.c < n64;
+          const int col = chunk_col(cur.c);
+          const bool last = cur.j == j_n - 1 && cur.c == nch - 1;
+          const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256 + (j_lo + cur.j) * sub_cols + col);
+          const int ch = n0 + col;
+          __syncwarp();   // tcgen05.ld is .sync.aligned
+          long long tl0 = 0;
+          if (timed) tl0 = clock64();
+          if (wide) {
+            uint32_t v[64];
+            tmem_ld64(t_addr, v);
             if (timed) t_ld += clock64() - tl0;
-            const int ch = n0 + col;
-            float y[32];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const float4 s4 = ld_shared_f4(v_scale + 4u * (uint32_t)(ch + e * 4));
-              const float4 b4 = ld_shared_f4(v_bias + 4u * (uint32_t)(ch + e * 4));
-              y[e * 4 + 0] = fmaf(__uint_as_float(v[e * 4 + 0]), s4.x, b4.x);
-              y[e * 4 + 1] = fmaf(__uint_as_float(v[e * 4 + 1]), s4.y, b4.y);
-              y[e * 4 + 2] = fmaf(__uint_as_float(v[e * 4 + 2]), s4.z, b4.z);
-              y[e * 4 + 3] = fmaf(__uint_as_float(v[e * 4 + 3]), s4.w, b4.w);
-            }
-            if (kOutMode == 2) {
-              if (ri.valid) {
-                float* o = p.out_f32 + ri.orow * p.out_f32_stride + ch;
-#pragma unroll
-                for (int e = 0; e < 8; ++e)
-                  if (ch + e * 4 < p.out_f32_cols) *(float4*)(o + e * 4) = make_float4(y[e * 4], y[e * 4 + 1], y[e * 4 + 2], y[e * 4 + 3]);
-              }
-            } else {
-              if (kRes) {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  float f[8];
-                  unpack_h8(R[u][e], f);
-#pragma unroll
-                  for (int k = 0; k < 8; ++k) y[e * 8 + k] += f[k];
-                }
-              }
-              if (kAct == PCB_ACT_RELU) {
-#pragma unroll
-                for (int e = 0; e < 32; ++e) y[e] = fmaxf(y[e], 0.f);
-              } else if (kAct == PCB_ACT_PRELU) {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                  const float4 a4 = ld_shared_f4(v_slope + 4u * (uint32_t)(ch + e * 4));
-                  y[e * 4 + 0] = y[e * 4 + 0] >= 0.f ? y[e * 4 + 0] : y[e * 4 + 0] * a4.x;
-                  y[e * 4 + 1] = y[e * 4 + 1] >= 0.f ? y[e * 4 + 1] : y[e * 4 + 1] * a4.y;
-                  y[e * 4 + 2] = y[e * 4 + 2] >= 0.f ? y[e * 4 + 2] : y[e * 4 + 2] * a4.z;
-                  y[e * 4 + 3] = y[e * 4 + 3] >= 0.f ? y[e * 4 + 3] : y[e * 4 + 3] * a4.w;
-                }
-              }
-              if (kOutMode == 1) {
-                if (ri.valid) {
-                  float* o = p.out_s32 + ri.orow * p.out_cp + ch;
-#pragma unroll
-                  for (int e = 0; e < 8; ++e)
-                    if (ch + e * 4 < p.out_c_store) *(float4*)(o + e * 4) = make_float4(y[e * 4], y[e * 4 + 1], y[e * 4 + 2], y[e * 4 + 3]);
-                }
-              } else {
-                if (!kStrided && p.tma_store) {
-                  // The chunk (32 consecutive P-rows x 32 channels) is staged in the 64B-swizzled layout TMA expects and leaves
-                  // through ONE bulk tensor store per output: no read-back, no per-row address arithmetic, asynchronous.  Rows
-                  // that are not image pixels are staged as zeros, so the padding of the output stays zero; rows past the end of
-                  // the tensor and channels past its width are clipped by the tensor map.
-                  const int prow32 = (int)(row0 - row_in_tile) + j * kBlockM + q * 32;     // first P-row of this warp's 32 rows
-                  uint4 pk[4];
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) pk[e] = ri.valid ? pack_h8(y + e * 8) : make_uint4(0, 0, 0, 0);
-                  if (lane == 0) tma_store_wait_read();       // the previous store has finished reading the staging buffer
-                  __syncwarp();
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) st_shared_v4(stg_w + (uint32_t)(((e ^ w_sw) & 3) * 16), pk[e]);
-                  fence_proxy_async_smem();
-                  __syncwarp();
-                  if (lane == 0) tma_store_2d(&tmO, smem_u32(stg), ch, prow32);
-                  if (kOut2) {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                      const float4 s4 = ld_shared_f4(v_scale2 + 4u * (uint32_t)(ch + e * 4));
-                      const float4 b4 = ld_shared_f4(v_bias2 + 4u * (uint32_t)(ch + e * 4));
-                      y[e * 4 + 0] = fmaf(y[e * 4 + 0], s4.x, b4.x);
-                      y[e * 4 + 1] = fmaf(y[e * 4 + 1], s4.y, b4.y);
-                      y[e * 4 + 2] = fmaf(y[e * 4 + 2], s4.z, b4.z);
-                      y[e * 4 + 3] = fmaf(y[e * 4 + 3], s4.w, b4.w);
-                    }
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) pk[e] = ri.valid ? pack_h8(y + e * 8) : make_uint4(0, 0, 0, 0);
-                    if (lane == 0) tma_store_wait_read();
-                    __syncwarp();
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) st_shared_v4(stg_w + (uint32_t)(((e ^ w_sw) & 3) * 16), pk[e]);
-                    fence_proxy_async_smem();
-                    __syncwarp();
-                    if (lane == 0) tma_store_2d(&tmO2, smem_u32(stg), ch, prow32);
-                  }
-                } else {
-                // transpose through shared memory so that 4 lanes write one row's 64 contiguous bytes (full sectors)
-                  const bool piece_ok = ch + rb_piece * 8 < p.out_c_store;
-  #pragma unroll
-                  for (int e = 0; e < 4; ++e) st_shared_v4(stg_w + (uint32_t)(((e ^ w_sw) & 3) * 16), pack_h8(y + e * 8));
-                  __syncwarp();
-  #pragma unroll
-                  for (int i = 0; i < 4; ++i) {
-                    const int r = i * 8 + (lane >> 2);
-                    const uint4 o4 = ld_shared_v4(smem_u32(stg) + (uint32_t)(r * 64 + ((rb_piece ^ (r >> 1)) & 3) * 16));
-                    if (wvalid[i] && piece_ok) *(uint4*)(p.out + woff[i] + ch) = o4;
-                  }
-                  if (kOut2) {
-  #pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                      const float4 s4 = ld_shared_f4(v_scale2 + 4u * (uint32_t)(ch + e * 4));
-                      const float4 b4 = ld_shared_f4(v_bias2 + 4u * (uint32_t)(ch + e * 4));
-                      y[e * 4 + 0] = fmaf(y[e * 4 + 0], s4.x, b4.x);
-                      y[e * 4 + 1] = fmaf(y[e * 4 + 1], s4.y, b4.y);
-                      y[e * 4 + 2] = fmaf(y[e * 4 + 2], s4.z, b4.z);
-                      y[e * 4 + 3] = fmaf(y[e * 4 + 3], s4.w, b4.w);
-                    }
-                    __syncwarp();
-  #pragma unroll
-                    for (int e = 0; e < 4; ++e) st_shared_v4(stg_w + (uint32_t)(((e ^ w_sw) & 3) * 16), pack_h8(y + e * 8));
-                    __syncwarp();
-  #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                      const int r = i * 8 + (lane >> 2);
-                      const uint4 o4 = ld_shared_v4(smem_u32(stg) + (uint32_t)(r * 64 + ((rb_piece ^ (r >> 1)) & 3) * 16));
-                      if (wvalid[i] && piece_ok) *(uint4*)(p.out2 + woff2[i] + ch) = o4;
-                    }
-                  }
-                }
-              }
-            }
-                }
-          if (kRes) res_load(R[u]);     // this slot's next use: four chunks from now
-          if (++c == nch) {
-            c = 0;
-            if (++j == p.mt) {
-              j = 0;
-              ++ti;
-              tile_done();
-              if (timed) t_epi += clock64() - te0;
-            }
+            if (last) tile_done();          // the accumulator is in registers: hand it back before the arithmetic
+            piece(v, R[u], ch);
+            piece(v + 32, R[u] + 4, ch + 32);
+          } else {
+            uint32_t v[32];
+            tmem_ld32(t_addr, v);
+            if (timed) t_ld += clock64() - tl0;
+            if (last) tile_done();
+            piece(v, R[u], ch);
           }
+          if (kRes) res_load(R[u]);     // this slot's next use: two chunks from now
+          advance(cur);
+          if (timed) t_epi += clock64() - te0;
         }
       }
     }
@@ -1298,6 +1336,9 @@ int pcb_conv_tc2(pcb_ctx* c, const ConvArgs& a) {
     if (p.mt == 2) p.n_iss = 2;
     else if (w.n_tile % 32 == 0) { p.n_iss = 2; p.split_n = 1; }
   }
+  // epilogue split: narrow layers with two sub-tiles give each warp of a lane quarter its own sub-tile (one 64-column chunk
+  // per tile, and no idle warps when n_tile <= 32); everything else splits the columns
+  p.epi_row_split = (p.mt == 2 && w.n_tile <= 64 && !env_int("PCB_EPI_NO_ROWSPLIT", 0)) ? 1 : 0;
   p.b_nloads = (p.pair && p.split_n) ? 2 : 1;
   p.b_load_rows = p.b_rows / p.b_nloads;
   p.b_resident = 0;
