@@ -11,6 +11,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PCB_LIB") or os.path.join(_HERE, "libpcb200.so")   # PCB_LIB: A/B another build of the library
+VAL_LIB_PATH = os.path.join(_HERE, "libpcb200_val.so")   # product + the CUDA-core validation convolution (tests / tools only)
 
 # P-layout padding (csrc/pcb_common.cuh kPadLo / kPad): activations are [n][h + P_PAD][w + P_PAD][cp], image pixel (y, x) at
 # [y + P_PAD_LO][x + P_PAD_LO], zeros elsewhere.  load() overwrites these with what the loaded library reports (pcb_layout_pad).
@@ -103,18 +104,18 @@ class PcbError(RuntimeError):
     pass
 
 
-_lib = None
+_libs = {}
 
 
-def load():
-    """Load libpcb200.so; raises if it has not been built (python __graft_entry__.py build)."""
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not os.path.isfile(LIB_PATH):
-        raise PcbError(f"{LIB_PATH} not found: build it with `make -C person_capture_b200/csrc` "
+def load(path: str = None):
+    """Load libpcb200.so (or the library at `path`); raises if it has not been built (python __graft_entry__.py build)."""
+    path = path or LIB_PATH
+    if path in _libs:
+        return _libs[path]
+    if not os.path.isfile(path):
+        raise PcbError(f"{path} not found: build it with `make -C person_capture_b200/csrc` "
                        "(there is no CPU fallback for the identity path)")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     vp, i32, f32 = C.c_void_p, C.c_int, C.c_float
     lib.pcb_create.restype = vp
     lib.pcb_create.argtypes = [i32, vp]
@@ -165,5 +166,5 @@ def load():
     lib.pcb_layout_pad.restype = None
     lib.pcb_layout_pad(C.byref(lo), C.byref(pad))
     P_PAD_LO, P_PAD = lo.value, pad.value     # follow the library that was actually loaded (PCB_LIB A/B builds)
-    _lib = lib
+    _libs[path] = lib
     return lib

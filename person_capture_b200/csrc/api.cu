@@ -128,6 +128,9 @@ extern "C" void pcb_layout_pad(int* pad_lo, int* pad) {
 
 extern "C" int pcb_set_conv_impl(pcb_ctx* c, int impl) {
   if (impl < 0 || impl > 2) return pcb_fail(c, PCB_ERR_ARG, "conv impl must be 0..2");
+#ifndef PCB_VALIDATION_KERNEL
+  if (impl == 1) return pcb_fail(c, PCB_ERR_ARG, "the CUDA-core validation kernel is not part of the product library (load libpcb200_val.so)");
+#endif
   c->conv_impl = impl;
   return PCB_OK;
 }
@@ -406,7 +409,11 @@ static int model_run(pcb_ctx* c, Model* m, Model::Run* r) {
           }
         }
         w.n_tile = pick_n_tile(c, w, a.in->rows());
+#ifdef PCB_VALIDATION_KERNEL
         rc = c->conv_impl == 0 ? pcb_conv_tc2(c, a) : c->conv_impl == 2 ? pcb_conv_tc(c, a) : pcb_conv_simple(c, a);
+#else
+        rc = c->conv_impl == 2 ? pcb_conv_tc(c, a) : pcb_conv_tc2(c, a);
+#endif
         break;
       }
       case PCB_OP_AFFINE: rc = pcb_op_affine(c, r->t[op.in0], r->t[op.out], m->aff_scale[i], m->aff_bias[i]); break;

@@ -43,14 +43,14 @@ class AlignResult:
 
 class Engine:
     def __init__(self, device: int = 0, scrfd: Optional[str] = "scrfd_10g_bnkps", arcface: Optional[str] = "arcface_r100",
-                 scrfd_params=None, arcface_params=None):
+                 scrfd_params=None, arcface_params=None, lib_path: Optional[str] = None, stream_priority: int = 0):
         if not torch.cuda.is_available():
             raise L.PcbError("no CUDA device: the identity path has no CPU fallback")
-        self.lib = L.load()
+        self.lib = L.load(lib_path)
         self.device = int(device)
         self.tdev = torch.device("cuda", self.device)
         torch.cuda.set_device(self.device)
-        self.stream = torch.cuda.Stream(device=self.tdev)
+        self.stream = torch.cuda.Stream(device=self.tdev, priority=int(stream_priority))
         self.copy_stream = torch.cuda.Stream(device=self.tdev)   # H2D prefetch of the next frame batch (prescan.compute_superset)
         self.ctx = self.lib.pcb_create(self.device, C.c_void_p(self.stream.cuda_stream))
         if not self.ctx:

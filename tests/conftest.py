@@ -37,3 +37,22 @@ def engine_10g_r100():
     eng = Engine(0, scrfd="scrfd_10g_bnkps", arcface="arcface_r100")
     yield eng
     eng.close()
+
+
+@pytest.fixture(scope="session")
+def engines_val():
+    """Engines on libpcb200_val.so (product sources + the CUDA-core validation convolution, conv impl 1), built lazily per
+    (scrfd, arcface) pair: the product library itself does not contain that kernel."""
+    from person_capture_b200 import _lib
+    from person_capture_b200.engine import Engine
+    made = {}
+
+    def get(scrfd, arcface):
+        key = (scrfd, arcface)
+        if key not in made:
+            made[key] = Engine(0, scrfd=scrfd, arcface=arcface, lib_path=_lib.VAL_LIB_PATH)
+        return made[key]
+
+    yield get
+    for eng in made.values():
+        eng.close()

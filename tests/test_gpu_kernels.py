@@ -93,11 +93,11 @@ def _scrfd_heads(eng, name, blob_img, S, impl):
 
 @pytest.mark.parametrize("name,fix,S", [("scrfd_2.5g_bnkps", "engine_25g_r50", 320), ("scrfd_10g_bnkps", "engine_10g_r50", 512)])
 @pytest.mark.parametrize("impl", [1, 2, 0])
-def test_scrfd_heads_match_oracle(request, name, fix, S, impl):
+def test_scrfd_heads_match_oracle(request, engines_val, name, fix, S, impl):
     """fp16 conv path (fp16 storage, fp32 accumulate, ~40 layers) vs fp32 oracle on identical weights: head maps agree to
     0.06 absolute in the worst element and 4e-3 on average on logits / distances (values are O(1..10)); impl 1 = CUDA-core validation kernel, 2 = first tcgen05 formulation,
     0 = product tcgen05 kernel (operand reuse in shared memory)."""
-    eng = request.getfixturevalue(fix)
+    eng = engines_val(name, None) if impl == 1 else request.getfixturevalue(fix)
     from person_capture_b200 import synth, _lib as L
     clip = synth.ClipSpec(S, S, 10, seed=3, target_segments=[(0, 9)])
     img = clip.frame(2)
@@ -114,9 +114,9 @@ def test_scrfd_heads_match_oracle(request, name, fix, S, impl):
 
 
 @pytest.mark.parametrize("impl", [1, 2, 0])
-def test_arcface_embeddings_match_oracle(engine_25g_r50, impl):
+def test_arcface_embeddings_match_oracle(engine_25g_r50, engines_val, impl):
     """cosine(e_gpu, e_oracle) >= 0.999 (north_star tolerance) on R50, with and without flip."""
-    eng = engine_25g_r50
+    eng = engines_val(None, "arcface_r50") if impl == 1 else engine_25g_r50
     from person_capture_b200 import synth
     rng = np.random.default_rng(11)
     chips = []
@@ -440,3 +440,10 @@ def test_eye_roll_branches_bit_exact(engine_25g_r50):
             gi += 1
     assert set(int(v) for v in kinds) >= {1, 2, 3}, kinds          # rotate+align, rotate+resize and plain resize all occurred
     assert exact >= total - 1, (exact, total)
+
+
+def test_product_library_has_no_validation_kernel(engine_25g_r50):
+    from person_capture_b200 import _lib as L
+    with pytest.raises(L.PcbError):
+        engine_25g_r50.set_conv_impl(1)
+    engine_25g_r50.set_conv_impl(0)

@@ -15,7 +15,8 @@ ap.add_argument("--verbose", action="store_true")
 args = ap.parse_args()
 from person_capture_b200.engine import Engine
 from person_capture_b200 import _lib as L
-eng = Engine(0, scrfd=args.scrfd, arcface=args.arcface)
+from person_capture_b200 import _lib as _L
+eng = Engine(0, scrfd=args.scrfd, arcface=args.arcface, lib_path=_L.VAL_LIB_PATH)   # the validation kernel lives in the test-only library
 rng = np.random.default_rng(0)
 import cv2
 frames = np.stack([cv2.GaussianBlur(rng.integers(0, 256, (270, 480, 3), dtype=np.uint8), (0, 0), 1.5) for _ in range(args.n)])

@@ -6,7 +6,8 @@ import bench
 from person_capture_b200.engine import Engine
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 frames, _ = bench.make_pool(n)
-eng = Engine(0, scrfd="scrfd_10g_bnkps", arcface=None)
+from person_capture_b200 import _lib as _L
+eng = Engine(0, scrfd="scrfd_10g_bnkps", arcface=None, lib_path=_L.VAL_LIB_PATH)
 fd = eng.resize(eng.to_device(frames), 540, 960, area=True)
 res = {}
 for impl in (1, 2, 0):
