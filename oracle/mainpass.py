@@ -13,9 +13,10 @@ SURVEY.md App. C describes), what person_capture/gui_app.py does to decide "is t
   * lock-face box update on accept            gui_app.py:7501-7505 (_set_lock_face_box :4164-4177)
   * runtime bank learning (off by default)    gui_app.py:7460-7494
   * cooldown decrement                        gui_app.py:8003-8006
-Crop composition, person association, saving and the frame-level arbitration between several person candidates
-(gui_app.py:7792-7818) are product logic downstream of identity and out of scope: every site here yields at most one
-candidate, so arbitration is the identity.
+  * per-person-crop site (boxes given)      gui_app.py:6269-6346, 6370-6437   -> person_crop_candidates
+  * frame-level arbitration + lock gate       gui_app.py:7788-7845              -> arbitrate
+Crop composition (ratio choice, margins, sharpness of the composed crop), the person detector and saving are product logic
+downstream of identity and out of scope: candidates carry the person box as their area and sharp = 0.
 """
 from __future__ import annotations
 
@@ -189,3 +190,104 @@ def _fullframe_candidate(g, bank, face_thresh, W2, H2, site, rec):
     if fd <= face_thresh:
         return dict(site=site, fd=fd, feat=g["feat"], quality=float(g.get("quality", 0.0)), box=(fx1, fy1, fx2, fy2))
     return None
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# per-person-crop identity site and frame-level arbitration (SURVEY.md App. C rules 2-4)
+# ---------------------------------------------------------------------------------------------------------------
+def iou_xyxy(a, b) -> float:
+    """gui_app.py:3484-3493."""
+    ax1, ay1, ax2, ay2 = a
+    bx1, by1, bx2, by2 = b
+    iw, ih = max(0, min(ax2, bx2) - max(ax1, bx1)), max(0, min(ay2, by2) - max(ay1, by1))
+    inter = iw * ih
+    union = max(0, (ax2 - ax1) * (ay2 - ay1)) + max(0, (bx2 - bx1) * (by2 - by1)) - inter + 1e-9
+    return inter / union
+
+
+def person_crop_candidates(frame, boxes, face, ref_face_feat, cfg):
+    """Identity kernel of the per-person site for person boxes given by the caller (gui_app.py:6269-6346, 6370-6437, face-only
+    pipeline): face.extract on each crop (padded retry when empty, :6273-6293), bestf = argmin fd (:6312-6323),
+    face_ok = fd <= face_thresh (:6377), accept = face_ok (:6394-6395), hard gate "face required if any face is visible"
+    (:6417-6437).  -> (candidates, info); a candidate is dict(i, box, fd, score, quality, face_box, area, sharp)."""
+    H2, W2 = frame.shape[:2]
+    bank = None if ref_face_feat is None else np.asarray(ref_face_feat, np.float32).reshape(-1, 512)
+    pad = float(getattr(cfg, "face_det_pad", 0.08))
+    qmin = float(cfg.face_quality_min)
+    faces_local = {}
+    faces_detected = faces_passing_quality = 0
+    for i, (x1, y1, x2, y2) in enumerate(boxes):
+        ffaces = face.extract(np.ascontiguousarray(frame[y1:y2, x1:x2]))
+        if not ffaces and pad > 0.0:
+            pw, ph = int(round((x2 - x1) * pad)), int(round((y2 - y1) * pad))
+            if pw > 0 or ph > 0:
+                px1, py1, px2, py2 = max(0, x1 - pw), max(0, y1 - ph), min(W2, x2 + pw), min(H2, y2 + ph)
+                if px2 > px1 and py2 > py1:
+                    ff2 = face.extract(np.ascontiguousarray(frame[py1:py2, px1:px2]))
+                    dx, dy = x1 - px1, y1 - py1
+                    ffaces = []
+                    for f in ff2:
+                        bb = f["bbox"].copy()
+                        bb[0] -= dx; bb[2] -= dx; bb[1] -= dy; bb[3] -= dy
+                        ffaces.append({"bbox": bb, "feat": f.get("feat"), "quality": f.get("quality", 0.0)})
+        faces_detected += len(ffaces)
+        if bank is not None and ffaces:
+            with_feat = [f for f in ffaces if f.get("feat") is not None]
+            bestf = min(with_feat, key=lambda f: OP.fd_min(f["feat"], bank)) if with_feat else pick_best(ffaces, None, qmin, False)
+        else:
+            bestf = pick_best(ffaces, None, qmin, False)
+        faces_local[i] = bestf
+        if bestf is not None and bestf.get("quality", 0.0) >= qmin:
+            faces_passing_quality += 1
+    any_face_visible = faces_passing_quality > 0 if bool(getattr(cfg, "face_visible_uses_quality", True)) else faces_detected > 0
+    cands = []
+    for i, (x1, y1, x2, y2) in enumerate(boxes):
+        bf = faces_local.get(i)
+        fd = OP.fd_min(bf["feat"], bank) if (bf is not None and bf.get("feat") is not None and bank is not None) else None
+        face_ok = fd is not None and fd <= float(cfg.face_thresh)
+        accept = face_ok
+        if bool(getattr(cfg, "require_face_if_visible", True)) and any_face_visible and bank is not None:
+            qfail = bf is None
+            if bf is not None and bf.get("quality", 0.0) < float(getattr(cfg, "face_quality_floor_absurd", 15)):
+                qfail = True
+            if bf is not None and not face_ok:
+                qfail = True
+            if qfail:
+                accept = False
+        if not accept:
+            continue
+        fb = bf["bbox"]
+        fx1 = max(0.0, min(float(W2), float(x1 + fb[0]))); fy1 = max(0.0, min(float(H2), float(y1 + fb[1])))
+        fx2 = max(fx1 + 1.0, min(float(W2), float(x1 + fb[2]))); fy2 = max(fy1 + 1.0, min(float(H2), float(y1 + fb[3])))
+        cands.append(dict(i=i, box=(x1, y1, x2, y2), fd=fd, score=fd, quality=float(bf.get("quality", 0.0)),
+                          face_box=(fx1, fy1, fx2, fy2), area=(x2 - x1) * (y2 - y1), sharp=0.0))
+    return cands, dict(faces_detected=faces_detected, faces_passing_quality=faces_passing_quality, any_face_visible=any_face_visible)
+
+
+def arbitrate(cands, any_face_visible, cfg, lock_hits=0, locked_face=False, prev_box=None, seek_cooldown=0):
+    """gui_app.py:7788-7845: ambiguity drop (two face-bearing candidates closer than face_margin_min), order by
+    (score, -area, -sharp), keep only the best when the top two scores are within score_margin, then the lock gate
+    (fd <= lock_face_thresh and IoU(prev_box, box) >= iou_gate once lock_after_hits hits were saved).  -> chosen or None."""
+    cands = list(cands)
+    if not cands:
+        return None
+    if bool(getattr(cfg, "prefer_face_when_available", True)) and any_face_visible:
+        fc = sorted([c for c in cands if c.get("fd") is not None], key=lambda d: d["fd"])
+        if len(fc) >= 2 and (fc[1]["fd"] - fc[0]["fd"]) < float(getattr(cfg, "face_margin_min", 0.05)):
+            return None
+    cands.sort(key=lambda c: (c["score"] if c["score"] is not None else 1e9, -c["area"], -c["sharp"]))
+    if len(cands) >= 2 and cands[0]["score"] is not None and cands[1]["score"] is not None:
+        if abs(cands[0]["score"] - cands[1]["score"]) < float(getattr(cfg, "score_margin", 0.03)):
+            cands = cands[:1]
+    use_lock = seek_cooldown <= 0 and lock_hits >= int(getattr(cfg, "lock_after_hits", 1)) and locked_face
+    for c in cands:
+        if use_lock:
+            ok = True
+            if c.get("fd") is not None:
+                ok = ok and c["fd"] <= float(getattr(cfg, "lock_face_thresh", 0.28))
+            if prev_box is not None and iou_xyxy(prev_box, c["box"]) < float(getattr(cfg, "iou_gate", 0.05)):
+                ok = False
+            if not ok:
+                continue
+        return c
+    return cands[0]

@@ -57,6 +57,7 @@ class Engine:
             raise L.PcbError("pcb_create failed (needs an sm_100 device)")
         self.graphs = {}
         self.bank_rows = 0
+        self.scrfd_name, self.arcface_name = scrfd, arcface
         if scrfd:
             self.load_model(L.MODEL_SCRFD, scrfd, scrfd_params)
         if arcface:

@@ -61,7 +61,9 @@ class FaceEmbedder:
             dev = int(s.split(":", 1)[1])
         elif not s.startswith("cuda"):
             raise RuntimeError("SCRFD backend requires a CUDA ctx (as the reference, face_embedder.py:510-515)")
-        self.engine = engine if engine is not None else Engine(dev, scrfd=name, arcface=arcface_model)
+        # the main stream gets the higher priority (lower number) so that work of the second context (flip_engine) yields to it
+        self.engine = engine if engine is not None else Engine(dev, scrfd=name, arcface=arcface_model, stream_priority=-1)
+        self._arcface_name = arcface_model if engine is None else getattr(engine, "arcface_name", arcface_model)
         self.backend = "scrfd"
         self.detector_backend = "scrfd"
         self.use_arcface = True
@@ -94,6 +96,13 @@ class FaceEmbedder:
         self.fast_no_face_imgsz = 512
         self.rot_phase = int(rot_phase) & 7   # stands in for `id(self) & 7` (face_embedder.py:2338)
         self.last_passes: List[dict] = []
+
+    def flip_engine(self) -> Engine:
+        """A second context on the same GPU (ArcFace graph only) whose stream yields to the main one: prescan_batched runs
+        the flip-TTA passes it predicts on it while the main stream works through the frame batches."""
+        if getattr(self, "_flip_engine", None) is None:
+            self._flip_engine = Engine(self.engine.device, scrfd=None, arcface=self._arcface_name, stream_priority=0)
+        return self._flip_engine
 
     # ---- knobs -----------------------------------------------------------------------
     def set_prescan_fast(self, enable: bool, *, mode: str = "rr") -> None:
@@ -213,8 +222,10 @@ class FaceEmbedder:
         if n_acc == 0:
             self._no_face_streak += 1
             if self.rot_adaptive:
-                need_rot = ((self._frame_idx - self._last_face_idx) <= self.rot_after_hit_frames
-                            or ((self._frame_idx + self.rot_phase) % self.rot_every_n) == 0)
+                recent = (self._frame_idx - self._last_face_idx) <= self.rot_after_hit_frames
+                if not recent and getattr(self, "rot_consults", None) is not None:
+                    self.rot_consults.append(self._frame_idx)     # the absolute call counter decided (main_pass_sharded checks these)
+                need_rot = recent or ((self._frame_idx + self.rot_phase) % self.rot_every_n) == 0
             else:
                 need_rot = True
             if fast:

@@ -534,6 +534,37 @@ class SampleRecord:
     heavy: Dict[int, _Variant] = field(default_factory=dict)
 
 
+class EarlyFlips:
+    """Flip-TTA passes issued WHILE the superset is still running, on a second libpcb200 context of the same GPU whose
+    stream has a lower priority than the main one: when frames arrive from the host, the SMs wait for PCIe between frame
+    batches, and the flip passes that the replay will need anyway fill those gaps instead of running after the last upload
+    (bench e2e: flips + refine used to run with the PCIe link idle).  Which rows: the rule of `_predict_flip_rows`
+    (a sample that follows, within the exit cooldown, a sample with a face at plain distance <= enter + margin from the
+    initial bank), applied run by run with the distances known so far.  A prediction only: the exact prediction after the
+    superset and the on-demand path of the replay compute whatever is missing, so results never depend on it."""
+
+    def __init__(self, engine, cfg, fps: int, carry_in: bool, margin: float = 0.12):
+        self.engine = engine
+        self.thr = float(cfg.prescan_fd_enter) + margin
+        stride = max(1, int(cfg.prescan_stride))
+        exit_cool = int(round(max(0.0, float(getattr(cfg, "prescan_exit_cooldown_sec", 0.5))) * fps))
+        self.tail = (exit_cool + stride - 1) // stride + 1
+        self.hot = np.zeros((0,), np.int64)          # sorted sample positions with a face within the threshold
+        if carry_in:                                  # the chunk may start inside another rank's active stretch
+            self.hot = np.array([-1], np.int64)
+
+    def select(self, sample_pos: np.ndarray, fd0: np.ndarray) -> np.ndarray:
+        """-> indices (into this run) of the rows to flip."""
+        hot_now = np.unique(sample_pos[fd0 <= self.thr])
+        if len(hot_now):
+            self.hot = np.union1d(self.hot, hot_now)
+        if not len(self.hot):
+            return np.zeros((0,), np.int64)
+        k = np.searchsorted(self.hot, sample_pos, side="left")          # hot samples strictly before the row's sample
+        prev = np.where(k > 0, self.hot[np.maximum(k - 1, 0)], -10 ** 9)
+        return np.nonzero(sample_pos - prev <= self.tail)[0].astype(np.int64)
+
+
 class FaceTable:
     """All faces of the superset: normalised features without / with flip-TTA (device + host).
 
@@ -545,9 +576,18 @@ class FaceTable:
     # images per ArcFace graph run (pcb_embed chunk; half as many faces when both variants are computed).  444 fills the 148 SMs
     # to >= 95 % in every iResNet stage (14x14: 888 tiles = 6.0 waves, 28x28: 10.5, 56x56: 39.4)
     EMBED_RUN = int(os.environ.get("PCB_EMBED_RUN", "444"))
+    # early flip passes (see `EarlyFlips`) go out in runs of at least this many images: whole waves in the 14x14 stage
+    EARLY_RUN = int(os.environ.get("PCB_EARLY_RUN", "296"))
 
-    def __init__(self, lazy: bool = False):
+    def __init__(self, lazy: bool = False, early: Optional["EarlyFlips"] = None):
         self.lazy = lazy
+        self.early = early if lazy else None   # flip passes issued on a second, lower-priority context while the superset runs
+        self.sp_parts: List[np.ndarray] = []   # per row: position of its sample in the rank's sample list (early flips only)
+        self.runs: List[tuple] = []            # lazy mode, per flushed run: (first row, rows, sim to the device bank, event)
+        self.runs_decided = 0
+        self.early_rows: List[np.ndarray] = [] # rows selected for an early flip pass, not issued yet
+        self.early_n = 0
+        self.early_done: List[tuple] = []      # (rows, normalised flip features on the device, completion event)
         self.feat_plain: List[torch.Tensor] = []
         self.feat_flip: List[torch.Tensor] = []
         self.raw: List[torch.Tensor] = []
@@ -560,9 +600,11 @@ class FaceTable:
         self.encoded = None
         self.flip_passes = 0          # faces that went through the flip pass (bench: ArcFace image passes / s)
 
-    def queue(self, eng, chips: torch.Tensor, k: int) -> np.ndarray:
+    def queue(self, eng, chips: torch.Tensor, k: int, sample_pos: Optional[np.ndarray] = None) -> np.ndarray:
         """Register k aligned chips; -> their row numbers.  Embedding happens in `flush`."""
         rows = np.arange(self.count, self.count + k)
+        if self.early is not None:
+            self.sp_parts.append(np.asarray(sample_pos if sample_pos is not None else np.full(k, -10 ** 9), np.int64))
         with torch.cuda.stream(eng.stream):
             self.pending.append(chips[:k].clone())
         self.pending_n += k
@@ -585,9 +627,14 @@ class FaceTable:
         use = chips[:take].contiguous()
         if self.lazy:
             emb, _ = eng.embed(use, take, False)
-            fp, _, _ = eng.match(emb, None, None, take)           # normalise(e(x))
+            fp, sim, _ = eng.match(emb, None, None, take)         # normalise(e(x)); sim: against the bank on the device
             self.raw.append(emb[:take])
             self.chip_list.append(use)
+            if self.early is not None:
+                ev = torch.cuda.Event()
+                ev.record(eng.stream)
+                self.runs.append((self.count - self.pending_n, take, sim, ev))
+                self._early_step(eng)
         else:
             emb, emb_flip = eng.embed(use, take, True)
             fp, _, _ = eng.match(emb, None, None, take)           # normalise(e(x))
@@ -601,6 +648,55 @@ class FaceTable:
             self.pending_n = n - take
         else:
             self.pending, self.pending_n = [], 0
+
+    # ---- early flips: see EarlyFlips
+    def _early_step(self, eng):
+        """Decide, for every flushed run whose similarities have arrived, which of its rows will most likely need the flip
+        feature, and issue flip passes for them on the second context.  Never waits for the GPU."""
+        ef = self.early
+        sp_all = None
+        while self.runs_decided < len(self.runs):
+            row0, take, sim, ev = self.runs[self.runs_decided]
+            if not ev.query():
+                break
+            if sp_all is None:
+                sp_all = np.concatenate(self.sp_parts)
+            fd0 = 1.0 - sim[:take].cpu().numpy().astype(np.float64)
+            rows = ef.select(sp_all[row0:row0 + take], fd0) + row0
+            if len(rows):
+                self.early_rows.append(rows)
+                self.early_n += len(rows)
+            self.runs_decided += 1
+        while self.early_n >= self.EARLY_RUN:
+            self._issue_early(eng, min(self.early_n, self.EMBED_RUN))
+
+    def _issue_early(self, eng, n: int):
+        feng = self.early.engine
+        allr = np.concatenate(self.early_rows)
+        rows, rest = allr[:n], allr[n:]
+        self.early_rows = [rest] if len(rest) else []
+        self.early_n = len(rest)
+        starts = np.asarray([r[0] for r in self.runs], np.int64)
+        part = np.searchsorted(starts, rows, side="right") - 1
+        order = []
+        with torch.cuda.stream(feng.stream):
+            chips, raws = [], []
+            for pi in np.unique(part):
+                feng.stream.wait_event(self.runs[pi][3])           # the run's chips / raw embeddings are final
+                sel = rows[part == pi]
+                loc = torch.as_tensor(sel - starts[pi], device=self.chip_list[pi].device)
+                chips.append(self.chip_list[pi].index_select(0, loc))
+                raws.append(self.raw[pi].index_select(0, loc))
+                order.append(sel)
+            chips = torch.cat(chips, 0).contiguous()
+            raws = torch.cat(raws, 0).contiguous()
+        order = np.concatenate(order)
+        _, emb_flip = feng.embed(chips, len(order), "only")
+        ff, _, _ = feng.match(raws, emb_flip, None, len(order))
+        done = torch.cuda.Event()
+        done.record(feng.stream)
+        self.early_done.append((order, ff[:len(order)], done, chips, raws))      # inputs stay referenced until the pass has run
+        self.flip_passes += len(order)
 
     def finalize(self, eng):
         self.flush(eng)
@@ -618,6 +714,17 @@ class FaceTable:
                 self.flip = eng.empty((1, L.FEAT_DIM), torch.float32)
         self.flip_ready = np.zeros(self.count, bool) if self.lazy else np.ones(self.count, bool)
         self.flip_host = np.zeros((self.count, L.FEAT_DIM), np.float32) if self.lazy else None
+        if self.early_done:
+            # flips computed on the second context while the superset was running
+            for rows, ff, done, _c, _r in self.early_done:
+                eng.stream.wait_event(done)
+                with torch.cuda.stream(eng.stream):
+                    self.flip.index_copy_(0, torch.as_tensor(rows, device=self.flip.device), ff)
+            eng.sync()
+            for rows, ff, _d, _c, _r in self.early_done:
+                self.flip_host[rows] = ff.cpu().numpy()
+                self.flip_ready[rows] = True
+            self.early_done = []
         self.feat_plain, self.feat_flip, self.raw, self.chip_list = [], [], [], []
 
     def ensure_flip(self, eng, rows: np.ndarray) -> bool:
@@ -642,7 +749,7 @@ class FaceTable:
         return True
 
 
-def _collect_variant(eng, frames, det, idx_list, records, key, table: FaceTable, max_faces: int, al=None):
+def _collect_variant(eng, frames, det, idx_list, records, key, table: FaceTable, max_faces: int, al=None, pos_of=None):
     """Align every accumulated face of `det` (batch over idx_list) and queue its chip for embedding.  `al`: the align
     result if the caller already enqueued it and waited for it."""
     if al is None:
@@ -652,7 +759,10 @@ def _collect_variant(eng, frames, det, idx_list, records, key, table: FaceTable,
     counts = al.face_count.cpu().numpy()
     if total == 0:
         return
-    rows = table.queue(eng, al.chips, total)
+    sample_pos = None
+    if table.early is not None and pos_of is not None:
+        sample_pos = np.repeat(np.asarray([pos_of[i] for i in idx_list], np.int64), counts[:len(idx_list)])
+    rows = table.queue(eng, al.chips, total, sample_pos)
     boxes = al.face_box[:total].cpu().numpy()
     qual = al.quality[:total].cpu().numpy()
     b64 = boxes.astype(np.int64)
@@ -671,7 +781,7 @@ def _collect_variant(eng, frames, det, idx_list, records, key, table: FaceTable,
 
 
 def compute_superset(clip, idxs: Sequence[int], face: FaceEmbedder, cfg, batch: int = 32, max_faces: int = 4096,
-                     lazy_flip: bool = False):
+                     lazy_flip: bool = False, early: Optional[EarlyFlips] = None):
     """GPU stage of the batched pre-scan for the samples `idxs` (fast pre-scan settings must be active).
     lazy_flip: compute e(flip x) later, only for the faces the replay evaluates while a span is active.
 
@@ -681,7 +791,8 @@ def compute_superset(clip, idxs: Sequence[int], face: FaceEmbedder, cfg, batch: 
     eng = face.engine
     wmax = int(getattr(cfg, "prescan_max_width", 0))
     records: Dict[int, SampleRecord] = {}
-    table = FaceTable(lazy=lazy_flip)
+    table = FaceTable(lazy=lazy_flip, early=early)
+    pos_of = {idx: k for k, idx in enumerate(idxs)} if early is not None else None
     chunks = [list(idxs[b0:b0 + batch]) for b0 in range(0, len(idxs), batch)]
     prefetch = bool(getattr(clip, "host_resident", False))
 
@@ -695,7 +806,11 @@ def compute_superset(clip, idxs: Sequence[int], face: FaceEmbedder, cfg, batch: 
             ev.record(eng.copy_stream)
         return fr, ev
 
-    fetched = {0: fetch(0)}
+    # host frames: the copy stream runs PREFETCH batches ahead of the SMs.  The link, not the SMs, paces a host-resident
+    # pre-scan, so it must never idle: with one batch of lead, every burst of extra work on the SMs (an early flip pass, the
+    # rotated passes of an empty batch) stalled the copies behind it and that time was lost for good.
+    depth = max(1, int(os.environ.get("PCB_PREFETCH", "3")))
+    fetched = {ci: fetch(ci) for ci in range(min(depth, len(chunks)))} if prefetch else {}
 
     def issue(ci):
         """Enqueue K0 + upright SCRFD + K4 of batch ci; nothing here waits for the GPU."""
@@ -704,7 +819,8 @@ def compute_superset(clip, idxs: Sequence[int], face: FaceEmbedder, cfg, batch: 
             frames, ev = fetched.pop(ci)
             eng.stream.wait_event(ev)
             frames.record_stream(eng.stream)
-            fetched[ci + 1] = fetch(ci + 1)
+            if ci + depth < len(chunks):
+                fetched[ci + depth] = fetch(ci + depth)
         else:
             frames = clip.device_batch(eng, chunk)
         n, h, w, _ = frames.shape
@@ -747,7 +863,7 @@ def compute_superset(clip, idxs: Sequence[int], face: FaceEmbedder, cfg, batch: 
         for i in chunk:
             records[i] = SampleRecord(i)
         acc0 = det0.acc_count.cpu().numpy()
-        _collect_variant(eng, frames, det0, chunk, records, "up", table, max_faces, al=cur["al"])
+        _collect_variant(eng, frames, det0, chunk, records, "up", table, max_faces, al=cur["al"], pos_of=pos_of)
         empty = [b for b in range(n) if acc0[b] == 0]
         cur = nxt
         if not empty:
@@ -775,7 +891,7 @@ def compute_superset(clip, idxs: Sequence[int], face: FaceEmbedder, cfg, batch: 
             raw = hv.raw_count.cpu().numpy()
             for j, sidx in enumerate(sel_idx):
                 records[sidx].heavy_raw[deg] = int(raw[j])
-            _collect_variant(eng, sub2, hv, sel_idx, records, deg, table, max_faces)
+            _collect_variant(eng, sub2, hv, sel_idx, records, deg, table, max_faces, pos_of=pos_of)
         encode_chunk(chunk)
     table.finalize(eng)
     one = lambda parts, dt: np.concatenate(parts).astype(dt) if parts else np.zeros(1, dt)
@@ -1213,8 +1329,19 @@ def prescan_batched(clip, fps: int, face: FaceEmbedder, ref_feat, cfg, batch: in
         per = (len(idxs) + world - 1) // world
         mine = idxs[rank * per:(rank + 1) * per]
         lazy = os.environ.get("PCB_EAGER_FLIP", "0") != "1"
-        records, table = compute_superset(clip, mine, face, cfg, batch=batch, lazy_flip=lazy)
+        # early flip passes on a second, lower-priority context: on by default when frames come from the host (the SMs then
+        # wait for PCIe between frame batches); PCB_EARLY_FLIP=1 / 0 forces it on / off
+        early = None
+        mode = os.environ.get("PCB_EARLY_FLIP", "auto")
+        if lazy and mode != "0" and (mode == "1" or bool(getattr(clip, "host_resident", False))):
+            bank0 = RefBank(cfg, ref_feat)
+            if len(bank0):
+                eng.set_bank(bank0.array())      # FaceTable.flush then gets the distances to the initial bank for free
+                early = EarlyFlips(face.flip_engine(), cfg, fps, carry_in=rank > 0)
+        records, table = compute_superset(clip, mine, face, cfg, batch=batch, lazy_flip=lazy, early=early)
         eng.sync()
+        if stats is not None:
+            stats["early_flip_rows"] = int(table.flip_ready.sum()) if (early is not None and table.count) else 0
         mark("superset")
         if lazy and table.count:
             bank0 = RefBank(cfg, ref_feat)

@@ -222,6 +222,31 @@ def test_prescan_batched_equals_sequential(engine_25g_r50):
     assert np.asarray(b1).shape[0] > np.asarray(bank).shape[0]      # the bank grew during the scan
 
 
+def test_early_flip_passes_do_not_change_results(engine_25g_r50, monkeypatch):
+    """Flip passes predicted and issued on the second context while the superset runs (the default for host-resident clips)
+    only move work: spans, bank and the per-sample log are bit-identical to the run without them, and flips were in fact
+    computed early."""
+    from person_capture_b200 import prescan as PS
+    from person_capture_b200.face_embedder import FaceEmbedder
+    cfg, clip, ref_img = _make_case(1003, 640, 360, 192, 1, prescan_add_cooldown_samples=2)
+    frames = [clip.frame(i) for i in range(clip.n_frames)]
+    face = FaceEmbedder("cuda:0", "scrfd_2.5g_bnkps", conf=cfg.face_det_conf, engine=engine_25g_r50, arcface_model="arcface_r50")
+    bank = PS.build_reference_bank(face, [ref_img], cfg)
+    src = PS.HostClip(lambda i: frames[i], len(frames))
+    monkeypatch.setattr(PS.FaceTable, "EMBED_RUN", 48)
+    monkeypatch.setattr(PS.FaceTable, "EARLY_RUN", 16)
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("PCB_EARLY_FLIP", mode)
+        log, stats = [], {}
+        spans, b = PS.prescan_batched(src, 24, face, bank, cfg, batch=16, log=log, stats=stats)
+        out[mode] = (spans, np.asarray(b), [(r["idx"], r["skip"], r["nfaces"], r["best"]) for r in log], stats)
+    assert out["0"][0] == out["1"][0] and len(out["0"][0]) >= 1
+    assert np.array_equal(out["0"][1], out["1"][1])
+    assert out["0"][2] == out["1"][2]
+    assert out["1"][3].get("early_flip_rows", 0) > 0 and out["0"][3].get("early_flip_rows", 0) == 0
+
+
 def test_prescan_cache_roundtrip_with_gpu_result(engine_25g_r50, tmp_path):
     from oracle import prescan as OP
     from person_capture_b200 import prescan as PS
