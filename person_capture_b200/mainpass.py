@@ -433,24 +433,26 @@ def index_rows(hits: Sequence[dict], fps: float) -> List[list]:
 
 
 def fullframe_identity(clip, idxs: Sequence[int], face: FaceEmbedder, ref_face_feat, cfg, batch: int = 16, max_faces: int = 4096):
-    """Throughput form of the full-frame identity site (normal mode: flip-TTA on) for the frames `idxs`.
+    """Throughput form of the full-frame identity site (normal mode: flip-TTA on) for the frames `idxs`, with the results of
+    calling FaceEmbedder.extract(frame, imgsz=face_fullframe_imgsz) on them one after the other.
 
-    One batched upright SCRFD pass at round32(face_fullframe_imgsz), K4 align, ArcFace e(x)+e(flip x), bank distance, gbest
-    + accept rule per frame.  Frames whose upright pass finds no face are returned with n_faces = 0 (the reference would walk
-    its scale-TTA / pad-probe / rotation chain for them, which is stateful; callers that need it run FaceEmbedder.extract on
-    those frames).  -> list of dict(idx, n_faces, fd, accept, face_box, quality)."""
+    Phase 1 (batched): upright SCRFD pass at round32(face_fullframe_imgsz), K4 align, ArcFace e(x)+e(flip x) in 444-image
+    runs, bank distances.  Phase 2 (host, in frame order): the FaceEmbedder counters are advanced exactly as extract() would
+    advance them, and the frames the batched pass cannot answer are handed to extract() itself -- a frame whose upright
+    pass found nothing (the reference then walks its scale-TTA / pad-probe / adaptive-rotation chain, face_embedder.py:
+    2251-2433) and a frame that follows three empty ones (the upright size drops to fast_no_face_imgsz, :2193-2194).
+    -> list of dict(idx, n_faces, fd, accept, face_box, quality, via)."""
     from .face_embedder import round32, _MIN_SIDE
+    from .prescan import FaceTable
     eng = face.engine
     bank = RefBank(cfg, ref_face_feat)
     eng.set_bank(bank.array())
     imgsz = getattr(cfg, "face_fullframe_imgsz", None)
-    dyn = round32(max(_MIN_SIDE, int(imgsz) if imgsz else 640))
+    imgsz = int(imgsz) if imgsz else None
+    dyn = round32(max(_MIN_SIDE, imgsz or 640))
     qmin = float(cfg.face_quality_min)
     use_qv = bool(getattr(cfg, "face_visible_uses_quality", True))
     thr = float(cfg.face_thresh)
-    # phase 1: SCRFD + K4 per frame batch; chips are queued and embedded in 444-image runs (the ArcFace batch must not
-    # depend on how few faces a frame batch holds)
-    from .prescan import FaceTable
     table = FaceTable(lazy=False)
     metas = []
     for b0 in range(0, len(idxs), batch):
@@ -466,31 +468,40 @@ def fullframe_identity(clip, idxs: Sequence[int], face: FaceEmbedder, ref_face_f
         metas.append((chunk, H2, W2, counts, rows, al.face_box[:total].cpu().numpy() if total else None,
                       al.quality[:total].cpu().numpy() if total else None))
     table.finalize(eng)
-    # phase 2: distances of normalise(e(x) + e(flip x)) against the bank, then gbest + accept per frame
     fds_all = np.zeros((0,), np.float64)
     if table.count:
         _, sim, _ = eng.match(table.flip, None, None, table.count, want_feat=False)
         eng.sync()
         fds_all = 1.0 - sim[:table.count].cpu().numpy().astype(np.float64)
+
+    def decide(rec, boxes, qual, fds, W2, H2):
+        sel = sorted(range(len(boxes)), key=lambda i: (qual[i], (boxes[i][2] - boxes[i][0]) * (boxes[i][3] - boxes[i][1])), reverse=True)
+        cand = [i for i in sel if qual[i] >= qmin] if use_qv else sel      # the reference sorts by (quality, area) first: ties go to the first
+        g = min(cand or sel, key=lambda i: fds[i])
+        fx1, fy1, fx2, fy2 = [float(v) for v in boxes[g]]
+        fx1 = max(0.0, min(float(W2), fx1)); fy1 = max(0.0, min(float(H2), fy1))
+        fx2 = max(fx1 + 1.0, min(float(W2), fx2)); fy2 = max(fy1 + 1.0, min(float(H2), fy2))
+        x1 = max(0, min(W2 - 1, int(round(fx1)))); y1 = max(0, min(H2 - 1, int(round(fy1))))
+        rec.update(fd=float(fds[g]), accept=bool(fds[g] <= thr), quality=float(qual[g]),
+                   face_box=(x1, y1, max(x1 + 1, min(W2, int(round(fx2)))), max(y1 + 1, min(H2, int(round(fy2))))))
+
     out = []
     for chunk, H2, W2, counts, rows, boxes, qual in metas:
-        fds = fds_all[rows] if len(rows) else None
         off = 0
         for b, idx in enumerate(chunk):
             k = int(counts[b])
-            rec = dict(idx=idx, n_faces=k, fd=None, accept=False, face_box=None, quality=None)
-            if k:
-                sel = list(range(off, off + k))
-                # the reference sorts faces by (quality, area) before taking the argmin, which decides ties
-                sel.sort(key=lambda i: (qual[i], (boxes[i][2] - boxes[i][0]) * (boxes[i][3] - boxes[i][1])), reverse=True)
-                cand = [i for i in sel if qual[i] >= qmin] if use_qv else sel
-                g = min(cand or sel, key=lambda i: fds[i])
-                fx1, fy1, fx2, fy2 = [float(v) for v in boxes[g]]
-                fx1 = max(0.0, min(float(W2), fx1)); fy1 = max(0.0, min(float(H2), fy1))
-                fx2 = max(fx1 + 1.0, min(float(W2), fx2)); fy2 = max(fy1 + 1.0, min(float(H2), fy2))
-                x1 = max(0, min(W2 - 1, int(round(fx1)))); y1 = max(0, min(H2 - 1, int(round(fy1))))
-                rec.update(fd=float(fds[g]), accept=bool(fds[g] <= thr), quality=float(qual[g]),
-                           face_box=(x1, y1, max(x1 + 1, min(W2, int(round(fx2)))), max(y1 + 1, min(H2, int(round(fy2))))))
+            rec = dict(idx=idx, n_faces=k, fd=None, accept=False, face_box=None, quality=None, via="batched")
+            if face._no_face_streak >= 3 and min(dyn, face.fast_no_face_imgsz) != dyn or k == 0:
+                # the sequential call sees a different upright size, or has to walk the empty-frame chain: let it
+                faces = face.extract(clip.device_batch(eng, [idx])[0], imgsz=imgsz)
+                rec.update(n_faces=len(faces), via="extract")
+                if faces and len(bank):
+                    fds = _fds_for_last_faces(face, bank)
+                    decide(rec, [f["bbox"] for f in faces], [f["quality"] for f in faces], fds, W2, H2)
+            else:
+                face._frame_idx += 1                      # what extract() does when its upright pass finds faces
+                face._no_face_streak, face._last_face_idx, face._rot_cycle = 0, face._frame_idx, 0
+                decide(rec, boxes[off:off + k], qual[off:off + k], fds_all[rows[off:off + k]], W2, H2)
             out.append(rec)
             off += k
     return out

@@ -45,6 +45,18 @@ def main():
                bank_equal=bool(np.asarray(bank_n).shape == np.asarray(bank_1).shape and np.array_equal(bank_n, bank_1)),
                bank_rows=int(np.asarray(bank_n).shape[0]), bank_rows_initial=int(np.asarray(bank).shape[0]), same_log=bool(same_log),
                refreshes=stats.get("distance_refreshes"), phase_ms=stats.get("phase_ms"))
+    # main pass over kept spans, sharded by span blocks vs sequential (config 3's "sharded across N GPUs")
+    from person_capture_b200 import mainpass as MP
+    mcfg = PrescanParams(face_model="scrfd_2.5g_bnkps", face_thresh=0.62, face_quality_min=40.0, face_fullframe_imgsz=640,
+                         frame_stride=2, face_fullframe_cadence=6, lock_face_roi_max_misses=3)
+    mspans = [(4, 40), (50, 70), (84, 120), (130, 170), (180, 239)]
+    mstats = {}
+    hits_n = MP.main_pass_sharded(dev, 24.0, mspans, face, bank, mcfg, stats=mstats)
+    face2 = FaceEmbedder(f"cuda:{local}", "scrfd_2.5g_bnkps", conf=cfg.face_det_conf, engine=face.engine)
+    hits_1 = MP.main_pass(dev, 24.0, mspans, face2, bank, mcfg)
+    key = lambda h: (h["idx"], h["site"], tuple(h["face_box"]), round(h["fd"], 6))
+    res.update(main_hits=len(hits_1), main_equal=[key(h) for h in hits_n] == [key(h) for h in hits_1], main_rounds=mstats.get("rounds"),
+               main_sites=sorted({h["site"] for h in hits_1}))
     gathered = [None] * world
     dist.all_gather_object(gathered, res)          # test harness only (not the product path)
     if rank == 0:

@@ -331,29 +331,39 @@ def test_main_pass_decisions_match_oracle(engine_25g_r50):
 
 
 def test_fullframe_identity_batched_matches_per_frame_extract(engine_25g_r50):
-    """Throughput form of the full-frame site: batched decisions == per-frame FaceEmbedder.extract + gbest/accept on the GPU."""
+    """Throughput form of the full-frame site == FaceEmbedder.extract + gbest/accept frame after frame, INCLUDING the frames
+    without an upright face (scale-TTA / pad probe / adaptive rotations, stateful) and the frames after a no-face streak
+    (smaller upright size): same faces, same distances, same decisions, same embedder counters at the end."""
     from person_capture_b200 import mainpass as MP, prescan as PS
     from person_capture_b200.face_embedder import FaceEmbedder
-    cfg, clip, ref_img = _mainpass_case(seed=1002, n=40)
+    cfg, clip, ref_img = _mainpass_case(seed=1002, n=96)
     frames = np.stack([clip.frame(i) for i in range(clip.n_frames)])
+    rng = np.random.default_rng(4)
+    for i in (20, 21, 22, 23, 24, 50):                          # a run of empty frames (streak >= 3) and an isolated one
+        frames[i] = synth.background(rng, 360, 640)
     face = FaceEmbedder("cuda:0", "scrfd_2.5g_bnkps", conf=cfg.face_det_conf, engine=engine_25g_r50)
     bank = PS.build_reference_bank(face, [ref_img], cfg)
     dev = PS.DeviceClip(engine_25g_r50.to_device(frames))
-    idxs = list(range(0, clip.n_frames, 3))
+    idxs = list(range(0, clip.n_frames, 2))
+    start = (face._frame_idx, face._no_face_streak, face._last_face_idx)
     recs = MP.fullframe_identity(dev, idxs, face, bank, cfg, batch=8)
+    end_batched = (face._frame_idx, face._no_face_streak, face._last_face_idx)
+    face._frame_idx, face._no_face_streak, face._last_face_idx = start
     rb = PS.RefBank(cfg, bank)
-    n_checked = 0
+    n_checked = n_seq = 0
     for rec in recs:
-        face._no_face_streak = 0
         faces = face.extract(frames[rec["idx"]], imgsz=cfg.face_fullframe_imgsz)
-        if rec["n_faces"] == 0:
+        assert len(faces) == rec["n_faces"], rec
+        n_seq += int(rec["via"] == "extract")
+        if not faces:
+            assert rec["fd"] is None and not rec["accept"]
             continue
-        assert len(faces) == rec["n_faces"]
         fds = PS._fds_for_last_faces(face, rb)
         g = MP._argmin_face(faces, fds, cfg.face_quality_min, True)
-        assert abs(float(fds[g]) - rec["fd"]) <= 1e-5 and (float(fds[g]) <= cfg.face_thresh) == rec["accept"]
+        assert abs(float(fds[g]) - rec["fd"]) <= 1e-5 and (float(fds[g]) <= cfg.face_thresh) == rec["accept"], rec
         n_checked += 1
-    assert n_checked >= 8 and any(r["accept"] for r in recs)
+    assert (face._frame_idx, face._no_face_streak, face._last_face_idx) == end_batched
+    assert n_checked >= 20 and n_seq >= 3 and any(r["accept"] for r in recs) and any(r["n_faces"] == 0 for r in recs)
 
 
 def test_curator_identity_matches_oracle(engine_25g_r50):

@@ -31,3 +31,5 @@ def test_n_ranks_equal_single_rank(tmp_path, mode):
         assert rec["spans_n"] == rec["spans_1"] == res[0]["spans_1"], rec
         assert rec["bank_equal"] and rec["same_log"], rec
     assert len(res[0]["spans_1"]) >= 2 and res[0]["bank_rows"] > res[0]["bank_rows_initial"]
+    for rec in res:                                   # span-sharded main pass == sequential main pass on every rank
+        assert rec["main_equal"] and rec["main_hits"] >= 20 and "lock_roi" in rec["main_sites"], rec
