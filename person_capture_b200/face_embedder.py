@@ -61,9 +61,7 @@ class FaceEmbedder:
             dev = int(s.split(":", 1)[1])
         elif not s.startswith("cuda"):
             raise RuntimeError("SCRFD backend requires a CUDA ctx (as the reference, face_embedder.py:510-515)")
-        # the main stream gets the higher priority (lower number) so that work of the second context (flip_engine) yields to it
-        self.engine = engine if engine is not None else Engine(dev, scrfd=name, arcface=arcface_model, stream_priority=-1)
-        self._arcface_name = arcface_model if engine is None else getattr(engine, "arcface_name", arcface_model)
+        self.engine = engine if engine is not None else Engine(dev, scrfd=name, arcface=arcface_model)
         self.backend = "scrfd"
         self.detector_backend = "scrfd"
         self.use_arcface = True
@@ -97,12 +95,13 @@ class FaceEmbedder:
         self.rot_phase = int(rot_phase) & 7   # stands in for `id(self) & 7` (face_embedder.py:2338)
         self.last_passes: List[dict] = []
 
-    def flip_engine(self) -> Engine:
-        """A second context on the same GPU (ArcFace graph only) whose stream yields to the main one: prescan_batched runs
-        the flip-TTA passes it predicts on it while the main stream works through the frame batches."""
-        if getattr(self, "_flip_engine", None) is None:
-            self._flip_engine = Engine(self.engine.device, scrfd=None, arcface=self._arcface_name, stream_priority=0)
-        return self._flip_engine
+    def aux_engine(self) -> Engine:
+        """A second context on the same GPU with the ArcFace graph only (own stream, own activation set).  The host-resident
+        pre-scan embeds on it, so that ArcFace runs are not queued behind SCRFD passes that wait for their frames to cross
+        PCIe (prescan.EarlyFlips)."""
+        if getattr(self, "_aux_engine", None) is None:
+            self._aux_engine = Engine(self.engine.device, scrfd=None, arcface=self.engine.arcface_name)
+        return self._aux_engine
 
     # ---- knobs -----------------------------------------------------------------------
     def set_prescan_fast(self, enable: bool, *, mode: str = "rr") -> None:

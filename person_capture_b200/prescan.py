@@ -534,17 +534,47 @@ class SampleRecord:
     heavy: Dict[int, _Variant] = field(default_factory=dict)
 
 
+class _Timeline:
+    """Optional GPU timeline of a pre-scan step (PCB_TIMELINE=file): named CUDA events per stream, dumped as milliseconds
+    from the first one.  Diagnostics only."""
+    path = os.environ.get("PCB_TIMELINE")
+
+    def __init__(self):
+        self.marks = []
+
+    def mark(self, name: str, stream):
+        if self.path:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(stream)
+            self.marks.append((name, ev))
+
+    def dump(self):
+        if self.path and self.marks:
+            torch.cuda.synchronize()
+            t0 = self.marks[0][1]
+            with open(self.path, "a") as fh:
+                fh.write(json.dumps([(n, round(t0.elapsed_time(e), 3)) for n, e in self.marks]) + "\n")
+        self.marks = []
+
+
+TIMELINE = _Timeline()
+
+
 class EarlyFlips:
-    """Flip-TTA passes issued WHILE the superset is still running, on a second libpcb200 context of the same GPU whose
-    stream has a lower priority than the main one: when frames arrive from the host, the SMs wait for PCIe between frame
-    batches, and the flip passes that the replay will need anyway fill those gaps instead of running after the last upload
-    (bench e2e: flips + refine used to run with the PCIe link idle).  Which rows: the rule of `_predict_flip_rows`
-    (a sample that follows, within the exit cooldown, a sample with a face at plain distance <= enter + margin from the
-    initial bank), applied run by run with the distances known so far.  A prediction only: the exact prediction after the
-    superset and the on-demand path of the replay compute whatever is missing, so results never depend on it."""
+    """Flip-TTA passes issued WHILE the superset is still running.  When frames arrive from the host the SMs wait for PCIe
+    between frame batches (timeline, profiles/r02_e2e_timeline.txt: a 64-frame batch is 3.5 ms of SCRFD per 7-9 ms of
+    copy), so a host-resident pre-scan embeds its chips in SMALL runs as they accumulate and follows each plain run with the
+    flip pass the replay will most likely need, all on a SECOND context (own stream): an ArcFace run queued on the main
+    stream would sit behind the next SCRFD pass, which itself waits for its frames -- on its own stream it runs in that
+    wait.  (First attempts, measured: flips alone on a second lower-priority context -- priorities do not preempt
+    persistent kernels and the first 444-chip run only existed after the copies had ended: no gain; small runs + flips on
+    the main stream: 116 -> 112 ms, the SMs still idle 16 of the first 32 ms.)  Which rows: the rule of `_predict_flip_rows` (a sample
+    that follows, within the exit cooldown, a sample with a face at plain distance <= enter + margin from the initial
+    bank), applied run by run with the distances known so far.  A prediction only: the exact prediction after the superset
+    and the on-demand path of the replay compute whatever is missing, so results never depend on it."""
 
     def __init__(self, engine, cfg, fps: int, carry_in: bool, margin: float = 0.12):
-        self.engine = engine
+        self.engine = engine        # the context the ArcFace runs of the superset go to (its own stream: see FaceTable.flush)
         self.thr = float(cfg.prescan_fd_enter) + margin
         stride = max(1, int(cfg.prescan_stride))
         exit_cool = int(round(max(0.0, float(getattr(cfg, "prescan_exit_cooldown_sec", 0.5))) * fps))
@@ -576,12 +606,17 @@ class FaceTable:
     # images per ArcFace graph run (pcb_embed chunk; half as many faces when both variants are computed).  444 fills the 148 SMs
     # to >= 95 % in every iResNet stage (14x14: 888 tiles = 6.0 waves, 28x28: 10.5, 56x56: 39.4)
     EMBED_RUN = int(os.environ.get("PCB_EMBED_RUN", "444"))
-    # early flip passes (see `EarlyFlips`) go out in runs of at least this many images: whole waves in the 14x14 stage
-    EARLY_RUN = int(os.environ.get("PCB_EARLY_RUN", "296"))
+    # host-resident clips (early flips on): plain runs of this many images as the chips accumulate, and flip passes of at least
+    # EARLY_RUN images (148 images = one full wave of 14x14 pair tiles)
+    HOST_RUN = int(os.environ.get("PCB_HOST_RUN", "222"))
+    FIRST_RUN = int(os.environ.get("PCB_FIRST_RUN", "74"))     # the first run goes out as soon as this many chips exist
+    EARLY_RUN = int(os.environ.get("PCB_EARLY_RUN", "148"))
 
     def __init__(self, lazy: bool = False, early: Optional["EarlyFlips"] = None):
         self.lazy = lazy
-        self.early = early if lazy else None   # flip passes issued on a second, lower-priority context while the superset runs
+        self.early = early if lazy else None   # flip passes issued while the superset runs (host-resident clips)
+        if self.early is not None:
+            self.EMBED_RUN = min(self.EMBED_RUN, self.HOST_RUN)
         self.sp_parts: List[np.ndarray] = []   # per row: position of its sample in the rank's sample list (early flips only)
         self.runs: List[tuple] = []            # lazy mode, per flushed run: (first row, rows, sim to the device bank, event)
         self.runs_decided = 0
@@ -605,34 +640,48 @@ class FaceTable:
         rows = np.arange(self.count, self.count + k)
         if self.early is not None:
             self.sp_parts.append(np.asarray(sample_pos if sample_pos is not None else np.full(k, -10 ** 9), np.int64))
-        with torch.cuda.stream(eng.stream):
+        # early mode: the caller has waited for K4 (the chips are final), and the copy goes to the ArcFace context's stream --
+        # on the main stream it would sit behind the next SCRFD pass, which is already queued and waits for its frames
+        st = self._work_stream(eng)
+        if st is not eng.stream:
+            chips.record_stream(st)
+        with torch.cuda.stream(st):
             self.pending.append(chips[:k].clone())
         self.pending_n += k
         self.count += k
         per_run = self.EMBED_RUN if self.lazy else self.EMBED_RUN // 2
-        if self.pending_n >= per_run:
+        if self.early is not None and not self.runs and self.pending_n >= self.FIRST_RUN:
+            self.flush(eng)                 # host-resident start-up: the SMs have nothing else to do yet, embed what is there
+        elif self.pending_n >= per_run:
             self.flush(eng, keep_remainder=True)
         return rows
+
+    def _work_stream(self, eng):
+        return self.early.engine.stream if self.early is not None else eng.stream
 
     def flush(self, eng, keep_remainder: bool = False):
         if not self.pending_n:
             return
         per_run = self.EMBED_RUN if self.lazy else self.EMBED_RUN // 2
-        with torch.cuda.stream(eng.stream):
+        with torch.cuda.stream(self._work_stream(eng)):
             chips = torch.cat(self.pending, 0) if len(self.pending) > 1 else self.pending[0]
         n = chips.shape[0]
         take = (n // per_run) * per_run if keep_remainder else n
         if take == 0:
             return
-        use = chips[:take].contiguous()
+        with torch.cuda.stream(self._work_stream(eng)):
+            use = chips[:take].contiguous()
         if self.lazy:
-            emb, _ = eng.embed(use, take, False)
-            fp, sim, _ = eng.match(emb, None, None, take)         # normalise(e(x)); sim: against the bank on the device
+            aeng = self.early.engine if self.early is not None else eng
+            TIMELINE.mark(f"arc{len(self.runs)}+", aeng.stream)
+            emb, _ = aeng.embed(use, take, False)
+            fp, sim, _ = aeng.match(emb, None, None, take)        # normalise(e(x)); sim: against the bank on that context
+            TIMELINE.mark(f"arc{len(self.runs)}-", aeng.stream)
             self.raw.append(emb[:take])
             self.chip_list.append(use)
             if self.early is not None:
                 ev = torch.cuda.Event()
-                ev.record(eng.stream)
+                ev.record(aeng.stream)
                 self.runs.append((self.count - self.pending_n, take, sim, ev))
                 self._early_step(eng)
         else:
@@ -643,7 +692,7 @@ class FaceTable:
             self.flip_passes += take
         self.feat_plain.append(fp[:take])
         if take < n:
-            with torch.cuda.stream(eng.stream):
+            with torch.cuda.stream(self._work_stream(eng)):
                 self.pending = [chips[take:].clone()]
             self.pending_n = n - take
         else:
@@ -668,10 +717,10 @@ class FaceTable:
                 self.early_n += len(rows)
             self.runs_decided += 1
         while self.early_n >= self.EARLY_RUN:
-            self._issue_early(eng, min(self.early_n, self.EMBED_RUN))
+            self._issue_early(eng, min(self.early_n, 444))
 
     def _issue_early(self, eng, n: int):
-        feng = self.early.engine
+        feng = self.early.engine        # the stream the plain runs went to: the pass follows the runs it belongs to
         allr = np.concatenate(self.early_rows)
         rows, rest = allr[:n], allr[n:]
         self.early_rows = [rest] if len(rest) else []
@@ -691,8 +740,10 @@ class FaceTable:
             chips = torch.cat(chips, 0).contiguous()
             raws = torch.cat(raws, 0).contiguous()
         order = np.concatenate(order)
+        TIMELINE.mark(f"flip{len(self.early_done)}({len(order)})+", feng.stream)
         _, emb_flip = feng.embed(chips, len(order), "only")
         ff, _, _ = feng.match(raws, emb_flip, None, len(order))
+        TIMELINE.mark(f"flip{len(self.early_done)}-", feng.stream)
         done = torch.cuda.Event()
         done.record(feng.stream)
         self.early_done.append((order, ff[:len(order)], done, chips, raws))      # inputs stay referenced until the pass has run
@@ -700,6 +751,12 @@ class FaceTable:
 
     def finalize(self, eng):
         self.flush(eng)
+        if self.early is not None and self.runs:
+            self.runs[-1][3].synchronize()      # the superset ends here anyway: decide the last runs and issue what is left
+            self._early_step(eng)
+            if self.early_n:
+                self._issue_early(eng, self.early_n)
+            self.early.engine.sync()            # everything the second context produced is final before the main stream reads it
         with torch.cuda.stream(eng.stream):
             if self.count:
                 self.plain = torch.cat(self.feat_plain, 0).contiguous()
@@ -801,9 +858,11 @@ def compute_superset(clip, idxs: Sequence[int], face: FaceEmbedder, cfg, batch: 
         if not prefetch or ci >= len(chunks):
             return None
         with torch.cuda.stream(eng.copy_stream):
+            TIMELINE.mark(f"copy{ci}+", eng.copy_stream)
             fr = clip.device_batch(eng, chunks[ci], stream=eng.copy_stream)
             ev = torch.cuda.Event()
             ev.record(eng.copy_stream)
+            TIMELINE.mark(f"copy{ci}-", eng.copy_stream)
         return fr, ev
 
     # host frames: the copy stream runs PREFETCH batches ahead of the SMs.  The link, not the SMs, paces a host-resident
@@ -829,8 +888,10 @@ def compute_superset(clip, idxs: Sequence[int], face: FaceEmbedder, cfg, batch: 
             frames = eng.resize(frames, nh, nw, area=True)
             h, w = nh, nw
         dyn = face.upright_size(h, w, None)
+        TIMELINE.mark(f"det{ci}+", eng.stream)
         det0 = eng.detect(frames, dyn, face.conf, min_box=int(face.scrfd_min_box_px), max_det=face.max_det)
         al = eng.align(frames, det0, max_faces=max_faces)
+        TIMELINE.mark(f"det{ci}-", eng.stream)
         done = torch.cuda.Event()
         done.record(eng.stream)
         return dict(chunk=chunk, frames=frames, h=h, w=w, dyn=dyn, det0=det0, al=al, done=done)
@@ -864,6 +925,8 @@ def compute_superset(clip, idxs: Sequence[int], face: FaceEmbedder, cfg, batch: 
             records[i] = SampleRecord(i)
         acc0 = det0.acc_count.cpu().numpy()
         _collect_variant(eng, frames, det0, chunk, records, "up", table, max_faces, al=cur["al"], pos_of=pos_of)
+        if table.early is not None:
+            table._early_step(eng)          # flips of the runs whose distances have arrived go out now
         empty = [b for b in range(n) if acc0[b] == 0]
         cur = nxt
         if not empty:
@@ -1329,16 +1392,18 @@ def prescan_batched(clip, fps: int, face: FaceEmbedder, ref_feat, cfg, batch: in
         per = (len(idxs) + world - 1) // world
         mine = idxs[rank * per:(rank + 1) * per]
         lazy = os.environ.get("PCB_EAGER_FLIP", "0") != "1"
-        # early flip passes on a second, lower-priority context: on by default when frames come from the host (the SMs then
-        # wait for PCIe between frame batches); PCB_EARLY_FLIP=1 / 0 forces it on / off
+        # early flip passes + small ArcFace runs: on by default when frames come from the host (the SMs then wait for PCIe
+        # between frame batches); PCB_EARLY_FLIP=1 / 0 forces it on / off
         early = None
         mode = os.environ.get("PCB_EARLY_FLIP", "auto")
         if lazy and mode != "0" and (mode == "1" or bool(getattr(clip, "host_resident", False))):
             bank0 = RefBank(cfg, ref_feat)
             if len(bank0):
-                eng.set_bank(bank0.array())      # FaceTable.flush then gets the distances to the initial bank for free
-                early = EarlyFlips(face.flip_engine(), cfg, fps, carry_in=rank > 0)
+                aux = face.aux_engine()
+                aux.set_bank(bank0.array())      # FaceTable.flush then gets the distances to the initial bank for free
+                early = EarlyFlips(aux, cfg, fps, carry_in=rank > 0)
         records, table = compute_superset(clip, mine, face, cfg, batch=batch, lazy_flip=lazy, early=early)
+        TIMELINE.mark("superset_end", eng.stream)
         eng.sync()
         if stats is not None:
             stats["early_flip_rows"] = int(table.flip_ready.sum()) if (early is not None and table.count) else 0
@@ -1351,6 +1416,7 @@ def prescan_batched(clip, fps: int, face: FaceEmbedder, ref_feat, cfg, batch: in
                 eng.sync()
                 fd0 = 1.0 - s0[:table.count].cpu().numpy().astype(np.float64)
                 table.ensure_flip(eng, _predict_flip_rows(records, mine, fd0, cfg, fps, carry_in=rank > 0))
+        TIMELINE.mark("predicted_flips_end", eng.stream)
         mark("predicted_flips")
         plain_h = table.plain[:table.count].cpu().numpy() if table.count else np.zeros((0, L.FEAT_DIM), np.float32)
         flip_h = (table.flip[:table.count].cpu().numpy() if (table.count and not lazy) else np.zeros((0, L.FEAT_DIM), np.float32))
@@ -1375,6 +1441,7 @@ def prescan_batched(clip, fps: int, face: FaceEmbedder, ref_feat, cfg, batch: in
                          owner=lambda j: max(r for r in range(world) if first_of[r] <= j or r == 0))
         spans = _post_process(spans, clip, fps, face, bank, ref_feat, cfg, trk, wmax, batched=batch, stats=stats, shard=shard)
         mark("refine")
+    TIMELINE.dump()
     if stats is not None:
         stats["phase_ms"] = {b[0]: round(1000.0 * (b[1] - a[1]), 2) for a, b in zip(tmark, tmark[1:])}
     out_bank = bank.array()
