@@ -22,6 +22,7 @@ struct Model {
   std::vector<int> outputs;
   float reg_scale[3] = {1.f, 1.f, 1.f};
   bool has_reg_scale = false;
+  int small_pad_max = 0;   // maps up to this many pixels wide use the trailing-pad layout (0: ring everywhere)
   struct Run {
     int n = 0, h = 0, w = 0;
     std::vector<PTensor> t;
@@ -211,6 +212,9 @@ extern "C" int pcb_model_load(pcb_ctx* c, int slot, const pcb_op* ops, int n_ops
   m->n_tensors = n_tensors;
   m->outputs.assign(outputs, outputs + n_outputs);
   if (reg_scale3) { memcpy(m->reg_scale, reg_scale3, sizeof(float) * 3); m->has_reg_scale = true; }
+  // iResNet: the 14x14 and 7x7 stages (half of the FLOPs) use the trailing-pad layout; PCB_SMALL_PAD_MAX=0 keeps the ring everywhere
+  // (A/B), any other value moves the boundary.  SCRFD keeps the ring: its head maps are read by K3 with the ring geometry.
+  if (slot == PCB_MODEL_ARCFACE) m->small_pad_max = getenv("PCB_SMALL_PAD_MAX") ? atoi(getenv("PCB_SMALL_PAD_MAX")) : 16;
   const uint8_t* blob = (const uint8_t*)blob_host;
   for (int i = 0; i < n_ops; ++i) {
     const pcb_op& op = m->ops[i];
@@ -310,14 +314,18 @@ static int model_prepare(pcb_ctx* c, Model* m, int n, int h, int w, Model::Run**
     *out = &it->second;
     return PCB_OK;
   }
+  int old_cap = 0;
   if (it != m->runs.end()) {   // grow: release the smaller set first
+    old_cap = it->second.n;
     PCB_CUDA(c, cudaStreamSynchronize(c->stream));
     for (auto& t : it->second.t) pcb_dev_free(c, t.data);
     pcb_dev_free(c, it->second.fc_out);
     if (m->last == &it->second) m->last = nullptr;
     m->runs.erase(it);
   }
-  const int cap = pcb_round_up(n, 8);
+  // geometric growth: a caller that ramps its batch up (first small ArcFace runs of a host-resident pre-scan) pays for at most
+  // log2 reallocations, each of which synchronises the stream
+  const int cap = pcb_round_up(n > 2 * old_cap ? n : 2 * old_cap, 8);
   Model::Run r;
   r.n = cap; r.h = h; r.w = w;
   r.t.resize(m->n_tensors);
@@ -336,12 +344,17 @@ static int model_prepare(pcb_ctx* c, Model* m, int n, int h, int w, Model::Run**
     PTensor& o = r.t[op.out];
     if (o.data) return pcb_fail(c, PCB_ERR_ARG, "graph writes a tensor twice");
     o.n = cap;
+    auto layout_for = [&](PTensor& t) {
+      if (!t.dense && t.w <= m->small_pad_max && t.h <= m->small_pad_max) { t.pad_lo = 0; t.pad = 1; }
+      else { t.pad_lo = kPadLo; t.pad = kPad; }
+    };
     switch (op.kind) {
       case PCB_OP_CONV: {
         const bool stem = op.in0 == 0;
         const int s = stem ? 1 : op.stride;
         o.h = a.h / s; o.w = a.w / s; o.c = op.cout; o.cp = pcb_round_up(op.cout, 8);
         o.f32 = (op.flags & PCB_OPF_OUT_F32) != 0;
+        layout_for(o);
         if (op.out2 >= 0) {
           PTensor& o2 = r.t[op.out2];
           if (o2.data) return pcb_fail(c, PCB_ERR_ARG, "graph writes a tensor twice");
@@ -353,11 +366,11 @@ static int model_prepare(pcb_ctx* c, Model* m, int n, int h, int w, Model::Run**
         }
         break;
       }
-      case PCB_OP_AFFINE: o.h = a.h; o.w = a.w; o.c = a.c; o.cp = a.cp; break;
+      case PCB_OP_AFFINE: o.h = a.h; o.w = a.w; o.c = a.c; o.cp = a.cp; layout_for(o); break;
       case PCB_OP_MAXPOOL3S2:
-      case PCB_OP_AVGPOOL2: o.h = a.h / 2; o.w = a.w / 2; o.c = a.c; o.cp = a.cp; break;
+      case PCB_OP_AVGPOOL2: o.h = a.h / 2; o.w = a.w / 2; o.c = a.c; o.cp = a.cp; layout_for(o); break;
       case PCB_OP_UPSAMPLE_ADD:
-      case PCB_OP_ADD: o.h = a.h; o.w = a.w; o.c = a.c; o.cp = a.cp; break;
+      case PCB_OP_ADD: o.h = a.h; o.w = a.w; o.c = a.c; o.cp = a.cp; layout_for(o); break;
       case PCB_OP_AFFINE_FLATTEN: o.dense = true; o.h = 1; o.w = 1; o.c = a.h * a.w * a.cp; o.cp = o.c; break;
       default: return pcb_fail(c, PCB_ERR_ARG, "unknown op kind");
     }
@@ -431,14 +444,14 @@ static int model_run(pcb_ctx* c, Model* m, Model::Run* r) {
 }
 
 __global__ void gather_nchw_kernel(const __half* __restrict__ in, float* __restrict__ out, int n, int c, int h, int w, int cp, int dense,
-                                   int is_f32) {
+                                   int is_f32, int pad_lo, int pad) {
   const long long total = (long long)n * c * h * w;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     const int x = (int)(idx % w);
     const int y = (int)((idx / w) % h);
     const int ch = (int)((idx / ((long long)w * h)) % c);
     const int img = (int)(idx / ((long long)w * h * c));
-    const long long row = dense ? img : pcb_prow(img, y, x, h, w);
+    const long long row = dense ? img : pcb_prow_l(img, y, x, h, w, pad_lo, pad);
     out[idx] = is_f32 ? ((const float*)in)[row * cp + ch] : __half2float(in[row * cp + ch]);
   }
 }
@@ -458,7 +471,7 @@ extern "C" int pcb_model_get_tensor(pcb_ctx* c, int slot, int tid, float* out_ho
   const size_t total = (size_t)t.n * C * (t.dense ? 1 : t.h * t.w);
   float* d = nullptr;
   PCB_CUDA(c, cudaMalloc(&d, total * sizeof(float)));
-  gather_nchw_kernel<<<1024, 256, 0, c->stream>>>(t.data, d, t.n, C, t.dense ? 1 : t.h, t.dense ? 1 : t.w, t.cp, t.dense ? 1 : 0, t.f32 ? 1 : 0);
+  gather_nchw_kernel<<<1024, 256, 0, c->stream>>>(t.data, d, t.n, C, t.dense ? 1 : t.h, t.dense ? 1 : t.w, t.cp, t.dense ? 1 : 0, t.f32 ? 1 : 0, t.pad_lo, t.pad);
   cudaError_t e = cudaMemcpyAsync(out_host, d, total * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
   cudaFree(d);
@@ -510,10 +523,12 @@ extern "C" int pcb_embed(pcb_ctx* c, const uint8_t* chips_dev, int f, float* emb
   if (!m) return pcb_fail(c, PCB_ERR_STATE, "embed: no ArcFace graph loaded");
   // 0: e(x) only, 1: e(x) and e(flip x), 2: e(flip x) only
   const int mode = emb_dev ? (emb_flip_dev ? 1 : 0) : 2;
-  // faces per graph run.  444 images make the 14x14 / 28x28 / 7x7 stages 3.0 / 10.5 / 1.9 waves of 256-row tiles over
-  // 148 SMs (>= 95% wave efficiency) and bound activation memory at ~11 GB for iResNet-100.
+  // images per graph run: whole waves of 256-row tiles over 74 CTA pairs in the 14x14 stage, which is half of the FLOPs.
+  // Trailing-pad layout (225 rows per 14x14 image): 504 images = 443 pair tiles = 5.99 waves (28x28: 11.97, 56x56: 44.8);
+  // ring layout (256 rows): 444 images = 6.0 waves.  Activation memory ~12.5 GB for iResNet-100.
   static const int chunk_env = getenv("PCB_EMBED_CHUNK") ? atoi(getenv("PCB_EMBED_CHUNK")) : 0;
-  const int chunk = chunk_env > 0 ? chunk_env : (mode == 1 ? 222 : 444);
+  const int run = m->small_pad_max >= 14 ? 504 : 444;
+  const int chunk = chunk_env > 0 ? chunk_env : (mode == 1 ? run / 2 : run);
   for (int f0 = 0; f0 < f; f0 += chunk) {
     const int fn = f - f0 < chunk ? f - f0 : chunk;
     const int imgs = mode == 1 ? 2 * fn : fn;

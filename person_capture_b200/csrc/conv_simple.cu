@@ -25,6 +25,7 @@ struct SimpleParams {
   int cin_eff;               // channels to reduce over (<= cp_in)
   int cout_store;            // channels to write
   int taps, cin_w, stride, act, dense, out_f32_stride, out_f32_cols;
+  int iplo, ipad, oplo, opad;   // input / output tensor padding
 };
 
 __global__ void conv_simple_kernel(const SimpleParams p) {
@@ -48,11 +49,11 @@ __global__ void conv_simple_kernel(const SimpleParams p) {
       for (int t = 0; t < p.taps; ++t) {
         const int dy = p.taps == 9 ? t / 3 - 1 : 0, dx = p.taps == 9 ? t % 3 - 1 : 0;
         if (yc + dy < 0 || yc + dy >= p.h || xc + dx < 0 || xc + dx >= p.w_) continue;   // zero padding
-        const __half* a = p.in + pcb_prow(img, yc + dy, xc + dx, p.h, p.w_) * p.cp_in;
+        const __half* a = p.in + pcb_prow_l(img, yc + dy, xc + dx, p.h, p.w_, p.iplo, p.ipad) * p.cp_in;
         const __half* wr = p.w + ((long long)co * p.taps + t) * p.cin_w;
         for (int ci = 0; ci < p.cin_eff; ++ci) acc = fmaf(__half2float(a[ci]), __half2float(wr[ci]), acc);
       }
-      orow = pcb_prow(img, yo, xo, p.ho, p.wo);
+      orow = pcb_prow_l(img, yo, xo, p.ho, p.wo, p.oplo, p.opad);
     }
     float y = fmaf(acc, p.scale[co], p.bias[co]);
     if (p.out_f32) {
@@ -84,6 +85,8 @@ int pcb_conv_simple(pcb_ctx* c, const ConvArgs& a) {
   p.h = in.h;
   p.w_ = in.w;
   p.cp_in = in.cp;
+  p.iplo = in.pad_lo; p.ipad = in.pad;
+  p.oplo = a.out ? a.out->pad_lo : kPadLo; p.opad = a.out ? a.out->pad : kPad;
   p.cin_eff = in.cp < w.cin_w ? in.cp : w.cin_w;
   p.taps = w.taps;
   p.cin_w = w.cin_w;

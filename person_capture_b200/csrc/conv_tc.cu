@@ -41,6 +41,7 @@ struct ConvTcParams {
   int n_tile, n_tiles, m_tiles;
   int stride;      // 1 | 2
   int hp_out, wp_out;
+  int pad_lo, pad_hi, pad_lo_out;   // input padding before / after the pixels, output padding before (per-tensor layout)
   int out_cp;      // channel stride of the fp16 output
   int out_c_store; // channels to store (<= out_cp, multiple of 8)
   int act;
@@ -261,10 +262,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int img = (int)(prow / plane);
         const int rem = (int)(prow - (long long)img * plane);
         const int y = rem / p.wp, x = rem - y * p.wp;
-        valid = valid && y >= kPadLo && y <= p.hp - 1 - (kPad - kPadLo) && x >= kPadLo && x <= p.wp - 1 - (kPad - kPadLo);
+        valid = valid && y >= p.pad_lo && y <= p.hp - 1 - p.pad_hi && x >= p.pad_lo && x <= p.wp - 1 - p.pad_hi;
         if (p.stride == 2) {
-          valid = valid && (((y - kPadLo) | (x - kPadLo)) & 1) == 0;
-          orow = ((long long)img * p.hp_out + ((y - kPadLo) >> 1) + kPadLo) * p.wp_out + ((x - kPadLo) >> 1) + kPadLo;
+          valid = valid && (((y - p.pad_lo) | (x - p.pad_lo)) & 1) == 0;
+          orow = ((long long)img * p.hp_out + ((y - p.pad_lo) >> 1) + p.pad_lo_out) * p.wp_out + ((x - p.pad_lo) >> 1) + p.pad_lo_out;
         }
       }
       if (ok) ok = mbar_wait(&tfull_bar[acc], acc_phase, p.err, 104);
@@ -407,8 +408,11 @@ int pcb_conv_tc(pcb_ctx* c, const ConvArgs& a) {
   ConvTcParams p{};
   p.rows = (int)in.rows();
   p.dense = in.dense ? 1 : 0;
-  p.hp = in.dense ? 0 : in.h + kPad;
-  p.wp = in.dense ? 0 : in.w + kPad;
+  p.hp = in.dense ? 0 : in.h + in.pad;
+  p.wp = in.dense ? 0 : in.w + in.pad;
+  p.pad_lo = in.pad_lo;
+  p.pad_hi = in.pad - in.pad_lo;
+  p.pad_lo_out = in.pad_lo;
   p.taps = w.taps;
   p.cin_w = w.cin_w;
   p.kchunks = w.cin_w / kKC;
@@ -431,8 +435,10 @@ int pcb_conv_tc(pcb_ctx* c, const ConvArgs& a) {
     else p.out = out.data;
     p.out_cp = out.cp;
     p.out_c_store = out.cp;
-    p.hp_out = out.h + kPad;
-    p.wp_out = out.w + kPad;
+    p.hp_out = out.h + out.pad;
+    p.wp_out = out.w + out.pad;
+    p.pad_lo_out = out.pad_lo;
+    if (a.stride == 1 && (out.pad != in.pad || out.pad_lo != in.pad_lo)) return pcb_fail(c, PCB_ERR_ARG, "conv_tc: stride-1 layers keep the layout");
     if (out.cp > w.npad) return pcb_fail(c, PCB_ERR_ARG, "conv_tc: output channels exceed packed weight rows");
     if (a.residual) {
       if (a.residual->f32) p.residual_f32 = (const float*)a.residual->data;

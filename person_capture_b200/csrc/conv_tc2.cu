@@ -109,6 +109,8 @@ struct Conv2Params {
   int fd_plane_shift, fd_wp_shift;
   int stride;      // 1 | 2
   int hp_out, wp_out;
+  int pad_lo, pad_hi;   // input tensor: padding before / after the pixels of a row and of an image (per-tensor layout)
+  int pad_lo_out;       // output tensor: padding before the pixels
   int out_cp;      // channel stride of the P-layout output
   int out_c_store; // channels to store (<= out_cp, multiple of 8)
   int act;
@@ -393,7 +395,7 @@ __device__ __forceinline__ RowInfo row_info(const Conv2Params& p, long long prow
     const int j = rem / p.s_bx, i = rem - j * p.s_bx;
     const int img = ig * p.s_nb + io, oy = ty * p.s_by + j, ox = tx * p.s_bx + i;
     r.valid = io < p.s_nb && img < p.s_n && oy < p.s_ho && ox < p.s_wo;
-    r.orow = ((long long)img * p.hp_out + oy + kPadLo) * p.wp_out + ox + kPadLo;
+    r.orow = ((long long)img * p.hp_out + oy + p.pad_lo_out) * p.wp_out + ox + p.pad_lo_out;
     return r;
   }
   r.valid = prow < p.rows;
@@ -403,10 +405,10 @@ __device__ __forceinline__ RowInfo row_info(const Conv2Params& p, long long prow
     const int img = fast_div((int)prow, p.fd_plane_mul, p.fd_plane_shift);
     const int rem = (int)prow - img * plane;
     const int y = fast_div(rem, p.fd_wp_mul, p.fd_wp_shift), x = rem - y * p.wp;
-    r.valid = r.valid && y >= kPadLo && y <= p.hp - 1 - (kPad - kPadLo) && x >= kPadLo && x <= p.wp - 1 - (kPad - kPadLo);
+    r.valid = r.valid && y >= p.pad_lo && y <= p.hp - 1 - p.pad_hi && x >= p.pad_lo && x <= p.wp - 1 - p.pad_hi;
     if (p.stride == 2) {
-      r.valid = r.valid && (((y - kPadLo) | (x - kPadLo)) & 1) == 0;
-      r.orow = ((long long)img * p.hp_out + ((y - kPadLo) >> 1) + kPadLo) * p.wp_out + ((x - kPadLo) >> 1) + kPadLo;
+      r.valid = r.valid && (((y - p.pad_lo) | (x - p.pad_lo)) & 1) == 0;
+      r.orow = ((long long)img * p.hp_out + ((y - p.pad_lo) >> 1) + p.pad_lo_out) * p.wp_out + ((x - p.pad_lo) >> 1) + p.pad_lo_out;
     }
   }
   return r;
@@ -541,7 +543,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 const int ky = p.taps == 9 ? t / 3 : 1, kx = p.taps == 9 ? t % 3 : 1;
                 mbar_expect_tx(&a_full[stage], (uint32_t)p.a_tx_bytes);
                 tma_load_4d(&tmA, &a_full[stage], smem_u32(smem_a + (size_t)stage * p.a_stage_bytes), kc * p.kc,
-                            2 * tx * p.s_bx + kx - 1 + kPadLo, 2 * ty * p.s_by + ky - 1 + kPadLo, ig * p.s_nb);   // -1: left / top pad = out-of-bounds zero fill
+                            2 * tx * p.s_bx + kx - 1 + p.pad_lo, 2 * ty * p.s_by + ky - 1 + p.pad_lo, ig * p.s_nb);   // -1: left / top pad = out-of-bounds zero fill
               }
               __syncwarp();
               if (++stage == p.a_stages) { stage = 0; phase ^= 1; }
@@ -1197,8 +1199,11 @@ int pcb_conv_tc2(pcb_ctx* c, const ConvArgs& a) {
   Conv2Params p{};
   p.rows = (int)in.rows();
   p.dense = in.dense ? 1 : 0;
-  p.hp = in.dense ? 0 : in.h + kPad;
-  p.wp = in.dense ? 0 : in.w + kPad;
+  p.hp = in.dense ? 0 : in.h + in.pad;
+  p.wp = in.dense ? 0 : in.w + in.pad;
+  p.pad_lo = in.pad_lo;
+  p.pad_hi = in.pad - in.pad_lo;
+  p.pad_lo_out = in.pad_lo;
   p.taps = w.taps;
   p.cin_w = w.cin_w;
   {
@@ -1241,8 +1246,15 @@ int pcb_conv_tc2(pcb_ctx* c, const ConvArgs& a) {
     else p.out = out.data;
     p.out_cp = out.cp;
     p.out_c_store = out.cp;
-    p.hp_out = out.h + kPad;
-    p.wp_out = out.w + kPad;
+    p.hp_out = out.h + out.pad;
+    p.wp_out = out.w + out.pad;
+    p.pad_lo_out = out.pad_lo;
+    // stride-1 layers address output rows as input rows: same layout on both sides (and on the residual / second output)
+    if (!in.dense && a.stride == 1 && (out.pad != in.pad || out.pad_lo != in.pad_lo))
+      return pcb_fail(c, PCB_ERR_ARG, "conv_tc2: a stride-1 layer cannot change the activation layout");
+    if ((a.residual && (a.residual->pad != out.pad || a.residual->pad_lo != out.pad_lo)) ||
+        (a.out2 && (a.out2->pad != out.pad || a.out2->pad_lo != out.pad_lo)))
+      return pcb_fail(c, PCB_ERR_ARG, "conv_tc2: residual / second output must share the output's layout");
     if (out.cp > w.npad) return pcb_fail(c, PCB_ERR_ARG, "conv_tc2: output channels exceed packed weight rows");
     if (a.residual) {
       p.residual = a.residual->data;
@@ -1367,7 +1379,7 @@ int pcb_conv_tc2(pcb_ctx* c, const ConvArgs& a) {
 
   CUtensorMap tmA, tmA2, tmB, tmO, tmO2;
   if (strided) {
-    if (!make_map_4d_s2(&tmA, in.data, in.n, in.h + kPad, in.w + kPad, in.cp, p.kc, p.s_bx, p.s_by, p.s_nb))
+    if (!make_map_4d_s2(&tmA, in.data, in.n, in.h + in.pad, in.w + in.pad, in.cp, p.kc, p.s_bx, p.s_by, p.s_nb))
       return pcb_fail(c, PCB_ERR_CUDA, "cuTensorMapEncodeTiled(A strided) failed");
     tmA2 = tmA;
   } else {

@@ -9,11 +9,13 @@ namespace {
 struct Geo {
   int n, h, w, cp;      // output tensor logical dims + channel stride
   int ih, iw, icp;      // input dims
+  int plo, pad;         // output tensor padding (PTensor::pad_lo / pad)
+  int iplo, ipad;       // input tensor padding
 };
 
-__device__ __forceinline__ long long prow(int img, int y, int x, int h, int w) {
-  return pcb_prow(img, y, x, h, w);
-}
+// output-tensor row / input-tensor row of pixel (y, x)
+__device__ __forceinline__ long long orow(const Geo& g, int img, int y, int x) { return pcb_prow_l(img, y, x, g.h, g.w, g.plo, g.pad); }
+__device__ __forceinline__ long long irow(const Geo& g, int img, int y, int x) { return pcb_prow_l(img, y, x, g.ih, g.iw, g.iplo, g.ipad); }
 
 __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
   const __half2* h = (const __half2*)&v;
@@ -45,12 +47,11 @@ __global__ void affine_kernel(const __half* __restrict__ in, __half* __restrict_
                               const float* __restrict__ bias, Geo g, long long total) {
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     PCB_DECODE_IDX(idx, g)
-    const long long r = prow(img, y, x, g.h, g.w);
     float f[8];
-    unpack8(*(const uint4*)(in + r * g.icp + c8 * 8), f);
+    unpack8(*(const uint4*)(in + irow(g, img, y, x) * g.icp + c8 * 8), f);
 #pragma unroll
     for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], __ldg(scale + c8 * 8 + j), __ldg(bias + c8 * 8 + j));
-    *(uint4*)(out + r * g.cp + c8 * 8) = pack8(f);
+    *(uint4*)(out + orow(g, img, y, x) * g.cp + c8 * 8) = pack8(f);
   }
 }
 
@@ -59,9 +60,8 @@ __global__ void affine_flatten_kernel(const __half* __restrict__ in, __half* __r
   // out: dense [n][h*w*cp] in (y, x, c) order
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     PCB_DECODE_IDX(idx, g)
-    const long long r = prow(img, y, x, g.h, g.w);
     float f[8];
-    unpack8(*(const uint4*)(in + r * g.icp + c8 * 8), f);
+    unpack8(*(const uint4*)(in + irow(g, img, y, x) * g.icp + c8 * 8), f);
 #pragma unroll
     for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], __ldg(scale + c8 * 8 + j), __ldg(bias + c8 * 8 + j));
     *(uint4*)(out + (((long long)img * g.h + y) * g.w + x) * g.cp + c8 * 8) = pack8(f);
@@ -82,12 +82,12 @@ __global__ void maxpool3s2_kernel(const __half* __restrict__ in, __half* __restr
         const int xx = 2 * x + dx;
         if (xx < 0 || xx >= g.iw) continue;
         float f[8];
-        unpack8(*(const uint4*)(in + prow(img, yy, xx, g.ih, g.iw) * g.icp + c8 * 8), f);
+        unpack8(*(const uint4*)(in + irow(g, img, yy, xx) * g.icp + c8 * 8), f);
 #pragma unroll
         for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], f[j]);
       }
     }
-    *(uint4*)(out + prow(img, y, x, g.h, g.w) * g.cp + c8 * 8) = pack8(m);
+    *(uint4*)(out + orow(g, img, y, x) * g.cp + c8 * 8) = pack8(m);
   }
 }
 
@@ -100,13 +100,13 @@ __global__ void avgpool2_kernel(const __half* __restrict__ in, __half* __restric
 #pragma unroll
       for (int dx = 0; dx < 2; ++dx) {
         float f[8];
-        unpack8(*(const uint4*)(in + prow(img, 2 * y + dy, 2 * x + dx, g.ih, g.iw) * g.icp + c8 * 8), f);
+        unpack8(*(const uint4*)(in + irow(g, img, 2 * y + dy, 2 * x + dx) * g.icp + c8 * 8), f);
 #pragma unroll
         for (int j = 0; j < 8; ++j) s[j] += f[j];
       }
 #pragma unroll
     for (int j = 0; j < 8; ++j) s[j] *= 0.25f;
-    *(uint4*)(out + prow(img, y, x, g.h, g.w) * g.cp + c8 * 8) = pack8(s);
+    *(uint4*)(out + orow(g, img, y, x) * g.cp + c8 * 8) = pack8(s);
   }
 }
 
@@ -115,8 +115,8 @@ __global__ void add_kernel(const __half* __restrict__ a, const __half* __restric
                            long long total) {
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     PCB_DECODE_IDX(idx, g)
-    const long long r = prow(img, y, x, g.h, g.w);
-    const long long rb = up ? prow(img, y >> 1, x >> 1, g.ih, g.iw) : r;
+    const long long r = orow(g, img, y, x);       // `a` has the output's geometry and layout
+    const long long rb = up ? irow(g, img, y >> 1, x >> 1) : irow(g, img, y, x);
     float fa[8], fb[8];
     unpack8(*(const uint4*)(a + r * g.cp + c8 * 8), fa);
     unpack8(*(const uint4*)(b + rb * g.icp + c8 * 8), fb);
@@ -137,6 +137,7 @@ inline Geo geo(const PTensor& in, const PTensor& out) {
   Geo g;
   g.n = out.n; g.h = out.h; g.w = out.w; g.cp = out.cp;
   g.ih = in.h; g.iw = in.w; g.icp = in.cp;
+  g.plo = out.pad_lo; g.pad = out.pad; g.iplo = in.pad_lo; g.ipad = in.pad;
   return g;
 }
 

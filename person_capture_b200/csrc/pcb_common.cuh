@@ -45,12 +45,20 @@ constexpr int kPad = PCB_PAD;        // pad elements per dimension in total
 __host__ __device__ __forceinline__ long long pcb_prow(int img, int y, int x, int h, int w) {
   return ((long long)img * (h + kPad) + (y + kPadLo)) * (w + kPad) + (x + kPadLo);
 }
+// The layout is a property of the TENSOR (round 2): small maps of the ArcFace graph use the trailing-pad form (pad_lo 0, pad 1
+// -- 225 instead of 256 GEMM rows per 14x14 image, 64 instead of 81 per 7x7 image), everything else the ring (pad_lo 1, pad 2).
+// Round 1 measured the trailing pad as a GLOBAL switch: small maps +13-20 %, wide maps -12...-30 %, so it stayed off; the
+// stride-2 convolutions that cross from 28x28 to 14x14 write the other layout for free (they address output rows themselves).
+__host__ __device__ __forceinline__ long long pcb_prow_l(int img, int y, int x, int h, int w, int pad_lo, int pad) {
+  return ((long long)img * (h + pad) + (y + pad_lo)) * (w + pad) + (x + pad_lo);
+}
 struct PTensor {
   __half* data = nullptr;
   int n = 0, h = 0, w = 0, c = 0, cp = 0;  // logical dims, cp = padded channel stride
+  int pad_lo = kPadLo, pad = kPad;         // spatial padding of THIS tensor (see above)
   bool dense = false;                      // dense: [n][cp] rows without spatial padding (FC input)
   bool f32 = false;                        // elements are float (iResNet residual stream) instead of __half
-  size_t rows() const { return dense ? (size_t)n : (size_t)n * (h + kPad) * (w + kPad); }
+  size_t rows() const { return dense ? (size_t)n : (size_t)n * (h + pad) * (w + pad); }
   size_t bytes() const { return rows() * cp * (f32 ? sizeof(float) : sizeof(__half)); }
 };
 

@@ -603,12 +603,13 @@ class FaceTable:
     Lazy mode (single process): only e(x) is computed up front, as the reference does while no span is active
     (face_embedder.py:1295); chips and raw embeddings stay resident and `ensure_flip` computes e(flip x) for the rows the
     replay actually evaluates in the active state (plus a look-ahead window, so the GPU sees large batches)."""
-    # images per ArcFace graph run (pcb_embed chunk; half as many faces when both variants are computed).  444 fills the 148 SMs
-    # to >= 95 % in every iResNet stage (14x14: 888 tiles = 6.0 waves, 28x28: 10.5, 56x56: 39.4)
-    EMBED_RUN = int(os.environ.get("PCB_EMBED_RUN", "444"))
+    # images per ArcFace graph run (= pcb_embed's chunk; half as many faces when both variants are computed): whole waves of
+    # tiles in the 14x14 stage -- 504 images with the trailing-pad layout of the small maps (443 pair tiles = 5.99 waves on 74
+    # CTA pairs; 28x28: 11.97 waves, 56x56: 44.8), 444 with the ring everywhere (PCB_SMALL_PAD_MAX=0)
+    EMBED_RUN = int(os.environ.get("PCB_EMBED_RUN", "504" if int(os.environ.get("PCB_SMALL_PAD_MAX", "16")) >= 14 else "444"))
     # host-resident clips (early flips on): plain runs of this many images as the chips accumulate, and flip passes of at least
     # EARLY_RUN images (148 images = one full wave of 14x14 pair tiles)
-    HOST_RUN = int(os.environ.get("PCB_HOST_RUN", "222"))
+    HOST_RUN = int(os.environ.get("PCB_HOST_RUN", "252"))
     FIRST_RUN = int(os.environ.get("PCB_FIRST_RUN", "74"))     # the first run goes out as soon as this many chips exist
     EARLY_RUN = int(os.environ.get("PCB_EARLY_RUN", "148"))
 
