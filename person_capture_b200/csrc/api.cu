@@ -30,6 +30,7 @@ struct Model {
   };
   std::map<std::vector<int>, Run> runs;
   Run* last = nullptr;
+  unsigned long long generation = 0;   // bumped whenever an activation set is (re)allocated: captured graphs hold its pointers
 };
 
 int pcb_fail(pcb_ctx* c, int code, const char* what, cudaError_t e) {
@@ -93,6 +94,7 @@ extern "C" void pcb_destroy(pcb_ctx* c) {
   if (c->live_sim_host) cudaFreeHost(c->live_sim_host);
   if (c->live_row_stage) cudaFreeHost(c->live_row_stage);
   if (c->bank_ev) cudaEventDestroy(c->bank_ev);
+  for (auto& kv : c->embed_graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   for (int i = 0; i < 4; ++i) delete c->models[i];
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -273,6 +275,10 @@ extern "C" int pcb_model_load(pcb_ctx* c, int slot, const pcb_op* ops, int n_ops
       if (!m->aff_scale[i] || !m->aff_bias[i]) { delete m; return pcb_fail(c, PCB_ERR_CUDA, "model_load: param upload failed"); }
     }
   }
+  if (slot == PCB_MODEL_ARCFACE) {            // captured small-call graphs hold pointers into the old model
+    for (auto& kv : c->embed_graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    c->embed_graphs.clear();
+  }
   if (Model* old = c->models[slot]) {
     // the replaced graph's weights, vectors and activation sets go back to the device now, not at pcb_destroy
     PCB_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -377,6 +383,7 @@ static int model_prepare(pcb_ctx* c, Model* m, int n, int h, int w, Model::Run**
     rc = alloc_tensor(c, o);
     if (rc) return rc;
   }
+  m->generation++;
   auto ins = m->runs.emplace(key, std::move(r));
   for (auto& t : ins.first->second.t) if (t.data) t.n = n;
   *out = &ins.first->second;
@@ -529,6 +536,59 @@ extern "C" int pcb_embed(pcb_ctx* c, const uint8_t* chips_dev, int f, float* emb
   static const int chunk_env = getenv("PCB_EMBED_CHUNK") ? atoi(getenv("PCB_EMBED_CHUNK")) : 0;
   const int run = m->small_pad_max >= 14 ? 504 : 444;
   const int chunk = chunk_env > 0 ? chunk_env : (mode == 1 ? run / 2 : run);
+  // 1..8 faces (the lock-face ROI path embeds one face + its mirror per frame): the ~110 launches of the graph are
+  // launch-latency bound at this size, so they are captured once per (mode, faces) into a CUDA graph that reads a fixed
+  // staging buffer and is replayed with one launch.  The first call of a key runs eagerly (one-time attribute / allocation work
+  // must not happen inside a capture), the second captures, later ones replay.  PCB_EMBED_GRAPH=0 disables.
+  static const int graph_on = getenv("PCB_EMBED_GRAPH") ? atoi(getenv("PCB_EMBED_GRAPH")) : 1;
+  if (graph_on && f >= 1 && f <= 8 && !c->profile && c->conv_impl == 0) {
+    const int imgs = mode == 1 ? 2 * f : f;
+    Model::Run* r = nullptr;
+    int rc = model_prepare(c, m, imgs, PCB_CHIP, PCB_CHIP, &r);
+    if (rc) return rc;
+    const size_t chip_bytes = (size_t)PCB_CHIP * PCB_CHIP * 3;
+    if (!c->embed_stage) {
+      c->embed_stage = (uint8_t*)pcb_dev_alloc(c, 8 * chip_bytes, true);
+      if (!c->embed_stage) return pcb_fail(c, PCB_ERR_CUDA, "embed: staging alloc failed");
+    }
+    pcb_ctx::EmbedGraph& g = c->embed_graphs[mode * 64 + f];
+    if (g.exec && g.gen != m->generation) {      // the activation set moved: the captured pointers are stale
+      cudaGraphExecDestroy(g.exec);
+      g.exec = nullptr;
+    }
+    PCB_CUDA(c, cudaMemcpyAsync(c->embed_stage, chips_dev, f * chip_bytes, cudaMemcpyDeviceToDevice, c->stream));
+    if (g.exec) {
+      PCB_CUDA(c, cudaGraphLaunch(g.exec, c->stream));
+      c->launches += 1;
+    } else if (!g.warmed) {
+      rc = pcb_chip_patch_impl(c, c->embed_stage, f, mode, r->t[0].data);
+      if (!rc) rc = model_run(c, m, r);
+      if (rc) return rc;
+      g.warmed = true;
+    } else {
+      cudaGraph_t graph = nullptr;
+      PCB_CUDA(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+      rc = pcb_chip_patch_impl(c, c->embed_stage, f, mode, r->t[0].data);
+      if (!rc) rc = model_run(c, m, r);
+      cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
+      if (rc || ce != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        return rc ? rc : pcb_fail(c, PCB_ERR_CUDA, "embed: graph capture failed", ce);
+      }
+      ce = cudaGraphInstantiate(&g.exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (ce != cudaSuccess) { g.exec = nullptr; return pcb_fail(c, PCB_ERR_CUDA, "embed: graph instantiate failed", ce); }
+      g.gen = m->generation;
+      PCB_CUDA(c, cudaGraphLaunch(g.exec, c->stream));
+    }
+    m->last = r;
+    float* first = mode == 2 ? emb_flip_dev : emb_dev;
+    PCB_CUDA(c, cudaMemcpyAsync(first, r->fc_out, (size_t)f * PCB_FEAT_DIM * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+    if (mode == 1)
+      PCB_CUDA(c, cudaMemcpyAsync(emb_flip_dev, r->fc_out + (size_t)f * PCB_FEAT_DIM, (size_t)f * PCB_FEAT_DIM * sizeof(float),
+                                  cudaMemcpyDeviceToDevice, c->stream));
+    return PCB_OK;
+  }
   for (int f0 = 0; f0 < f; f0 += chunk) {
     const int fn = f - f0 < chunk ? f - f0 : chunk;
     const int imgs = mode == 1 ? 2 * fn : fn;

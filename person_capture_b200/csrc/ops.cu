@@ -69,25 +69,28 @@ __global__ void affine_flatten_kernel(const __half* __restrict__ in, __half* __r
 }
 
 __global__ void maxpool3s2_kernel(const __half* __restrict__ in, __half* __restrict__ out, Geo g, long long total) {
-  // 3x3, stride 2, pad 1 (pad value -inf): window rows 2y-1..2y+1 of the input
+  // 3x3, stride 2, pad 1 (pad value -inf): window rows 2y-1..2y+1 of the input.  fp16 max is exact, so the window is reduced in
+  // packed half2 registers (no fp32 round trip): 9 16-byte loads + 36 HMNMX2 per 8 channels -- the kernel is bound by L2 reads
+  // (every input pixel is touched 2.25 times), not by arithmetic.
+  const __half2 lowest = __half2half2(__ushort_as_half((unsigned short)0xFBFF));      // -65504
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     PCB_DECODE_IDX(idx, g)
-    float m[8];
+    __half2 m[4] = {lowest, lowest, lowest, lowest};
 #pragma unroll
-    for (int j = 0; j < 8; ++j) m[j] = -65504.f;
     for (int dy = -1; dy <= 1; ++dy) {
       const int yy = 2 * y + dy;
       if (yy < 0 || yy >= g.ih) continue;
+#pragma unroll
       for (int dx = -1; dx <= 1; ++dx) {
         const int xx = 2 * x + dx;
         if (xx < 0 || xx >= g.iw) continue;
-        float f[8];
-        unpack8(*(const uint4*)(in + irow(g, img, yy, xx) * g.icp + c8 * 8), f);
+        const uint4 v = __ldg((const uint4*)(in + irow(g, img, yy, xx) * g.icp + c8 * 8));
+        const __half2* h = (const __half2*)&v;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], f[j]);
+        for (int j = 0; j < 4; ++j) m[j] = __hmax2(m[j], h[j]);
       }
     }
-    *(uint4*)(out + orow(g, img, y, x) * g.cp + c8 * 8) = pack8(m);
+    *(uint4*)(out + orow(g, img, y, x) * g.cp + c8 * 8) = *(const uint4*)m;
   }
 }
 

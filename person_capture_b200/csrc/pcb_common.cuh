@@ -123,6 +123,10 @@ struct pcb_ctx {
   float* live_row_stage = nullptr;   // pinned [512]: the one bank row that changed
   int live_rows = 0, live_cap = 0;
   int live_bank_rows = 0;            // bank rows the device-side sims are current for (-1: never refreshed)
+  // small ArcFace calls (lock-face ROI path: 1-2 faces per frame) replay a captured CUDA graph of the ~110 launches
+  struct EmbedGraph { cudaGraphExec_t exec = nullptr; unsigned long long gen = 0; bool warmed = false; };
+  std::map<int, EmbedGraph> embed_graphs;     // key = mode * 64 + faces
+  uint8_t* embed_stage = nullptr;             // [8][112][112][3] fixed input of those graphs
   // profiling (bench.py roofline): CUDA events around every conv launch + algorithmic FLOPs
   bool profile = false;
   std::vector<cudaEvent_t> ev_pool;

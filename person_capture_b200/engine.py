@@ -28,6 +28,7 @@ class DetectResult:
     acc_score: torch.Tensor  # [n, max_det]
     acc_count: torch.Tensor  # [n]
     acc_unfiltered: torch.Tensor  # [n] entries before the min-size filter
+    counts: Optional[torch.Tensor] = None   # [3, n] = raw_count | acc_count | acc_unfiltered when allocated by Engine.alloc_detect
 
 
 @dataclass
@@ -147,9 +148,12 @@ class Engine:
     # ------------------------------------------------------------------ K1+K2+K3
     def alloc_detect(self, n: int, max_det: int) -> DetectResult:
         e = self.empty
-        return DetectResult(e((n, max_det, 5), torch.float32), e((n, max_det, 10), torch.float32), e((n,), torch.int32),
-                            e((n, max_det, 4), torch.int32), e((n, max_det, 10), torch.float32), e((n, max_det), torch.float32),
-                            e((n,), torch.int32), e((n,), torch.int32))
+        counts = e((3, n), torch.int32)     # raw / accumulated / unfiltered counts share one buffer: one device->host copy reads all
+        res = DetectResult(e((n, max_det, 5), torch.float32), e((n, max_det, 10), torch.float32), counts[0],
+                           e((n, max_det, 4), torch.int32), e((n, max_det, 10), torch.float32), e((n, max_det), torch.float32),
+                           counts[1], counts[2])
+        res.counts = counts
+        return res
 
     def _detect_args(self, frames, S, thresh, rot, pad, fix_mode, fix_scale_inv, orig_hw, min_box, res: DetectResult):
         n, h, w, _ = frames.shape

@@ -93,6 +93,7 @@ class FaceEmbedder:
         self.rot_after_hit_frames = 8
         self.fast_no_face_imgsz = 512
         self.rot_phase = int(rot_phase) & 7   # stands in for `id(self) & 7` (face_embedder.py:2338)
+        self.keep_debug = False               # True: extract() also keeps last_chips / last_kinds (device->host copies)
         self.last_passes: List[dict] = []
 
     def aux_engine(self) -> Engine:
@@ -169,9 +170,8 @@ class FaceEmbedder:
         det = eng.detect(ps.frames, ps.size, ps.conf, rot=ps.rot, pad=ps.pad, fix_mode=ps.fix, fix_scale_inv=ps.scale_inv,
                          orig_hw=(H0, W0), min_box=mb, max_det=self.max_det)
         eng.sync()
-        raw = int(det.raw_count.cpu()[0])
-        acc = int(det.acc_count.cpu()[0])
-        self._last_unfiltered = int(det.acc_unfiltered.cpu()[0])
+        cnt = det.counts.cpu()              # one copy: raw / accumulated / unfiltered
+        raw, acc, self._last_unfiltered = int(cnt[0, 0]), int(cnt[1, 0]), int(cnt[2, 0])
         self.last_passes.append(dict(shape=tuple(ps.frames.shape[1:3]), size=ps.size, conf=float(ps.conf), rot=ps.rot,
                                      pad=ps.pad, n=raw, acc=acc))
         return det, raw, acc
@@ -274,24 +274,28 @@ class FaceEmbedder:
             self._rot_cycle = 0
 
         do_flip = (not fast) or self._prescan_escalate
-        return self._faces_from(frame, chosen, do_flip)
+        return self._faces_from(frame, chosen, do_flip, n_acc)
 
-    def _faces_from(self, frame: torch.Tensor, det, do_flip: bool):
+    def _faces_from(self, frame: torch.Tensor, det, do_flip: bool, n_acc: int):
+        """K4 -> ArcFace -> normalise for the accumulated detections of the chosen pass.  The cross-pass suppression keeps
+        between 1 and n_acc of them (the best one always survives), so the whole chain is enqueued for n_acc candidates
+        without asking the GPU how many K4 kept -- rows past the kept count are computed and ignored -- and the host waits ONCE."""
         eng = self.engine
         al = eng.align(frame, det, max_faces=self.max_det)
+        cand = min(int(n_acc), self.max_det)
+        emb, emb_flip = eng.embed(al.chips, cand, do_flip)
+        feat, _sim, _arg = eng.match(emb, emb_flip, None, cand)
         eng.sync()
         f = int(al.face_total.cpu()[0])
         if f == 0:
             return []
-        emb, emb_flip = eng.embed(al.chips, f, do_flip)
-        feat, _sim, _arg = eng.match(emb, emb_flip, None, f)
-        eng.sync()
         self.last_face_count = f
         boxes = al.face_box[:f].cpu().numpy()
         qual = al.quality[:f].cpu().numpy()
         feats = feat[:f].cpu().numpy()
-        self.last_chips = al.chips[:f].cpu().numpy()
-        self.last_kinds = al.face_kind[:f].cpu().numpy()
+        if self.keep_debug:                  # chips / alignment kinds of the last call (parity tooling only: 37 KB per face)
+            self.last_chips = al.chips[:f].cpu().numpy()
+            self.last_kinds = al.face_kind[:f].cpu().numpy()
         out = [dict(bbox=boxes[i].astype(np.int32).copy(), feat=feats[i].astype(np.float32).copy(), quality=float(qual[i]))
                for i in range(f)]
         self.last_order = sorted(range(f), key=lambda i: (out[i]["quality"], (out[i]["bbox"][2] - out[i]["bbox"][0]) *

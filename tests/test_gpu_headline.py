@@ -89,6 +89,33 @@ def test_r100_embeddings_small_call(engine_10g_r100):
     assert np.abs(fd_gpu - fd_ref).max() <= FD_TOL_SAME_CHIPS
 
 
+def test_small_embed_calls_replay_a_graph_with_identical_results(engine_10g_r100):
+    """1..8 faces go through a captured CUDA graph from the third call on (first eager, second captures): every call returns the
+    bits of the eager one, for changing inputs and face counts, and one launch replaces the ~110 of the eager pass."""
+    eng = engine_10g_r100
+    chips = _chips(12, 31)
+    eager = {}
+    for f, lo in ((1, 0), (2, 3), (5, 6)):
+        dev = eng.to_device(chips[lo:lo + f])
+        outs = []
+        for call in range(4):
+            eng.reset_launch_count()
+            emb, emb_flip = eng.embed(dev, f, True)
+            eng.sync()
+            outs.append((emb.cpu().numpy()[:f].copy(), emb_flip.cpu().numpy()[:f].copy(), eng.launch_count()))
+        for o in outs[1:]:
+            assert np.array_equal(o[0], outs[0][0]) and np.array_equal(o[1], outs[0][1])
+        assert outs[0][2] > 50 and outs[3][2] == 1, [o[2] for o in outs]
+        eager[f] = outs[0]
+    # the graph of f=2 with OTHER chips (inputs are staged, not baked in) and the big-batch path agree
+    other = eng.to_device(chips[8:10])
+    e2, f2 = eng.embed(other, 2, True)
+    big, bigf = eng.embed(eng.to_device(chips), 12, True)
+    eng.sync()
+    assert np.array_equal(e2.cpu().numpy()[:2], big.cpu().numpy()[8:10]) and np.array_equal(f2.cpu().numpy()[:2], bigf.cpu().numpy()[8:10])
+    assert not np.array_equal(e2.cpu().numpy()[:2], eager[2][0])
+
+
 def test_r100_full_run_444_images(engine_10g_r100):
     """A production-size ArcFace run (222 faces + flips = 444 images per graph run, the tile counts / pair / two-issuer variants
     bench.py uses): embeddings of sampled faces vs the fp32 oracle, the same faces through a 6-chip call (batch invariance),

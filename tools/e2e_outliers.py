@@ -7,6 +7,7 @@ import pcb_test_helpers as H
 from person_capture_b200 import synth
 from person_capture_b200.face_embedder import FaceEmbedder
 face = FaceEmbedder("cuda:0", "scrfd_10g_bnkps", conf=0.5, arcface_model="arcface_r50")
+face.keep_debug = True
 ora = H.oracle_embedder("scrfd_10g_bnkps", "arcface_r50", conf=0.5)
 for f in (face, ora):
     f.configure_rotation_strategy(adaptive=False); f.set_prescan_fast(True, mode="rr"); f._prescan_probe_imgsz = 512
