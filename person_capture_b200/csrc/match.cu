@@ -7,6 +7,7 @@
 // One arithmetic for every path: a (face row, bank row) cosine is always computed by ONE warp with `row_dot` below
 // (explicit fma chain per lane, xor-butterfly sum), so pcb_match, the full live refresh and the one-row incremental
 // refresh give bit-identical similarities -- max(old, dot(new row)) IS the full recomputation.
+#include <stdlib.h>
 #include <string.h>
 
 #include "pcb_common.cuh"
@@ -163,6 +164,115 @@ __global__ void __launch_bounds__(256) live_update_kernel(const float* __restric
   }
 }
 
+// ---- large banks (BASELINE config 4: 10 000 rows x thousands of faces): the per-face kernel above re-reads the whole bank from L2
+// for every face (82 GB for 4 096 faces).  Here a block owns 32 faces (4 per warp, kept in registers in row_dot's lane layout)
+// and streams the bank through shared memory once (16 rows per stage, double buffered with cp.async): 32x less L2 traffic,
+// 64 FMA per 4 LDS.128.  Every (face, bank row) cosine is computed with row_dot's fma chain and its butterfly tree (the four
+// partial sums of a warp are reduced by a transposing butterfly: same pairs, same order), so results are bit-identical to
+// match_kernel's, including the first-occurrence argmax.
+constexpr int kGemmFaces = 32, kGemmRows = 16;
+constexpr size_t kGemmSmem = 2 * kGemmRows * PCB_FEAT_DIM * sizeof(float);
+
+__global__ void __launch_bounds__(256) match_prep_kernel(const float* __restrict__ emb, const float* __restrict__ emb_flip,
+                                                         const uint8_t* __restrict__ use_flip, int f, float* __restrict__ feat_out,
+                                                         float* __restrict__ V) {
+  __shared__ __align__(16) float v[kD];
+  __shared__ float red[8];
+  const int face = blockIdx.x;
+  if (face >= f) return;
+  const bool fl = emb_flip != nullptr && (use_flip == nullptr || use_flip[face] != 0);
+  float x0 = emb[(size_t)face * kD + threadIdx.x];
+  float x1 = emb[(size_t)face * kD + 256 + threadIdx.x];
+  if (fl) {
+    x0 += emb_flip[(size_t)face * kD + threadIdx.x];
+    x1 += emb_flip[(size_t)face * kD + 256 + threadIdx.x];
+  }
+  normalise_twice(x0, x1, v, red, feat_out ? feat_out + (size_t)face * kD : nullptr);
+  V[(size_t)face * kD + threadIdx.x] = v[threadIdx.x];
+  V[(size_t)face * kD + 256 + threadIdx.x] = v[256 + threadIdx.x];
+}
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool pred) {
+  const int sz = pred ? 16 : 0;     // src-size 0: zero fill (rows past the bank's end)
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+
+__global__ void __launch_bounds__(256) match_gemm_kernel(const float* __restrict__ V, int f, const float* __restrict__ bank, int rows,
+                                                         float* __restrict__ sim_out, int* __restrict__ arg_out) {
+  extern __shared__ __align__(16) float stage_dyn[];           // [2][kGemmRows][kD] = 64 KB (opt-in dynamic shared memory)
+  float (*stage)[kGemmRows][kD] = (float (*)[kGemmRows][kD])stage_dyn;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int face0 = blockIdx.x * kGemmFaces + warp * 4;
+  // my 4 faces, 16 elements each: float4 index lane + 32 j (row_dot's layout)
+  float4 q[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int face = face0 + a < f ? face0 + a : f - 1;       // clamp: surplus lanes compute a duplicate that is not stored
+    const float4* v4 = (const float4*)(V + (size_t)face * kD);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) q[a][j] = v4[lane + 32 * j];
+  }
+  const int my = ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1);   // the face whose total this lane ends up holding
+  float best = -3.0e38f;
+  int barg = -1;
+  const int n_stages = (rows + kGemmRows - 1) / kGemmRows;
+  auto load_stage = [&](int st) {
+    const int r0 = st * kGemmRows;
+    const uint32_t dst0 = (uint32_t)__cvta_generic_to_shared(&stage[st & 1][0][0]);
+    for (int i = threadIdx.x; i < kGemmRows * (kD / 4); i += 256) {
+      const int rr = i / (kD / 4), c4 = i - rr * (kD / 4);
+      const bool in = r0 + rr < rows;
+      cp_async16(dst0 + (uint32_t)(i * 16), bank + (size_t)(in ? r0 + rr : 0) * kD + c4 * 4, in);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  load_stage(0);
+  for (int st = 0; st < n_stages; ++st) {
+    if (st + 1 < n_stages) {
+      load_stage(st + 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const int r0 = st * kGemmRows;
+    const int nr = rows - r0 < kGemmRows ? rows - r0 : kGemmRows;
+    for (int rr = 0; rr < nr; ++rr) {
+      const float4* b4 = (const float4*)&stage[st & 1][rr][0];
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 a = b4[lane + 32 * j];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          acc[k] = __fmaf_rn(a.x, q[k][j].x, acc[k]);
+          acc[k] = __fmaf_rn(a.y, q[k][j].y, acc[k]);
+          acc[k] = __fmaf_rn(a.z, q[k][j].z, acc[k]);
+          acc[k] = __fmaf_rn(a.w, q[k][j].w, acc[k]);
+        }
+      }
+      // transposing butterfly: xor 16 leaves two faces per lane, xor 8 one; then the plain butterfly (same pairs as row_dot)
+      const bool hi16 = (lane & 16) != 0, hi8 = (lane & 8) != 0;
+      const float s0 = hi16 ? acc[0] : acc[2], s1 = hi16 ? acc[1] : acc[3];      // what the partner keeps
+      float k0 = hi16 ? acc[2] : acc[0], k1 = hi16 ? acc[3] : acc[1];            // what I keep
+      k0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+      k1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+      const float s = hi8 ? k0 : k1;
+      float t = hi8 ? k1 : k0;
+      t += __shfl_xor_sync(0xffffffffu, s, 8);
+      t += __shfl_xor_sync(0xffffffffu, t, 4);
+      t += __shfl_xor_sync(0xffffffffu, t, 2);
+      t += __shfl_xor_sync(0xffffffffu, t, 1);
+      if (t > best) { best = t; barg = r0 + rr; }       // rows ascending: first occurrence wins
+    }
+    __syncthreads();      // the stage is free for the load after next
+  }
+  if ((lane & 7) == 0 && face0 + my < f) {
+    sim_out[face0 + my] = barg >= 0 ? best : -8.0f;
+    if (arg_out) arg_out[face0 + my] = barg;
+  }
+}
+
 // device bank with room for `rows` rows (geometric growth; the old buffer is released once the stream has drained)
 int bank_reserve(pcb_ctx* c, int rows) {
   if (rows <= c->bank_cap) return PCB_OK;
@@ -209,6 +319,27 @@ extern "C" int pcb_match(pcb_ctx* c, const float* emb_dev, const float* emb_flip
   PCB_ENTER(c);
   if (f < 0 || (f > 0 && (!emb_dev || !sim_dev))) return pcb_fail(c, PCB_ERR_ARG, "match: bad arguments");
   if (f == 0) return PCB_OK;
+  // large bank x many faces: the tiled kernel (bank streamed once per 32 faces); PCB_MATCH_GEMM_ROWS moves / disables the switch
+  const char* env = getenv("PCB_MATCH_GEMM_ROWS");
+  const int min_rows = env ? atoi(env) : 1024;
+  if (min_rows > 0 && c->bank_rows >= min_rows && f >= 2 * kGemmFaces) {
+    const size_t need = (size_t)f * kD * sizeof(float);
+    if (c->match_v_bytes < need) {
+      void* nb = pcb_dev_alloc(c, need, false);
+      if (!nb) return pcb_fail(c, PCB_ERR_CUDA, "match: scratch alloc failed");
+      if (c->match_v) { PCB_CUDA(c, cudaStreamSynchronize(c->stream)); pcb_dev_free(c, c->match_v); }
+      c->match_v = (float*)nb;
+      c->match_v_bytes = need;
+    }
+    match_prep_kernel<<<f, 256, 0, c->stream>>>(emb_dev, emb_flip_dev, use_flip_dev, f, feat_dev, c->match_v);
+    PCB_LAUNCH_CHECK(c, "match_prep_kernel");
+    static unsigned long long attr_devs = 0;
+    if (pcb_attr_needed(&attr_devs, c->device))
+      PCB_CUDA(c, cudaFuncSetAttribute(match_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
+    match_gemm_kernel<<<(f + kGemmFaces - 1) / kGemmFaces, 256, kGemmSmem, c->stream>>>(c->match_v, f, c->bank, c->bank_rows, sim_dev, argmax_dev);
+    PCB_LAUNCH_CHECK(c, "match_gemm_kernel");
+    return PCB_OK;
+  }
   match_kernel<<<f, 256, 0, c->stream>>>(emb_dev, emb_flip_dev, use_flip_dev, f, c->bank, c->bank_rows, feat_dev, sim_dev, argmax_dev);
   PCB_LAUNCH_CHECK(c, "match_kernel");
   return PCB_OK;

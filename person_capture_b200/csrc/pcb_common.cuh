@@ -116,6 +116,8 @@ struct pcb_ctx {
   std::map<std::vector<int>, std::pair<void*, void*>> lin_tabs;
   // live distance table of the pre-scan replay (match.cu): normalised face rows, their best cosine / argmax against
   // the live bank on the device, and the pinned host mirror pcb_live_refresh hands to the replay
+  float* match_v = nullptr;          // normalised face vectors of the tiled large-bank matcher
+  size_t match_v_bytes = 0;
   float* live_v = nullptr;
   float* live_sim = nullptr;
   int* live_arg = nullptr;

@@ -447,3 +447,36 @@ def test_product_library_has_no_validation_kernel(engine_25g_r50):
     with pytest.raises(L.PcbError):
         engine_25g_r50.set_conv_impl(1)
     engine_25g_r50.set_conv_impl(0)
+
+
+def test_match_large_bank_tiled_equals_per_face(engine_25g_r50, monkeypatch):
+    """K5 for large banks (config 4): the tiled kernel (bank streamed once per 32 faces) returns the bits of the per-face
+    kernel -- similarities, argmax (first occurrence, planted duplicates) and features -- and both agree with numpy."""
+    eng = engine_25g_r50
+    rng = np.random.default_rng(19)
+    f, B = 203, 3001
+    emb = rng.normal(size=(f, 512)).astype(np.float32)
+    embf = rng.normal(size=(f, 512)).astype(np.float32)
+    bank = rng.normal(size=(B, 512)).astype(np.float32)
+    bank /= np.linalg.norm(bank, axis=1, keepdims=True)
+    for k in (5, 77, 202):                                   # planted matches, one duplicated further down the bank
+        v = emb[k] + embf[k]
+        bank[100 + k] = v / np.linalg.norm(v)
+    bank[2900] = bank[105]
+    eng.set_bank(bank)
+    outs = {}
+    for mode in ("0", "1024"):
+        monkeypatch.setenv("PCB_MATCH_GEMM_ROWS", mode)
+        eng.reset_launch_count()
+        feat, sim, arg = eng.match(_dev(eng, emb), _dev(eng, embf), None, f)
+        eng.sync()
+        outs[mode] = (feat.cpu().numpy()[:f].copy(), sim.cpu().numpy()[:f].copy(), arg.cpu().numpy()[:f].copy(), eng.launch_count())
+    assert outs["0"][3] == 1 and outs["1024"][3] == 2          # per-face kernel vs prep + tiled kernel
+    for a, b in zip(outs["0"][:3], outs["1024"][:3]):
+        assert np.array_equal(a, b)
+    v = emb + embf
+    v = v / np.linalg.norm(v, axis=1, keepdims=True)
+    sims = v @ bank.T
+    assert np.allclose(outs["1024"][1], sims.max(1), atol=5e-6)
+    assert np.array_equal(outs["1024"][2], sims.argmax(1)) and int(outs["1024"][2][5]) == 105
+    eng.set_bank(None)
