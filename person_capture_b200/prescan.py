@@ -996,7 +996,7 @@ class _LiveDistances:
                 if self.sim_dev is None or self.sim_dev.shape[0] < n2:
                     self.sim_dev = eng.empty((n2,), torch.float32)
                     self.arg_dev = eng.empty((n2,), torch.int32)
-                    self.sim_host = torch.empty((n2,), dtype=torch.float32).pin_memory()
+                    self.sim_host = _pinned("live_sim", (n2,), torch.float32)
                 eng.set_bank(bank.array())
                 eng._check(eng.lib.pcb_match(eng.ctx, self.both.data_ptr(), None, None, n2, None, self.sim_dev.data_ptr(),
                                              self.arg_dev.data_ptr()), "pcb_match")
@@ -1449,6 +1449,22 @@ def prescan_batched(clip, fps: int, face: FaceEmbedder, ref_feat, cfg, batch: in
     return spans, (out_bank if out_bank is not None else ref_feat)
 
 
+_PINNED: Dict[tuple, torch.Tensor] = {}
+
+
+def _pinned(tag: str, shape, dtype) -> torch.Tensor:
+    """Reusable pinned host buffer (cudaHostAlloc costs ~1 ms per call; the gather runs every pre-scan on every rank)."""
+    n = 1
+    for d in shape:
+        n *= int(d)
+    key = (tag, dtype)
+    buf = _PINNED.get(key)
+    if buf is None or buf.numel() < n:
+        buf = torch.empty((max(n, 1),), dtype=dtype).pin_memory()
+        _PINNED[key] = buf
+    return buf[:n].view(*shape)
+
+
 def _gather_shards(eng, enc_local, table, plain_h, flip_h, world, group):
     """All-gather of everything the replicated replay needs from the other ranks, as TWO tensor collectives: a 2-word
     header (face rows, samples) and one packed byte buffer per rank
@@ -1492,7 +1508,9 @@ def _gather_shards(eng, enc_local, table, plain_h, flip_h, world, group):
     fview = lambda buf, off, n: buf[off:off + n * L.FEAT_DIM * 4].view(torch.float32).view(n, L.FEAT_DIM)
     if backend_cuda:
         with torch.cuda.stream(eng.stream):
-            send[:o_p].copy_(torch.from_numpy(small).pin_memory(), non_blocking=True)
+            stage = _pinned("gather_small_out", (o_p,), torch.uint8)
+            stage.copy_(torch.from_numpy(small))
+            send[:o_p].copy_(stage, non_blocking=True)
             if count:
                 fview(send, o_p, count).copy_(table.plain[:count])
                 fview(send, o_f, count).copy_(table.flip[:count])
@@ -1510,17 +1528,18 @@ def _gather_shards(eng, enc_local, table, plain_h, flip_h, world, group):
     flip_all = torch.cat([fview(recv[r], o_f, counts[r]) for r in range(world)], 0) if base else torch.zeros((1, L.FEAT_DIM), device=dev)
     if backend_cuda:
         # host copies (the replay hands bank offers a host vector): pinned, one copy per array
-        small_h = torch.empty((world, o_p), dtype=torch.uint8).pin_memory()
+        small_h = _pinned("gather_small_in", (world, o_p), torch.uint8)
         small_h.copy_(recv[:, :o_p], non_blocking=True)
-        ph = torch.empty((max(base, 1), L.FEAT_DIM), dtype=torch.float32).pin_memory()
-        fh = torch.empty((max(base, 1), L.FEAT_DIM), dtype=torch.float32).pin_memory()
+        ph = _pinned("gather_plain", (max(base, 1), L.FEAT_DIM), torch.float32)
+        fh = _pinned("gather_flip", (max(base, 1), L.FEAT_DIM), torch.float32)
         if base:
             ph[:base].copy_(plain_all, non_blocking=True)
             fh[:base].copy_(flip_all, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         eng.stream.wait_stream(torch.cuda.current_stream())
         plain_all, flip_all = plain_all.contiguous(), flip_all.contiguous()
-        small_np, plain_host, flip_host = small_h.numpy(), ph[:base].numpy(), fh[:base].numpy()
+        # (copies: the pinned buffers are reused by the next pre-scan, the replay keeps these arrays)
+        small_np, plain_host, flip_host = small_h.numpy().copy(), ph[:base].numpy().copy(), fh[:base].numpy().copy()
     else:
         small_np = recv[:, :o_p].numpy()
         plain_host, flip_host = plain_all[:base].numpy().copy(), flip_all[:base].numpy().copy()
