@@ -253,7 +253,7 @@ def main():
         faces_seen["passes"] = stats.get("arcface_passes", 0)  # ArcFace image passes (e(x), plus e(flip x) where the span logic needs it)
         faces_seen["spans"] = [list(map(int, sp)) for sp in spans]
         faces_seen["phase_ms"] = stats.get("phase_ms")
-        faces_seen["bank"] = {k: stats.get(k) for k in ("bank_rows", "bank_versions", "distance_refreshes")}
+        faces_seen["bank"] = {k: stats.get(k) for k in ("bank_rows", "bank_versions", "distance_refreshes", "flip_on_demand", "early_flip_rows")}
         return spans
 
     def timed(clip, steps, profile=False):

@@ -1214,7 +1214,12 @@ def replay(records: Dict[int, SampleRecord], table, feats_host, idxs: Sequence[i
 
     lookahead = 96
 
+    flip_calls = [0, 0.0]
+
     def on_flip(_user, s_i):
+        import time as _t
+        t0 = _t.perf_counter()
+        flip_calls[0] += 1
         try:
             want = []
             for m in meta[s_i:s_i + lookahead]:
@@ -1226,6 +1231,7 @@ def replay(records: Dict[int, SampleRecord], table, feats_host, idxs: Sequence[i
                     arm_live()
                 elif hasattr(distances, "invalidate"):
                     distances.invalidate()
+            flip_calls[1] += _t.perf_counter() - t0
             return 0
         except BaseException as exc:      # noqa: BLE001
             failure.append(exc)
@@ -1278,6 +1284,7 @@ def replay(records: Dict[int, SampleRecord], table, feats_host, idxs: Sequence[i
     trk.spans = [(int(a), int(b)) for a, b in spans[:n_spans.value]]
     trk.active = False          # pcb_replay already closed the open span (gui_app.py:1648-1655)
     trk.distance_refreshes = int(n_refresh.value)
+    trk.flip_on_demand = (flip_calls[0], round(1000.0 * flip_calls[1], 2))      # (calls, ms inside them)
     if log is not None:
         for i, idx in enumerate(idxs):
             log.append(dict(idx=idx, skip=bool(skip[i]), best=float(best[i]), active_before=bool(act[i]), nfaces=int(nf[i])))
@@ -1432,6 +1439,7 @@ def prescan_batched(clip, fps: int, face: FaceEmbedder, ref_feat, cfg, batch: in
         if stats is not None:
             stats["bank_rows"], stats["bank_versions"] = len(bank), bank.version
             stats["distance_refreshes"] = getattr(trk, "distance_refreshes", None)
+            stats["flip_on_demand"] = getattr(trk, "flip_on_demand", None)
         _count_passes(stats, local_table)      # this rank's faces / ArcFace image passes
         spans = trk.finish()
         wmax = int(getattr(cfg, "prescan_max_width", 0))
@@ -1538,8 +1546,9 @@ def _gather_shards(eng, enc_local, table, plain_h, flip_h, world, group):
         torch.cuda.current_stream().synchronize()
         eng.stream.wait_stream(torch.cuda.current_stream())
         plain_all, flip_all = plain_all.contiguous(), flip_all.contiguous()
-        # (copies: the pinned buffers are reused by the next pre-scan, the replay keeps these arrays)
-        small_np, plain_host, flip_host = small_h.numpy().copy(), ph[:base].numpy().copy(), fh[:base].numpy().copy()
+        # views of the reusable pinned buffers: valid until the next gather, i.e. for the rest of this pre-scan (the replay
+        # reads them, on-demand flips write flip_host in place)
+        small_np, plain_host, flip_host = small_h.numpy(), ph[:base].numpy(), fh[:base].numpy()
     else:
         small_np = recv[:, :o_p].numpy()
         plain_host, flip_host = plain_all[:base].numpy().copy(), flip_all[:base].numpy().copy()
