@@ -1385,8 +1385,10 @@ def prescan_batched(clip, fps: int, face: FaceEmbedder, ref_feat, cfg, batch: in
     if dist.is_available() and dist.is_initialized() and not single_rank:     # single_rank: this process scans the whole clip alone
         world, rank = dist.get_world_size(dist_group), dist.get_rank(dist_group)
     if int(getattr(cfg, "prescan_probe_imgsz", 512)) > int(face.fast_no_face_imgsz):
-        raise RuntimeError("prescan_batched requires prescan_probe_imgsz <= fast_no_face_imgsz (the upright size would "
-                           "depend on the no-face streak, SURVEY.md H1); use prescan_sequential")
+        # the upright detector size would then depend on the no-face streak (face_embedder.py:2193-2194), i.e. on the
+        # sequential state: the superset is not state independent for such a configuration.  Same results,
+        # one extract per sample; with several ranks every rank runs it (no collective is needed).
+        return prescan_sequential(clip, fps, face, ref_feat, cfg, log=log)
     eng = face.engine
     import time as _time
     tmark = [("start", _time.perf_counter())]

@@ -86,7 +86,7 @@ def test_lmeds_and_warp(hs):
         M, inl = cv2.estimateAffinePartial2D(src, DST, method=cv2.LMEDS)
         Me = np.zeros(6)
         assert hs.hs_lmeds(P(src), P(DST), 5, P(Me)) == 1 and M is not None
-        assert np.abs(M.ravel() - Me).max() < 1e-9
+        assert np.abs(M.ravel() - Me).max() < 2e-12          # measured max 2.3e-13 over 400 cases: cv2's LM ends on the LS optimum
         M2, mask = E.estimate_affine_partial_lmeds(src, DST)
         bad_mask += int(not np.array_equal(mask, inl.ravel().astype(bool)))
         assert np.abs(M - M2).max() < 1e-9

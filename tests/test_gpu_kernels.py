@@ -302,7 +302,9 @@ def test_align_chips_bit_exact(engine_25g_r50):
             assert abs(float(al.quality[gi].cpu()) - q) <= 1e-9 * max(1.0, q)
             gi += 1
     assert gi == total
-    assert exact >= int(0.95 * total)
+    # the closed-form least-squares fit and cv2's Levenberg-Marquardt refinement agree to ~2e-13 (tests/test_cpu_arith.py), so a
+    # 1/32-px sample position flips for about one chip in 1e5: every chip of this test is expected bit-exact, one may differ
+    assert exact >= total - 1, (exact, total)
 
 
 # ---------------------------------------------------------------- K5
