@@ -333,6 +333,12 @@ def main():
         pass
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (measured)" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
+    traffic = {}
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")) as fh:
+            traffic = json.load(fh)
+    except Exception:
+        pass
     conv_ms, conv_flops, conv_n = prof
     achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
     g_s = graphs.build_graph("scrfd_10g_bnkps")
@@ -355,13 +361,16 @@ def main():
         "wall_ms_per_step": 1000.0 * wall / args.steps,
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(h2d),
-                "d2h_bytes_per_step": int(faces_seen["passes"] * 2048 + faces_seen["n"] * 64 + args.frames_per_step * 64)},
+                # device->host per step: normalised features of every face (plain + the flip features that were computed), per-face
+                # box / quality / counts, per-batch detection counts, and the live-distance read-backs of the replay
+                "d2h_bytes_per_step": int(faces_seen["passes"] * 2048 + faces_seen["n"] * (16 + 8 + 4) + (args.frames_per_step // args.batch + 1) * 3 * 4 * args.batch
+                                          + (faces_seen.get("bank") or {}).get("distance_refreshes", 0) * faces_seen["n"] * 8)},
         "roofline": {"kernel": "conv_tc2_kernel", "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": achieved / peak_tf if peak_tf else None,
-                     # DRAM bytes per launch of the dominant layer shape (iResNet-100 stage 3, 14x14 256->256, 444 images) from the
-                     # round's ncu --set full capture (profiles/r01_ncu_conv_tc2_stage3_keymetrics.txt): 59.5 MB read + 11.7 MB
-                     # written for 59.4 MB of algorithmic input+weight bytes (the output stays in the 126 MB L2)
-                     "traffic": 71.2e6, "traffic_layer": "14x14 256->256 conv1, 444 images, 102.6 GFLOP/launch",
+                     # DRAM bytes per launch of the dominant layer shape, read from the committed ncu --set full capture
+                     # (dram__bytes_read.sum + dram__bytes_write.sum; profiles/r02_ncu_traffic.json names the command)
+                     "traffic": traffic.get("traffic_bytes_per_launch"), "traffic_layer": traffic.get("layer"),
+                     "traffic_source": "profiles/r02_ncu_traffic.json" if traffic else None,
                      "peak_source": peak_src,
                      "conv_launches": conv_n, "conv_ms_per_step": conv_ms / args.steps,
                      "conv_share_of_step": (conv_ms / ms) if ms > 0 else None},

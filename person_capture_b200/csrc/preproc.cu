@@ -152,8 +152,15 @@ __global__ void __launch_bounds__(256) letterbox_kernel(const LetterboxParams p)
 // chips [f][112][112][3] BGR -> patch tensor [f(*2)][114][114][32].  with_flip: 0 = chips only, 1 = chips then (images
 // f..2f-1) their mirror images, 2 = mirror images only (flip-TTA computed lazily for faces that turn out to need it).
 __global__ void __launch_bounds__(256) chip_patch_kernel(const uint8_t* __restrict__ chips, __half* __restrict__ out, int f, int with_flip) {
+  // rgb.astype(float32) / 127.5 - 1.0 (float32 ops), then fp16 storage: a function of the byte alone, so it is tabulated once per
+  // block with the exact operations (the IEEE division was ~15 instructions x 27 taps per pixel; ncu: 213 us per 504 chips at 26 %
+  // of HBM peak, instruction bound)
+  __shared__ __half lut[256];
+  lut[threadIdx.x] = __float2half_rn(__fsub_rn(__fdiv_rn((float)threadIdx.x, 127.5f), 1.0f));
+  __syncthreads();
   const int total_imgs = with_flip == 1 ? 2 * f : f;
   const long long total = (long long)total_imgs * PCB_CHIP * PCB_CHIP;
+  const __half zero = __float2half_rn(0.f);
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     const int x = (int)(idx % PCB_CHIP);
     const int y = (int)((idx / PCB_CHIP) % PCB_CHIP);
@@ -170,14 +177,10 @@ __global__ void __launch_bounds__(256) chip_patch_kernel(const uint8_t* __restri
         const int sx = flip ? (PCB_CHIP - 1 - xx) : xx;
         const uint8_t* px = chip + ((size_t)(in ? yy : 0) * PCB_CHIP + (in ? sx : 0)) * 3;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          // rgb.astype(float32) / 127.5 - 1.0 (float32 ops), then fp16 storage
-          const float fv = in ? __fsub_rn(__fdiv_rn((float)px[2 - c], 127.5f), 1.0f) : 0.f;
-          vals[(ky * 3 + kx) * 3 + c] = __float2half_rn(fv);
-        }
+        for (int c = 0; c < 3; ++c) vals[(ky * 3 + kx) * 3 + c] = in ? lut[px[2 - c]] : zero;      // BGR -> RGB
       }
 #pragma unroll
-    for (int j = 27; j < 32; ++j) vals[j] = __float2half_rn(0.f);
+    for (int j = 27; j < 32; ++j) vals[j] = zero;
     __half* o = out + pcb_prow(img, y, x, PCB_CHIP, PCB_CHIP) * 32;
 #pragma unroll
     for (int j = 0; j < 4; ++j) ((uint4*)o)[j] = ((const uint4*)vals)[j];
