@@ -83,12 +83,28 @@ struct LetterboxParams {
 constexpr int kLbTile = 16;                 // patch pixels per block edge
 constexpr int kLbDet = 2 * kLbTile + 1;     // det pixels needed per edge (33)
 
+// kPlain: no rotation, no replicate border, bilinear tables (the upright pass of every frame): source pixels are addressed directly
+template <bool kPlain>
 __global__ void __launch_bounds__(256) letterbox_kernel(const LetterboxParams p) {
   __shared__ uint8_t tile[kLbDet][kLbDet][4];   // [.][.][3] = 1 when the det pixel is inside [0,S)
   const int img = blockIdx.z;
   const int oy0 = blockIdx.y * kLbTile, ox0 = blockIdx.x * kLbTile;
   const int dy0 = 2 * oy0 - 1, dx0 = 2 * ox0 - 1;
+  const int half = p.S / 2;
+  if ((dy0 >= p.new_h || dx0 >= p.new_w) && dy0 >= 0 && dx0 >= 0 && dy0 + kLbDet <= p.S && dx0 + kLbDet <= p.S && !p.det_img) {
+    // the block lies in the zero padding of the letterbox (44 % of a 16:9 frame's square): every tap is the normalised zero pixel
+    const int ly = threadIdx.x / kLbTile, lx = threadIdx.x % kLbTile;
+    const __half z = __float2half_rn((0.f - 127.5f) * (1.0f / 128.0f)), o0 = __float2half_rn(0.f);
+    __align__(16) __half vals[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) vals[j] = j < 27 ? z : o0;
+    __half* o = p.out + pcb_prow(img, oy0 + ly, ox0 + lx, half, half) * 32;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) ((uint4*)o)[j] = ((const uint4*)vals)[j];
+    return;
+  }
   PcbView v = pcb_make_view(p.frames + (size_t)img * p.h * p.w * 3, p.h, p.w, p.rot, p.pad);
+  const uint8_t* frame = p.frames + (size_t)img * p.h * p.w * 3;
   for (int i = threadIdx.x; i < kLbDet * kLbDet; i += blockDim.x) {
     const int ty = i / kLbDet, tx = i - ty * kLbDet;
     const int y = dy0 + ty, x = dx0 + tx;
@@ -97,14 +113,23 @@ __global__ void __launch_bounds__(256) letterbox_kernel(const LetterboxParams p)
     if (y >= 0 && y < p.S && x >= 0 && x < p.S) {
       inside = 1;
       if (y < p.new_h && x < p.new_w) {
-        if (p.mode == PCB_RS_LINEAR) {
+        if (kPlain || p.mode == PCB_RS_LINEAR) {
           const LinTab cx = p.xtab[x], cy = p.ytab[y];
           const int x1 = pcb_iminf(cx.s + 1, v.vw - 1);
           const int y0 = pcb_clampi(cy.s, 0, v.vh - 1), y1 = pcb_clampi(cy.s + 1, 0, v.vh - 1);
-          const uint8_t* p00 = pcb_view_px(v, y0, cx.s);
-          const uint8_t* p01 = pcb_view_px(v, y0, x1);
-          const uint8_t* p10 = pcb_view_px(v, y1, cx.s);
-          const uint8_t* p11 = pcb_view_px(v, y1, x1);
+          const uint8_t *p00, *p01, *p10, *p11;
+          if (kPlain) {
+            const int xs = pcb_clampi(cx.s, 0, p.w - 1);          // what pcb_view_px does for an unrotated, unpadded view
+            const uint8_t* r0 = frame + (size_t)y0 * p.w * 3;
+            const uint8_t* r1 = frame + (size_t)y1 * p.w * 3;
+            const int xe = pcb_clampi(x1, 0, p.w - 1);
+            p00 = r0 + xs * 3; p01 = r0 + xe * 3; p10 = r1 + xs * 3; p11 = r1 + xe * 3;
+          } else {
+            p00 = pcb_view_px(v, y0, cx.s);
+            p01 = pcb_view_px(v, y0, x1);
+            p10 = pcb_view_px(v, y1, cx.s);
+            p11 = pcb_view_px(v, y1, x1);
+          }
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
             const int h0 = p00[c] * cx.a0 + p01[c] * cx.a1;
@@ -125,7 +150,6 @@ __global__ void __launch_bounds__(256) letterbox_kernel(const LetterboxParams p)
   __syncthreads();
   const int ly = threadIdx.x / kLbTile, lx = threadIdx.x % kLbTile;
   const int oy = oy0 + ly, ox = ox0 + lx;
-  const int half = p.S / 2;
   if (oy >= half || ox >= half) return;
   __align__(16) __half vals[32];
 #pragma unroll
@@ -275,7 +299,8 @@ int pcb_letterbox_impl(pcb_ctx* c, const uint8_t* frames, int n, int h, int w, i
   p.det_img = det_img;
   const int half = S / 2;
   dim3 grid((half + kLbTile - 1) / kLbTile, (half + kLbTile - 1) / kLbTile, n);
-  letterbox_kernel<<<grid, 256, 0, c->stream>>>(p);
+  if (p.mode == PCB_RS_LINEAR && rot == 0 && pad == 0) letterbox_kernel<true><<<grid, 256, 0, c->stream>>>(p);
+  else letterbox_kernel<false><<<grid, 256, 0, c->stream>>>(p);
   PCB_LAUNCH_CHECK(c, "letterbox_kernel");
   return PCB_OK;
 }

@@ -355,3 +355,32 @@ def test_replay_callback_failure_is_raised():
     with pytest.raises(RuntimeError, match="matcher lost its device"):
         PS.replay(records, None, (P, Fl), PS.sample_indices(n, 1), 24, n, FakeFace(sc), ref_feat, cfg, distances=Exploding(P, Fl))
     assert Exploding.calls == 3
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+@pytest.mark.parametrize("carry", [False, True])
+def test_vectorised_flip_prediction_equals_the_loop(seed, carry):
+    """The flat-record form of the flip prediction (used inside the timed step) selects exactly the rows of the per-sample loop."""
+    rng = np.random.default_rng(seed)
+    cfg = PrescanParams()
+    fps, n = 24, 160
+    records, rows_next = {}, 0
+    for i in range(n):
+        rec = PS.SampleRecord(i)
+        k = int(rng.integers(0, 4))
+        if k:
+            rec.up = PS._Variant(np.zeros((k, 4), np.int32), np.ones(k), np.arange(rows_next, rows_next + k))
+            rows_next += k
+        else:
+            for deg in (90, 270):
+                if rng.random() < 0.3:
+                    rec.hits[deg] = rec.heavy_raw[deg] = 1
+                    rec.heavy[deg] = PS._Variant(np.zeros((1, 4), np.int32), np.ones(1), np.arange(rows_next, rows_next + 1))
+                    rows_next += 1
+        records[i] = rec
+    fd = rng.uniform(0.2, 1.2, rows_next)
+    idxs = list(range(n))
+    meta, _, _ = PS.encode_records(records, idxs, rows_next)
+    want = np.sort(PS._predict_flip_rows(records, idxs, fd, cfg, fps, carry_in=carry))
+    got = np.sort(PS._predict_flip_rows_meta(meta, fd, cfg, fps, carry_in=carry))
+    assert np.array_equal(got, want) and len(want) > 0
