@@ -11,7 +11,10 @@ Follows person_capture/face_embedder.py:
   state + knobs                            :473-500, :1224-1272
 The networks are the folded torch-CPU executors of oracle/models.py (stand-in for ONNX
 Runtime CPU, which is not installed); every image operation is the real cv2 call the
-reference makes.  parity unpinned (the reference has no tests).
+reference makes.  Pinned against the reference itself: tests/golden/reference_golden.npz holds what the
+unmodified `FaceEmbedder` (sessions substituted, tests/golden/ref_harness.py) returned for 18 alignment unit cases and a
+53-call extract script (228 recorded SCRFD passes); tests/test_cpu_reference_golden.py replays the detector and demands the same
+passes (input image CRC, size, threshold, order), chips, boxes, qualities, features and streak / rotation state from this module.
 
 `id(self) & 7` in the adaptive-rotation period test (face_embedder.py:2338) is process
 dependent in the reference; the oracle exposes it as `rot_phase` (default 0).

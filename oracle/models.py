@@ -8,7 +8,7 @@ ONNX files themselves are downloaded at run time (face_embedder.py:55-83) and ar
 here, so this file *defines* the architectures from the upstream InsightFace configs and
 both sides (oracle and CUDA path) load the same exported weight file.
 
-parity unpinned: the reference ships no tests or golden vectors for these graphs
+parity unpinned for the graphs: the reference ships no tests or golden vectors for them
 (SURVEY.md F2); torch-CPU fp32 stands in for ONNX Runtime CPU (not installed, F4) and is
 cross-checked against cv2.dnn running the exported ONNX file (tests/test_oracle_onnx.py).
 

@@ -11,7 +11,10 @@ Follows person_capture/gui_app.py:
 UI command handling, decode/seek and Qt status are out of scope: frames come from a
 `get_frame(i)` callable.  The wall-clock refine budget (gui_app.py:1692-1696) makes the
 reference timing dependent; the oracle runs with the budget disabled.
-parity unpinned (no reference tests).
+Pinned against the reference itself: tests/golden/reference_golden.npz holds the outputs of the unmodified
+`Processor._fd_min / _stream_ref_bank_update / _prescan / _prescan_cache_*` run in the build container on seeded scripts
+(tests/golden/make_reference_golden.py); tests/test_cpu_reference_golden.py demands identical actions, banks, spans, per-call
+knob state and cache key / file from this module.
 """
 from __future__ import annotations
 

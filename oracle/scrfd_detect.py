@@ -5,7 +5,8 @@ Third-party dependency, not vendored in /root/reference: `insightface>=0.7.3`
 (person_capture/face_embedder.py:215-262) and calls `scrfd.detect(img, input_size=(S, S))`
 with `scrfd.det_thresh` set per call (face_embedder.py:2176-2187).  The algorithm below is
 restated from the published upstream source as summarised in SURVEY.md App. A.1; the
-reference has no test or golden vector for it -> parity unpinned.
+reference has no test or golden vector for it and the package is absent here -> parity unpinned for THIS file
+(the code around it is pinned: oracle/face_embedder.py).
 
 Uses real cv2 calls (cv2.resize, cv2.dnn.blobFromImage) so that the fixed-point arithmetic
 is OpenCV's own (cv2 4.13 here; the reference pins 4.9.0.80).

@@ -1342,11 +1342,15 @@ int pcb_conv_tc2(pcb_ctx* c, const ConvArgs& a) {
   }
   // two MMA issuers where the K step can be split by accumulator (PCB_CONV_ISS=1 forces one)
   static const int iss_mode = env_int("PCB_CONV_ISS", 2);
+  // MT = 1 layers split the N extent between the two issuers, pair layers excepted: there each half-N instruction re-reads the
+  // whole A operand of both CTAs from shared memory for 64 tensor cycles of work, and one issuer keeps the pipe fed
+  // (same-box A/B, gpurun r2r: 14x14 / 7x7 / 28x28->256 layers +3 % without the split, the stride-2 layers -3 %)
+  static const int split_pair = env_int("PCB_CONV_SPLIT_PAIR", 0);
   p.n_iss = 1;
   p.split_n = 0;
   if (iss_mode >= 2) {
     if (p.mt == 2) p.n_iss = 2;
-    else if (w.n_tile % 32 == 0) { p.n_iss = 2; p.split_n = 1; }
+    else if (w.n_tile % 32 == 0 && (!p.pair || split_pair)) { p.n_iss = 2; p.split_n = 1; }
   }
   // epilogue split: narrow layers with two sub-tiles give each warp of a lane quarter its own sub-tile (one 64-column chunk
   // per tile, and no idle warps when n_tile <= 32); everything else splits the columns

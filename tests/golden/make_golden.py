@@ -1,6 +1,6 @@
 """Generates tests/golden/oracle_golden.npz: outputs of the CPU oracle (torch-CPU fp32 + real cv2 4.13) on
-fixed seeded inputs.  The reference ships no golden vectors and cannot be imported here
-(ONNX Runtime / insightface absent), so these pin the *oracle* across machines and over time; the cv2-level
+fixed seeded inputs.  These pin the *oracle including its networks* across machines and over time (the reference's own
+non-network code is pinned by make_reference_golden.py / reference_golden.npz); the cv2-level
 known answers (LMedS subset sequence, fixed-point resize/warp) are pinned against cv2 itself in
 tests/test_cpu_arith.py.   usage: python tests/golden/make_golden.py
 """
