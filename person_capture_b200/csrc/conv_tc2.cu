@@ -512,6 +512,16 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Programmatic dependent launch: everything above touches only this kernel's own state and constants (barriers, TMEM,
+  // per-channel vectors), so it may run while the previous kernel of the stream drains its last tiles.  From here on the
+  // warps read activations / residuals and write outputs: they wait for the previous grid to complete (and its writes to
+  // be visible).  The weight producer (warp 2) does not wait -- weights are constants -- so the B ring is already full when
+  // the first activation tile lands.  The trigger for OUR dependent goes out right away: this grid is fully resident
+  // (persistent, <= 1 CTA per SM), so the next kernel's CTAs can only take SMs our CTAs have left.  Both instructions are
+  // no-ops when the launch carries no programmatic attribute (PCB_CONV_PDL=0).
+  if (warp != 2) asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
   // (setmaxnreg sits at the top of each role branch: ptxas bounds the registers of the code a setmaxnreg dominates)
   if (warp < kEpiWarp0) {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");     // one instruction for the whole warpgroup (warps 0-3)
@@ -1434,29 +1444,36 @@ int pcb_conv_tc2(pcb_ctx* c, const ConvArgs& a) {
     if (mode != 0 && (p.residual || p.out2)) return pcb_fail(c, PCB_ERR_ARG, "conv_tc2: fp32 outputs take no residual / second output");
     const int key = mode == 0 ? (p.act * 4 + (p.residual ? 2 : 0) + (p.out2 ? 1 : 0)) : (100 + mode * 4 + p.act);
     cudaError_t le = cudaErrorInvalidValue;
+    // programmatic dependent launch (see the kernel's prologue); off while the per-launch profile or the stall counters are on
+    static const int pdl_mode = env_int("PCB_CONV_PDL", 1);
+    const bool pdl = pdl_mode != 0 && !c->profile && !p.dbg;
 #define PCB_TC2_LAUNCH(ACT, RES, OUT2, MODE, VAR)                                                                       \
   {                                                                                                                    \
     static unsigned long long attr_devs = 0; /* the opt-in is per device */                                            \
     if (pcb_attr_needed(&attr_devs, c->device))                                                                        \
       cudaFuncSetAttribute(conv_tc2_kernel<ACT, RES, OUT2, MODE, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
+    cudaLaunchConfig_t cfg = {};                                                                                       \
+    cfg.gridDim = dim3(grid);                                                                                          \
+    cfg.blockDim = dim3(kThreads);                                                                                     \
+    cfg.dynamicSmemBytes = smem;                                                                                       \
+    cfg.stream = c->stream;                                                                                            \
+    cudaLaunchAttribute at[2];                                                                                         \
+    int n_at = 0;                                                                                                      \
     if (VAR == kVarPair) {                                                                                             \
-      cudaLaunchConfig_t cfg = {};                                                                                     \
-      cfg.gridDim = dim3(grid);                                                                                        \
-      cfg.blockDim = dim3(kThreads);                                                                                   \
-      cfg.dynamicSmemBytes = smem;                                                                                     \
-      cfg.stream = c->stream;                                                                                          \
-      cudaLaunchAttribute at[1];                                                                                       \
-      at[0].id = cudaLaunchAttributeClusterDimension;                                                                  \
-      at[0].val.clusterDim.x = 2;                                                                                      \
-      at[0].val.clusterDim.y = 1;                                                                                      \
-      at[0].val.clusterDim.z = 1;                                                                                      \
-      cfg.attrs = at;                                                                                                  \
-      cfg.numAttrs = 1;                                                                                                \
-      le = cudaLaunchKernelEx(&cfg, conv_tc2_kernel<ACT, RES, OUT2, MODE, VAR>, tmA, tmA2, tmB, tmO, tmO2, p);                    \
-    } else {                                                                                                           \
-      conv_tc2_kernel<ACT, RES, OUT2, MODE, VAR><<<grid, kThreads, smem, c->stream>>>(tmA, tmA2, tmB, tmO, tmO2, p);              \
-      le = cudaSuccess;                                                                                                \
+      at[n_at].id = cudaLaunchAttributeClusterDimension;                                                               \
+      at[n_at].val.clusterDim.x = 2;                                                                                   \
+      at[n_at].val.clusterDim.y = 1;                                                                                   \
+      at[n_at].val.clusterDim.z = 1;                                                                                   \
+      ++n_at;                                                                                                          \
     }                                                                                                                  \
+    if (pdl) {                                                                                                         \
+      at[n_at].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                                \
+      at[n_at].val.programmaticStreamSerializationAllowed = 1;                                                         \
+      ++n_at;                                                                                                          \
+    }                                                                                                                  \
+    cfg.attrs = at;                                                                                                    \
+    cfg.numAttrs = n_at;                                                                                               \
+    le = cudaLaunchKernelEx(&cfg, conv_tc2_kernel<ACT, RES, OUT2, MODE, VAR>, tmA, tmA2, tmB, tmO, tmO2, p);            \
   }
 #define PCB_TC2_CASE(KEY, ACT, RES, OUT2, MODE)                                                                         \
   case KEY:                                                                                                            \

@@ -104,6 +104,52 @@ __global__ void __launch_bounds__(256) match_kernel(const float* __restrict__ em
   bank_scan(v, bank, rows, wmax, warg, sim_out + face, arg_out ? arg_out + face : nullptr);
 }
 
+// Few faces x large bank (the lock-face ROI site against a 10 000-row bank: one face per frame): match_kernel would scan the
+// whole bank with ONE block.  Here block (face, seg) scans rows [seg * seg_rows, ...) with the same row_dot arithmetic and
+// leaves its (max, first row) in part[face][seg]; match_split_reduce_kernel picks the maximum with the smallest row index,
+// which is match_kernel's rule -- results are bit-identical.
+__global__ void __launch_bounds__(256) match_split_kernel(const float* __restrict__ emb, const float* __restrict__ emb_flip,
+                                                          const uint8_t* __restrict__ use_flip, int f, const float* __restrict__ bank,
+                                                          int rows, int seg_rows, float* __restrict__ feat_out,
+                                                          float* __restrict__ part_sim, int* __restrict__ part_arg) {
+  __shared__ __align__(16) float v[kD];
+  __shared__ float red[8];
+  __shared__ float wmax[8];
+  __shared__ int warg[8];
+  const int face = blockIdx.x, seg = blockIdx.y;
+  const bool fl = emb_flip != nullptr && (use_flip == nullptr || use_flip[face] != 0);
+  float x0 = emb[(size_t)face * kD + threadIdx.x];
+  float x1 = emb[(size_t)face * kD + 256 + threadIdx.x];
+  if (fl) {
+    x0 += emb_flip[(size_t)face * kD + threadIdx.x];
+    x1 += emb_flip[(size_t)face * kD + 256 + threadIdx.x];
+  }
+  normalise_twice(x0, x1, v, red, (feat_out && seg == 0) ? feat_out + (size_t)face * kD : nullptr);
+  const int r0 = seg * seg_rows;
+  const int n = rows - r0 < seg_rows ? rows - r0 : seg_rows;
+  float sim;
+  int arg;
+  bank_scan(v, bank + (size_t)r0 * kD, n, wmax, warg, &sim, &arg);
+  if (threadIdx.x == 0) {
+    part_sim[face * gridDim.y + seg] = sim;
+    part_arg[face * gridDim.y + seg] = arg >= 0 ? arg + r0 : -1;
+  }
+}
+
+__global__ void match_split_reduce_kernel(const float* __restrict__ part_sim, const int* __restrict__ part_arg, int segs,
+                                          float* __restrict__ sim_out, int* __restrict__ arg_out) {
+  const int face = blockIdx.x;
+  float m = -3.0e38f;
+  int a = -1;
+  for (int s = 0; s < segs; ++s) {                       // segments ascend in row index: strict > keeps the first occurrence
+    const int as = part_arg[face * segs + s];
+    const float ms = part_sim[face * segs + s];
+    if (as >= 0 && ms > m) { m = ms; a = as; }
+  }
+  sim_out[face] = a >= 0 ? m : -8.0f;
+  if (arg_out) arg_out[face] = a;
+}
+
 // live table: V[r] = the vector match_kernel would hold in shared memory for feature row r
 __global__ void __launch_bounds__(256) live_prepare_kernel(const float* __restrict__ feats, float* __restrict__ V, int rows) {
   __shared__ __align__(16) float v[kD];
@@ -339,6 +385,32 @@ extern "C" int pcb_match(pcb_ctx* c, const float* emb_dev, const float* emb_flip
     match_gemm_kernel<<<(f + kGemmFaces - 1) / kGemmFaces, 256, kGemmSmem, c->stream>>>(c->match_v, f, c->bank, c->bank_rows, sim_dev, argmax_dev);
     PCB_LAUNCH_CHECK(c, "match_gemm_kernel");
     return PCB_OK;
+  }
+  if (min_rows > 0 && c->bank_rows >= min_rows) {
+    // few faces: split the bank over enough blocks to fill the GPU (>= 128 rows per block)
+    int segs = (2 * c->num_sms + f - 1) / f;
+    const int max_segs = (c->bank_rows + 127) / 128;
+    if (segs > max_segs) segs = max_segs;
+    if (segs >= 2) {
+      const int seg_rows = (c->bank_rows + segs - 1) / segs;
+      segs = (c->bank_rows + seg_rows - 1) / seg_rows;
+      const size_t need = (size_t)f * segs * 2 * sizeof(float);
+      if (c->match_v_bytes < need) {
+        void* nb = pcb_dev_alloc(c, need < 65536 ? 65536 : need, false);
+        if (!nb) return pcb_fail(c, PCB_ERR_CUDA, "match: scratch alloc failed");
+        if (c->match_v) { PCB_CUDA(c, cudaStreamSynchronize(c->stream)); pcb_dev_free(c, c->match_v); }
+        c->match_v = (float*)nb;
+        c->match_v_bytes = need < 65536 ? 65536 : need;
+      }
+      float* part_sim = c->match_v;
+      int* part_arg = (int*)(c->match_v + (size_t)f * segs);
+      match_split_kernel<<<dim3(f, segs), 256, 0, c->stream>>>(emb_dev, emb_flip_dev, use_flip_dev, f, c->bank, c->bank_rows, seg_rows,
+                                                              feat_dev, part_sim, part_arg);
+      PCB_LAUNCH_CHECK(c, "match_split_kernel");
+      match_split_reduce_kernel<<<f, 1, 0, c->stream>>>(part_sim, part_arg, segs, sim_dev, argmax_dev);
+      PCB_LAUNCH_CHECK(c, "match_split_reduce_kernel");
+      return PCB_OK;
+    }
   }
   match_kernel<<<f, 256, 0, c->stream>>>(emb_dev, emb_flip_dev, use_flip_dev, f, c->bank, c->bank_rows, feat_dev, sim_dev, argmax_dev);
   PCB_LAUNCH_CHECK(c, "match_kernel");

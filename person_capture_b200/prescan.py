@@ -1237,9 +1237,14 @@ def replay(records: Dict[int, SampleRecord], table, feats_host, idxs: Sequence[i
             failure.append(exc)
             return -1
 
+    import time as _t
+    t_parts = [_t.perf_counter()]
     try:
         if use_gpu and n_rows:
             arm_live()
+            if os.environ.get("PCB_REPLAY_TIMING", "0") == "1":
+                eng.sync()
+        t_parts.append(_t.perf_counter())
         rc = L.ReplayCfg(enter=trk.enter, exit_thr=trk.exit, fd_add=float(getattr(cfg, "prescan_fd_add", trk.enter)),
                          quality_min=float(cfg.face_quality_min), total_frames=trk.total, pad=trk.pad, min_len=trk.min_len,
                          exit_cool=trk.exit_cool, stride=trk.stride, cooldown=int(getattr(cfg, "prescan_add_cooldown_samples", 5)),
@@ -1264,6 +1269,7 @@ def replay(records: Dict[int, SampleRecord], table, feats_host, idxs: Sequence[i
                         skip_out=ptr(skip), active_out=ptr(act), nfaces_out=ptr(nf), spans_out=ptr(spans), max_spans=max_spans,
                         n_spans_out=C.pointer(n_spans), refreshes_out=C.pointer(n_refresh))
         err = lib.pcb_replay(eng.ctx if use_gpu else None, C.byref(rc), nb, C.byref(io), C.byref(st))
+        t_parts.append(_t.perf_counter())
         if failure:
             raise failure[0]
         if err:
@@ -1285,6 +1291,7 @@ def replay(records: Dict[int, SampleRecord], table, feats_host, idxs: Sequence[i
     trk.active = False          # pcb_replay already closed the open span (gui_app.py:1648-1655)
     trk.distance_refreshes = int(n_refresh.value)
     trk.flip_on_demand = (flip_calls[0], round(1000.0 * flip_calls[1], 2))      # (calls, ms inside them)
+    trk.replay_parts_ms = [round(1000.0 * (b - a), 3) for a, b in zip(t_parts, t_parts[1:])]      # [arm live table, pcb_replay]
     if log is not None:
         for i, idx in enumerate(idxs):
             log.append(dict(idx=idx, skip=bool(skip[i]), best=float(best[i]), active_before=bool(act[i]), nfaces=int(nf[i])))
@@ -1475,6 +1482,7 @@ def prescan_batched(clip, fps: int, face: FaceEmbedder, ref_feat, cfg, batch: in
             stats["bank_rows"], stats["bank_versions"] = len(bank), bank.version
             stats["distance_refreshes"] = getattr(trk, "distance_refreshes", None)
             stats["flip_on_demand"] = getattr(trk, "flip_on_demand", None)
+            stats["replay_parts_ms"] = getattr(trk, "replay_parts_ms", None)
         _count_passes(stats, local_table)      # this rank's faces / ArcFace image passes
         spans = trk.finish()
         wmax = int(getattr(cfg, "prescan_max_width", 0))

@@ -482,3 +482,34 @@ def test_match_large_bank_tiled_equals_per_face(engine_25g_r50, monkeypatch):
     assert np.allclose(outs["1024"][1], sims.max(1), atol=5e-6)
     assert np.array_equal(outs["1024"][2], sims.argmax(1)) and int(outs["1024"][2][5]) == 105
     eng.set_bank(None)
+
+
+@pytest.mark.parametrize("f", [1, 3, 40])
+def test_match_large_bank_few_faces_split_equals_per_face(engine_25g_r50, monkeypatch, f):
+    """K5 for a few faces against a large bank (config 5 with a 10 000-row bank): the bank is split over blocks; the bits equal
+    the per-face kernel's -- similarity, argmax with first-occurrence ties across segment borders, features."""
+    eng = engine_25g_r50
+    rng = np.random.default_rng(23 + f)
+    B = 10007
+    emb = rng.normal(size=(f, 512)).astype(np.float32)
+    embf = rng.normal(size=(f, 512)).astype(np.float32)
+    bank = rng.normal(size=(B, 512)).astype(np.float32)
+    bank /= np.linalg.norm(bank, axis=1, keepdims=True)
+    v0 = emb[0] + embf[0]
+    bank[9000] = v0 / np.linalg.norm(v0)
+    bank[311] = bank[9000]                                   # duplicate in an earlier segment: row 311 must win
+    eng.set_bank(bank)
+    outs = {}
+    for mode in ("0", "1024"):
+        monkeypatch.setenv("PCB_MATCH_GEMM_ROWS", mode)
+        eng.reset_launch_count()
+        feat, sim, arg = eng.match(_dev(eng, emb), _dev(eng, embf), None, f)
+        eng.sync()
+        outs[mode] = (feat.cpu().numpy()[:f].copy(), sim.cpu().numpy()[:f].copy(), arg.cpu().numpy()[:f].copy(), eng.launch_count())
+    assert outs["0"][3] == 1 and outs["1024"][3] == 2          # per-face kernel vs split + reduce
+    for a, b in zip(outs["0"][:3], outs["1024"][:3]):
+        assert np.array_equal(a, b)
+    assert int(outs["1024"][2][0]) == 311
+    v = emb + embf
+    v = v / np.linalg.norm(v, axis=1, keepdims=True)
+    assert np.array_equal(outs["1024"][2], (v @ bank.T).argmax(1))
