@@ -236,13 +236,17 @@ typedef struct pcb_replay_io {
   int32_t n_rows;                          /* face-table rows */
   const double* quality; const int64_t* area;
   const uint8_t* flip_ready;               /* [n_rows] or NULL: all flip features present */
-  const float* feat_plain; const float* feat_flip;   /* host [n_rows][512]: what a bank offer appends (flip while a span is active) */
+  const float* feat_plain; const float* feat_flip;   /* host [n_rows][512]: what a bank offer appends (flip while a span is active);
+                                                         both NULL (ctx required): rows are read from the device tables below */
   double* fd_plain; double* fd_flip;       /* [n_rows] host distances, kept current by the refresh */
   pcb_replay_refresh_cb refresh; pcb_replay_flip_cb need_flip; void* user;
   /* outputs */
   double* best_out; uint8_t* skip_out; uint8_t* active_out; int32_t* nfaces_out;
   int64_t* spans_out; int32_t max_spans; int32_t* n_spans_out;
   int64_t* refreshes_out;                  /* may be NULL: distance refreshes performed */
+  const float* feat_plain_dev; const float* feat_flip_dev;   /* device [n_rows][512], used when the host tables are NULL: a 2 KB
+                                               * read per offer that is not a certain duplicate (tens per pre-scan) instead of
+                                               * a device->host copy of every feature */
 } pcb_replay_io;
 /* ctx may be NULL (no GPU: distances come from io->refresh).  With ctx, pcb_live_begin must have been called on the
  * [plain; flip] table (2 * n_rows rows) and fd_plain / fd_flip are filled by the library before the first sample. */

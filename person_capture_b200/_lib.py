@@ -97,7 +97,7 @@ class ReplayIO(C.Structure):
                 ("refresh", REPLAY_REFRESH_CB), ("need_flip", REPLAY_FLIP_CB), ("user", C.c_void_p),
                 ("best_out", C.c_void_p), ("skip_out", C.c_void_p), ("active_out", C.c_void_p), ("nfaces_out", C.c_void_p),
                 ("spans_out", C.c_void_p), ("max_spans", C.c_int32), ("n_spans_out", C.POINTER(C.c_int32)),
-                ("refreshes_out", C.POINTER(C.c_int64))]
+                ("refreshes_out", C.POINTER(C.c_int64)), ("feat_plain_dev", C.c_void_p), ("feat_flip_dev", C.c_void_p)]
 
 
 class PcbError(RuntimeError):

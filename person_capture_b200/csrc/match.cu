@@ -417,6 +417,18 @@ extern "C" int pcb_match(pcb_ctx* c, const float* emb_dev, const float* emb_flip
   return PCB_OK;
 }
 
+// replay.cu: the feature row a bank offer appends, read from the device table on demand (a handful per pre-scan: the replay
+// skips certain duplicates without looking at the vector)
+int pcb_fetch_row(pcb_ctx* c, const float* row_dev, float* out_host) {
+  PCB_ENTER(c);
+  if (!c->live_row_stage) PCB_CUDA(c, cudaMallocHost((void**)&c->live_row_stage, kD * sizeof(float)));
+  // live_row_stage: every user (this, pcb_live_refresh's bank row upload) synchronises the stream before returning
+  PCB_CUDA(c, cudaMemcpyAsync(c->live_row_stage, row_dev, kD * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  PCB_CUDA(c, cudaStreamSynchronize(c->stream));
+  memcpy(out_host, c->live_row_stage, kD * sizeof(float));
+  return PCB_OK;
+}
+
 extern "C" int pcb_live_begin(pcb_ctx* c, const float* feats_dev, int rows) {
   PCB_ENTER(c);
   if (rows < 0 || (rows > 0 && !feats_dev)) return pcb_fail(c, PCB_ERR_ARG, "live_begin: bad arguments");

@@ -13,7 +13,12 @@
 #include <algorithm>
 #include <vector>
 
+#include <stdlib.h>
+
 #include "../../include/pcb200.h"
+
+// match.cu: one 512-float row of a device feature table -> host (synchronous on the context's stream)
+int pcb_fetch_row(pcb_ctx* c, const float* row_dev, float* out_host);
 
 // ---------------------------------------------------------------------------------------------------------------
 // live bank
@@ -226,6 +231,10 @@ extern "C" int pcb_replay(pcb_ctx* ctx, const pcb_replay_cfg* cfg, pcb_bank* ban
 
   Tracker trk;
   trk.c = cfg;
+  const char* df_env = getenv("PCB_REPLAY_DUP_FILTER");
+  const bool dup_filter = !(df_env && df_env[0] == '0');
+  const double dedup_certain = bank->cfg.dedup + 1e-4;
+  float fetched[PCB_FEAT_DIM];
   long long last_add = -1000000000LL;
   std::vector<int> order;
   for (int s = 0; s < n_samples; ++s) {
@@ -293,7 +302,22 @@ extern "C" int pcb_replay(pcb_ctx* ctx, const pcb_replay_cfg* cfg, pcb_bank* ban
             const double f = fd[row];
             if (f < best) best = f;
             if (f <= cfg->fd_add && (long long)s - last_add >= cfg->cooldown && io->quality[row] >= cfg->quality_min) {
-              const float* vec = (active ? io->feat_flip : io->feat_plain) + (size_t)row * PCB_FEAT_DIM;
+              // `f` is 1 - max cosine of this row against the CURRENT bank (the refresh keeps it so), computed in fp32 on the
+              // GPU; pcb_bank_offer's own fp32 maximum differs from it by < 3.1e-5 (512 x 2^-24 for unit vectors), so a
+              // similarity at least 1e-4 above the de-duplication threshold is "dup" whatever the rounding: the offer (35+
+              // dot products on the host, for every target face of the clip once the bank has settled) and the feature row
+              // it would read are skipped.  Anything closer to the threshold takes the exact path.
+              if (dup_filter && pcb_bank_rows(bank) > 0 && 1.0 - f >= dedup_certain) continue;
+              const float* vec = nullptr;
+              const float* host = active ? io->feat_flip : io->feat_plain;
+              if (host) {
+                vec = host + (size_t)row * PCB_FEAT_DIM;
+              } else {
+                const float* dev = active ? io->feat_flip_dev : io->feat_plain_dev;
+                if (!ctx || !dev) return 2;
+                if (pcb_fetch_row(ctx, dev + (size_t)row * PCB_FEAT_DIM, fetched)) return PCB_REPLAY_ABORTED;
+                vec = fetched;
+              }
               int32_t slot = -1;
               const int act = pcb_bank_offer(bank, vec, io->quality[row], &slot);
               if (act == PCB_BANK_ADDED || act == PCB_BANK_REPLACED) {

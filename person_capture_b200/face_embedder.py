@@ -190,7 +190,13 @@ class FaceEmbedder:
         eng = self.engine
         H0, W0 = int(bgr_img.shape[0]), int(bgr_img.shape[1])
         # frames already resident in HBM (north_star) are used in place; host arrays go through pinned staging
-        frame = bgr_img.contiguous()[None] if on_device else eng.to_device(bgr_img[None])
+        if on_device:
+            # the caller may have produced the tensor on torch's current stream; everything below runs on the engine's
+            eng.stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(eng.stream):
+                frame = bgr_img.contiguous()[None]          # (a crop view is compacted here, on the stream that reads it)
+        else:
+            frame = eng.to_device(bgr_img[None])
         dyn = self.upright_size(H0, W0, imgsz)
         heavy90, heavy180 = self.heavy_sizes(H0, W0, dyn)
         fast = self._fast_prescan

@@ -101,8 +101,9 @@ class MainPassIdentity:
                 if rx2 > rx1 + 8 and ry2 > ry1 + 8:
                     ran = True
                     rec["roi"] = (rx1, ry1, rx2, ry2)
-                    roi = frame[ry1:ry2, rx1:rx2]
-                    roi = roi.contiguous() if isinstance(roi, torch.Tensor) else np.ascontiguousarray(roi)
+                    roi = frame[ry1:ry2, rx1:rx2]          # device frames: a view; extract() compacts it on the engine's stream
+                    if not isinstance(roi, torch.Tensor):
+                        roi = np.ascontiguousarray(roi)
                     cand = self._site(roi, "lock_roi", (rx1, ry1), W2, H2, rec)
                     if cand is not None:
                         self.misses = 0
@@ -154,8 +155,8 @@ def person_site(st: "MainPassIdentity", frame, boxes: Sequence[Tuple[int, int, i
     thr = float(cfg.face_thresh)
 
     def crop_of(x1, y1, x2, y2):
-        c = frame[y1:y2, x1:x2]
-        return c.contiguous() if isinstance(c, torch.Tensor) else np.ascontiguousarray(c)
+        c = frame[y1:y2, x1:x2]                            # device frames: a view; extract() compacts it on the engine's stream
+        return c if isinstance(c, torch.Tensor) else np.ascontiguousarray(c)
 
     def distances(faces):
         if not faces or not have_bank:

@@ -366,13 +366,13 @@ def prescan_sequential(clip, fps: int, face: FaceEmbedder, ref_feat, cfg, log: O
 
 
 def _post_process(spans, clip, fps, face, bank: RefBank, ref_feat, cfg, trk: SpanTracker, wmax: int, batched: int = 0, stats=None,
-                  shard=None):
+                  shard=None, known=None):
     gap = int(round(cfg.prescan_bridge_gap_sec * fps))
     do_bridge = getattr(cfg, "prescan_bridge_gap_sec", 0) > 0
     if spans and do_bridge:
         spans = bridge_spans(spans, gap)
     if batched:
-        spans = _refine_edges_batched(spans, clip, fps, face, bank, ref_feat, cfg, trk, batched, stats=stats, shard=shard)
+        spans = _refine_edges_batched(spans, clip, fps, face, bank, ref_feat, cfg, trk, batched, stats=stats, shard=shard, known=known)
     else:
         spans = _refine_edges(spans, clip, fps, face, bank, ref_feat, cfg, trk, wmax)
     if spans and do_bridge:
@@ -430,10 +430,16 @@ def _refine_edges(spans, clip, fps, face, bank: RefBank, ref_feat, cfg, trk: Spa
     return out
 
 
-def _refine_edges_batched(spans, clip, fps, face, bank: RefBank, ref_feat, cfg, trk: SpanTracker, batch: int, stats=None, shard=None):
+def _refine_edges_batched(spans, clip, fps, face, bank: RefBank, ref_feat, cfg, trk: SpanTracker, batch: int, stats=None, shard=None,
+                          known=None):
     """Same result as _refine_edges, but every candidate probe frame of all spans goes through the
     batched superset (two GPU rounds: all left windows, then all right windows, whose start depends
-    on the refined left edge).  Probes run in "full"/escalate mode: flip-TTA on, 90 then 270."""
+    on the refined left edge).  Probes run in "full"/escalate mode: flip-TTA on, 90 then 270.
+
+    `known` = dict(pos={frame: sample index}, meta=flat records, table=face table of the main scan): a probe frame that was a
+    SAMPLE of the main scan is not detected / embedded again -- its record is the same function of the same frame (the
+    superset is state independent), so the probe reduces to the flip-TTA distance of its faces to the final bank (missing flip
+    features are computed for those rows only).  With stride 1 every probe frame is such a frame."""
     if not spans:
         return spans
     total = clip.total_frames
@@ -449,6 +455,26 @@ def _refine_edges_batched(spans, clip, fps, face, bank: RefBank, ref_feat, cfg, 
         all_ids = sorted(set(frame_ids))
         if not all_ids:
             return {}
+        res_known = {}
+        if known is not None:
+            pos, meta, t = known["pos"], known["meta"], known["table"]
+            rows_of = {}
+            for j in all_ids:
+                if j not in pos:
+                    continue
+                m = meta[pos[j]]
+                c0 = 0 if m[0] >= 0 else next((6 + 2 * d for d in (0, 1) if m[2 + d] and m[4 + d] and m[6 + 2 * d] >= 0), None)
+                rows_of[j] = np.arange(m[c0], m[c0] + m[c0 + 1]) if c0 is not None else None
+            need = [r for r in rows_of.values() if r is not None]
+            fdf = None
+            if need:
+                if getattr(t, "lazy", False) and t.ensure_flip(face.engine, np.concatenate(need)):
+                    known["dist"].invalidate()          # (several ranks: every rank asks for the same rows -- a matched collective)
+                _, fdf = known["dist"].get(use_bank)
+            res_known = {j: bool(r is not None and (fdf[r] <= trk.enter).any()) for j, r in rows_of.items()}
+            all_ids = [j for j in all_ids if j not in res_known]
+            if not all_ids:
+                return res_known
         # several ranks: each probe frame is evaluated by the rank that owns its time chunk, results are all-gathered
         ids = all_ids if shard is None else [j for j in all_ids if shard["owner"](j) == shard["rank"]]
         res = {}
@@ -480,6 +506,7 @@ def _refine_edges_batched(spans, clip, fps, face, bank: RefBank, ref_feat, cfg, 
             dist.all_gather_into_tensor(recv.view(-1), mine.to(dev), group=shard["group"])
             hits = recv.cpu().numpy()
             res = {j: bool(hits[r, k]) for r in range(world) for k, j in enumerate(owned[r])}
+        res.update(res_known)
         return res
 
     left_ids = []
@@ -1164,7 +1191,7 @@ def replay(records: Dict[int, SampleRecord], table, feats_host, idxs: Sequence[i
         return _replay_python(records, table, feats_host, idxs, fps, total_frames, face, ref_feat, cfg, log, distances)
     lib = L.load()
     trk = SpanTracker(cfg, fps, total_frames)
-    plain_h, flip_h = feats_host
+    plain_h, flip_h = feats_host if feats_host is not None else (None, None)
     lazy = table is not None and getattr(table, "lazy", False)
     if lazy:
         flip_h = table.flip_host
@@ -1177,11 +1204,16 @@ def replay(records: Dict[int, SampleRecord], table, feats_host, idxs: Sequence[i
     frame_idx = np.asarray(idxs, np.int64)
     fdp = np.full(max(n_rows, 1), FD_NONE, np.float64)
     fdf = np.full(max(n_rows, 1), FD_NONE, np.float64)
-    plain_c = np.ascontiguousarray(plain_h, np.float32) if n_rows else np.zeros((1, L.FEAT_DIM), np.float32)
-    flip_c = np.ascontiguousarray(flip_h, np.float32) if (n_rows and flip_h is not None and len(flip_h)) else np.zeros((max(n_rows, 1), L.FEAT_DIM), np.float32)
-    if lazy and n_rows:
-        flip_c = table.flip_host            # filled in place by ensure_flip: the library must see the same memory
-        assert flip_c.flags["C_CONTIGUOUS"] and flip_c.dtype == np.float32
+    # bank offers read the face's feature row: from host tables when the caller has them (tests, gloo), else straight from
+    # the device tables, a row at a time (the replay skips certain duplicates, so only a handful of rows are ever read)
+    dev_feats = (distances is None and plain_h is None and table is not None and n_rows > 0 and getattr(table.plain, "is_cuda", False))
+    plain_c = flip_c = None
+    if not dev_feats:
+        plain_c = np.ascontiguousarray(plain_h, np.float32) if n_rows else np.zeros((1, L.FEAT_DIM), np.float32)
+        flip_c = np.ascontiguousarray(flip_h, np.float32) if (n_rows and flip_h is not None and len(flip_h)) else np.zeros((max(n_rows, 1), L.FEAT_DIM), np.float32)
+        if lazy and n_rows:
+            flip_c = table.flip_host            # filled in place by ensure_flip: the library must see the same memory
+            assert flip_c.flags["C_CONTIGUOUS"] and flip_c.dtype == np.float32
     ref_rows = None
     if ref_feat is not None:
         ref_rows = np.ascontiguousarray(np.asarray(ref_feat, np.float32).reshape(-1, L.FEAT_DIM))
@@ -1264,7 +1296,10 @@ def replay(records: Dict[int, SampleRecord], table, feats_host, idxs: Sequence[i
         ready = table.flip_ready.view(np.uint8) if lazy else None
         cb_r, cb_f = L.REPLAY_REFRESH_CB(on_refresh), L.REPLAY_FLIP_CB(on_flip)
         io = L.ReplayIO(meta=ptr(meta), frame_idx=ptr(frame_idx), n_samples=n, n_rows=n_rows, quality=ptr(quality), area=ptr(area),
-                        flip_ready=ptr(ready) if ready is not None else None, feat_plain=ptr(plain_c), feat_flip=ptr(flip_c),
+                        flip_ready=ptr(ready) if ready is not None else None,
+                        feat_plain=None if dev_feats else ptr(plain_c), feat_flip=None if dev_feats else ptr(flip_c),
+                        feat_plain_dev=table.plain.data_ptr() if dev_feats else None,
+                        feat_flip_dev=table.flip.data_ptr() if dev_feats else None,
                         fd_plain=ptr(fdp), fd_flip=ptr(fdf), refresh=cb_r, need_flip=cb_f, user=None, best_out=ptr(best),
                         skip_out=ptr(skip), active_out=ptr(act), nfaces_out=ptr(nf), spans_out=ptr(spans), max_spans=max_spans,
                         n_spans_out=C.pointer(n_spans), refreshes_out=C.pointer(n_refresh))
@@ -1308,15 +1343,15 @@ def _predict_flip_rows(records: Dict[int, SampleRecord], idxs: Sequence[int], fd
     stride = max(1, int(cfg.prescan_stride))
     exit_cool = int(round(max(0.0, float(getattr(cfg, "prescan_exit_cooldown_sec", 0.5))) * fps))
     tail = (exit_cool + stride - 1) // stride + 1
-    remaining = tail if carry_in else 0
+    # ... widened by the span padding on both sides: boundary refinement probes the padded edges in flip-TTA mode
+    pad_s = (int(round(max(0.0, float(getattr(cfg, "prescan_pad_sec", 0.0))) * fps)) + stride - 1) // stride + 1
+    per = [_rows_of(records[idx]) for idx in idxs]
+    hot = [bool(rws) and min(float(fd_plain[r].min()) for r in rws) <= enter + margin for rws in per]
+    n = len(per)
     rows: List[np.ndarray] = []
-    for idx in idxs:
-        rws = _rows_of(records[idx])
-        if remaining > 0:
-            rows += rws
-            remaining -= 1
-        if rws and min(float(fd_plain[r].min()) for r in rws) <= enter + margin:
-            remaining = tail
+    for k in range(n):
+        if any(hot[max(k - tail - pad_s, 0):min(k + pad_s + 1, n)]) or (carry_in and k < tail):
+            rows += per[k]
     return np.concatenate(rows) if rows else np.zeros((0,), np.int64)
 
 
@@ -1340,8 +1375,11 @@ def _predict_flip_rows_meta(meta: np.ndarray, fd_plain: np.ndarray, cfg, fps: in
             mins = np.minimum.reduceat(fd_plain[idx], np.cumsum(cnt[has]) - cnt[has])
             hot[has] |= mins <= thr
     c = np.concatenate([[0], np.cumsum(hot)])                     # c[k] = hot samples among the first k
-    lo = np.maximum(np.arange(n) - tail, 0)
-    sel = (c[np.arange(n)] - c[lo]) > 0                              # a hot sample among the `tail` samples before this one
+    # a hot sample among the `tail` samples before this one (the span is then active), widened by the padding on both sides:
+    # boundary refinement probes the padded edges of every span in flip-TTA mode and answers them from this table
+    pad_s = (int(round(max(0.0, float(getattr(cfg, "prescan_pad_sec", 0.0))) * fps)) + stride - 1) // stride + 1
+    k = np.arange(n)
+    sel = (c[np.minimum(k + pad_s + 1, n)] - c[np.maximum(k - tail - pad_s, 0)]) > 0
     if carry_in:
         sel[:tail] = True
     rows = []
@@ -1393,12 +1431,13 @@ class _ShardedTable:
         dist.all_gather_into_tensor(recv.view(-1), send.view(-1), group=self.group)
         if cuda:
             eng.stream.wait_stream(torch.cuda.current_stream())
-        host = recv.cpu().numpy()
+        host = recv.cpu().numpy() if self.flip_host is not None else None
         for r in range(world):
             rows_g = owned[r]
             if not len(rows_g):
                 continue
-            self.flip_host[rows_g] = host[r, :len(rows_g)]
+            if self.flip_host is not None:
+                self.flip_host[rows_g] = host[r, :len(rows_g)]
             self.flip_ready[rows_g] = True
             if cuda:
                 with torch.cuda.stream(eng.stream):
@@ -1468,12 +1507,18 @@ def prescan_batched(clip, fps: int, face: FaceEmbedder, ref_feat, cfg, batch: in
                 table.ensure_flip(eng, _predict_flip_rows_meta(table.encoded[0], fd0, cfg, fps, carry_in=rank > 0))
         TIMELINE.mark("predicted_flips_end", eng.stream)
         mark("predicted_flips")
-        plain_h = table.plain[:table.count].cpu().numpy() if table.count else np.zeros((0, L.FEAT_DIM), np.float32)
-        flip_h = (table.flip[:table.count].cpu().numpy() if (table.count and not lazy) else np.zeros((0, L.FEAT_DIM), np.float32))
+        # host copies of the features: only for the pure-Python replay, a non-NCCL group, or when asked for
+        # (PCB_REPLAY_HOST_FEATS=1); the native replay reads the few rows it offers to the bank from the device tables
+        want_host = (os.environ.get("PCB_PY_REPLAY", "0") == "1" or os.environ.get("PCB_REPLAY_HOST_FEATS", "0") == "1"
+                     or not table.count or not table.plain.is_cuda or (world > 1 and dist.get_backend(dist_group) != "nccl"))
+        plain_h = flip_h = None
+        if want_host:
+            plain_h = table.plain[:table.count].cpu().numpy() if table.count else np.zeros((0, L.FEAT_DIM), np.float32)
+            flip_h = (table.flip[:table.count].cpu().numpy() if (table.count and not lazy) else np.zeros((0, L.FEAT_DIM), np.float32))
         local_table = table
         encoded = table.encoded       # flat records built chunk by chunk during the GPU stage
         if world > 1:
-            table, plain_h, flip_h, encoded = _gather_shards(eng, encoded, table, plain_h, flip_h, world, dist_group)
+            table, plain_h, flip_h, encoded = _gather_shards(eng, encoded, table, plain_h, flip_h, world, dist_group, want_host=want_host)
             records = None
         mark("gather")
         trk, bank = replay(records, table, (plain_h, flip_h), idxs, fps, total, face, ref_feat, cfg, log, encoded=encoded)
@@ -1491,7 +1536,10 @@ def prescan_batched(clip, fps: int, face: FaceEmbedder, ref_feat, cfg, batch: in
             first_of = [idxs[min(r * per, len(idxs) - 1)] for r in range(world)]
             shard = dict(world=world, rank=rank, group=dist_group,
                          owner=lambda j: max(r for r in range(world) if first_of[r] <= j or r == 0))
-        spans = _post_process(spans, clip, fps, face, bank, ref_feat, cfg, trk, wmax, batched=batch, stats=stats, shard=shard)
+        known = None
+        if os.environ.get("PCB_REFINE_REUSE", "1") != "0" and table.count and getattr(table.plain, "is_cuda", False):
+            known = dict(pos={int(j): k for k, j in enumerate(idxs)}, meta=encoded[0], table=table, dist=_LiveDistances(eng, table))
+        spans = _post_process(spans, clip, fps, face, bank, ref_feat, cfg, trk, wmax, batched=batch, stats=stats, shard=shard, known=known)
         mark("refine")
     TIMELINE.dump()
     if stats is not None:
@@ -1516,7 +1564,7 @@ def _pinned(tag: str, shape, dtype) -> torch.Tensor:
     return buf[:n].view(*shape)
 
 
-def _gather_shards(eng, enc_local, table, plain_h, flip_h, world, group):
+def _gather_shards(eng, enc_local, table, plain_h, flip_h, world, group, want_host: bool = True):
     """All-gather of everything the replicated replay needs from the other ranks, as TWO tensor collectives: a 2-word
     header (face rows, samples) and one packed byte buffer per rank
 
@@ -1581,17 +1629,22 @@ def _gather_shards(eng, enc_local, table, plain_h, flip_h, world, group):
         # host copies (the replay hands bank offers a host vector): pinned, one copy per array
         small_h = _pinned("gather_small_in", (world, o_p), torch.uint8)
         small_h.copy_(recv[:, :o_p], non_blocking=True)
-        ph = _pinned("gather_plain", (max(base, 1), L.FEAT_DIM), torch.float32)
-        fh = _pinned("gather_flip", (max(base, 1), L.FEAT_DIM), torch.float32)
-        if base:
-            ph[:base].copy_(plain_all, non_blocking=True)
-            fh[:base].copy_(flip_all, non_blocking=True)
+        plain_host = flip_host = None
+        if want_host:
+            # (8 ranks x all features through one host memory system: 5 ms of a 90 ms step on the 8-GPU box -- hence optional)
+            ph = _pinned("gather_plain", (max(base, 1), L.FEAT_DIM), torch.float32)
+            fh = _pinned("gather_flip", (max(base, 1), L.FEAT_DIM), torch.float32)
+            if base:
+                ph[:base].copy_(plain_all, non_blocking=True)
+                fh[:base].copy_(flip_all, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         eng.stream.wait_stream(torch.cuda.current_stream())
         plain_all, flip_all = plain_all.contiguous(), flip_all.contiguous()
         # views of the reusable pinned buffers: valid until the next gather, i.e. for the rest of this pre-scan (the replay
         # reads them, on-demand flips write flip_host in place)
-        small_np, plain_host, flip_host = small_h.numpy(), ph[:base].numpy(), fh[:base].numpy()
+        small_np = small_h.numpy()
+        if want_host:
+            plain_host, flip_host = ph[:base].numpy(), fh[:base].numpy()
     else:
         small_np = recv[:, :o_p].numpy()
         plain_host, flip_host = plain_all[:base].numpy().copy(), flip_all[:base].numpy().copy()
@@ -1613,7 +1666,8 @@ def _gather_shards(eng, enc_local, table, plain_h, flip_h, world, group):
         row0 += counts[r]
     if lazy:
         ready = np.concatenate(readies) if base else np.zeros((0,), bool)
-        new = _ShardedTable(table, counts, rank, group, plain_all, flip_all, ready, np.ascontiguousarray(flip_host, np.float32))
+        new = _ShardedTable(table, counts, rank, group, plain_all, flip_all, ready,
+                            np.ascontiguousarray(flip_host, np.float32) if flip_host is not None else None)
     else:
         new = FaceTable()
         new.count = base

@@ -39,7 +39,12 @@ class ScrfdSession:
             raise ValueError("max_num > 0 (area/centre re-ranking) is not used by the reference and not implemented")
         eng = self.engine
         on_dev = isinstance(img, torch.Tensor)
-        frame = img.contiguous()[None] if on_dev else eng.to_device(np.ascontiguousarray(img)[None])
+        if on_dev:
+            eng.stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(eng.stream):
+                frame = img.contiguous()[None]
+        else:
+            frame = eng.to_device(np.ascontiguousarray(img)[None])
         res = eng.detect(frame, int(input_size[0]), float(self.det_thresh), min_box=0, max_det=self.max_det)
         eng.sync()
         n = int(res.raw_count.cpu()[0])

@@ -273,3 +273,28 @@ def test_vectorised_flip_prediction_equals_the_loop(seed, carry):
     want = np.sort(PS._predict_flip_rows(records, idxs, fd, cfg, fps, carry_in=carry))
     got = np.sort(PS._predict_flip_rows_meta(meta, fd, cfg, fps, carry_in=carry))
     assert np.array_equal(got, want) and len(want) > 0
+
+
+@pytest.mark.parametrize("seed,bank_max", [(0, 64), (2, 3), (11, 5)])
+def test_replay_dup_filter_is_a_pure_shortcut(seed, bank_max, monkeypatch):
+    """pcb_replay skips bank offers whose live distance says "certain duplicate" (similarity >= dedup + 1e-4).  With the
+    shortcut switched off (PCB_REPLAY_DUP_FILTER=0) every offer is evaluated: spans, bank and log must not change."""
+    rng = np.random.default_rng(seed)
+    n = 240
+    target = unit(rng.normal(size=512))
+    sc = make_scenario(rng, n, target)
+    cfg = PrescanParams(prescan_stride=1, prescan_max_width=10 ** 6, prescan_bank_max=bank_max, prescan_fd_add=0.3,
+                        prescan_add_cooldown_samples=0, face_quality_min=50.0, prescan_min_segment_sec=0.25,
+                        prescan_pad_sec=0.1, prescan_exit_cooldown_sec=0.2, prescan_boundary_refine_sec=0.0)
+    ref_feat = unit(target + rng.normal(0, 0.03, 512))[None]
+    records, P, Fl = to_records(sc)
+    idxs = PS.sample_indices(n, 1)
+    res = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("PCB_REPLAY_DUP_FILTER", mode)
+        face, glog = FakeFace(sc), []
+        trk, bank = PS.replay(records, None, (P, Fl), idxs, 24, n, face, ref_feat, cfg, log=glog, distances=NumpyDistances(P, Fl), native=True)
+        res[mode] = (trk.finish(), bank.version, [(g["idx"], g["skip"], g["active_before"], g["nfaces"], g["best"]) for g in glog], bank.array())
+    assert res["0"][:3] == res["1"][:3]
+    assert np.array_equal(res["0"][3], res["1"][3])
+    assert res["0"][1] >= 3

@@ -13,6 +13,7 @@ FD_TOL_E2E = 3e-3
 import numpy as np
 import pytest
 import cv2
+import torch
 
 import pcb_test_helpers as H
 from person_capture_b200 import synth
@@ -247,6 +248,57 @@ def test_early_flip_passes_do_not_change_results(engine_25g_r50, monkeypatch):
     assert out["1"][3].get("early_flip_rows", 0) > 0 and out["0"][3].get("early_flip_rows", 0) == 0
 
 
+def test_replay_device_features_and_dup_filter_do_not_change_results(engine_25g_r50, monkeypatch):
+    """The native replay reads the feature rows it offers to the bank from the device tables and skips offers that are certain
+    duplicates (similarity >= dedup + 1e-4 by the live distances).  Both only remove work: spans, bank rows and the per-sample
+    log are bit-identical to the run with host feature tables and every offer evaluated."""
+    from person_capture_b200 import prescan as PS
+    from person_capture_b200.face_embedder import FaceEmbedder
+    cfg, clip, ref_img = _make_case(1003, 640, 360, 192, 1, prescan_add_cooldown_samples=0, prescan_bank_max=6)
+    frames = [clip.frame(i) for i in range(clip.n_frames)]
+    face = FaceEmbedder("cuda:0", "scrfd_2.5g_bnkps", conf=cfg.face_det_conf, engine=engine_25g_r50, arcface_model="arcface_r50")
+    bank = PS.build_reference_bank(face, [ref_img], cfg)
+    src = PS.HostClip(lambda i: frames[i], len(frames))
+    out = {}
+    for host_feats, dup_filter in (("1", "0"), ("1", "1"), ("0", "0"), ("0", "1")):
+        monkeypatch.setenv("PCB_REPLAY_HOST_FEATS", host_feats)
+        monkeypatch.setenv("PCB_REPLAY_DUP_FILTER", dup_filter)
+        log, stats = [], {}
+        spans, b = PS.prescan_batched(src, 24, face, bank, cfg, batch=16, log=log, stats=stats)
+        out[(host_feats, dup_filter)] = (spans, np.asarray(b), [(r["idx"], r["skip"], r["nfaces"], r["best"]) for r in log], stats)
+    base = out[("1", "0")]
+    assert len(base[0]) >= 1 and base[1].shape[0] > np.asarray(bank).shape[0] and base[3]["bank_versions"] >= 3
+    for k, v in out.items():
+        assert v[0] == base[0], k
+        assert np.array_equal(v[1], base[1]), k
+        assert v[2] == base[2], k
+        assert v[3]["bank_versions"] == base[3]["bank_versions"], k
+
+
+@pytest.mark.parametrize("stride", [1, 2])
+def test_refine_reuses_main_scan_records_without_changing_spans(engine_25g_r50, monkeypatch, stride):
+    """Boundary refinement answers probe frames that were samples of the main scan from the face table (flip-TTA distance to
+    the final bank) instead of detecting / embedding them again; off-grid frames (stride 2: every other one) still go through
+    the GPU.  Spans and bank equal the run that recomputes every probe, and the sequential driver."""
+    from person_capture_b200 import prescan as PS
+    from person_capture_b200.face_embedder import FaceEmbedder
+    cfg, clip, ref_img = _make_case(1003, 640, 360, 192, stride, prescan_add_cooldown_samples=2)
+    frames = [clip.frame(i) for i in range(clip.n_frames)]
+    face = FaceEmbedder("cuda:0", "scrfd_2.5g_bnkps", conf=cfg.face_det_conf, engine=engine_25g_r50, arcface_model="arcface_r50")
+    bank = PS.build_reference_bank(face, [ref_img], cfg)
+    src = PS.HostClip(lambda i: frames[i], len(frames))
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("PCB_REFINE_REUSE", mode)
+        stats = {}
+        spans, b = PS.prescan_batched(src, 24, face, bank, cfg, batch=16, stats=stats)
+        out[mode] = (spans, np.asarray(b), stats["faces"])
+    s_seq, b_seq = PS.prescan_sequential(src, 24, face, bank, cfg)
+    assert out["0"][0] == out["1"][0] == s_seq and len(s_seq) >= 1
+    assert np.array_equal(out["0"][1], out["1"][1])
+    assert out["1"][2] < out["0"][2]              # fewer faces went through detection + embedding
+
+
 def test_prescan_cache_roundtrip_with_gpu_result(engine_25g_r50, tmp_path):
     from oracle import prescan as OP
     from person_capture_b200 import prescan as PS
@@ -328,6 +380,35 @@ def test_main_pass_decisions_match_oracle(engine_25g_r50):
             assert np.abs(np.array(h["face_box"]) - np.array(oh[h["idx"]]["face_box"])).max() <= 2, (h, oh[h["idx"]])
             assert abs(h["fd"] - oh[h["idx"]]["fd"]) <= FD_TOL_E2E * 2
     assert len(ohits) >= 10 and any(h["site"] == "lock_roi" for h in ohits)
+
+
+def test_main_pass_on_device_frames_is_repeatable_and_equals_host_frames(engine_25g_r50):
+    """ROI crops of device-resident frames are views compacted on the ENGINE's stream (they used to be compacted on torch's
+    current stream, unordered with the kernels that read them: on 4K frames the lock-face ROI site then saw stale pixels and
+    the main pass was not repeatable).  Two runs over device frames and one over host frames give identical hits, with a
+    competing copy kept busy on torch's current stream."""
+    from person_capture_b200 import mainpass as MP, prescan as PS
+    from person_capture_b200.face_embedder import FaceEmbedder
+    eng = engine_25g_r50
+    cfg = PrescanParams(face_model="scrfd_2.5g_bnkps", face_thresh=0.62, face_quality_min=40.0, face_fullframe_imgsz=640,
+                        frame_stride=1, face_fullframe_cadence=6, lock_face_roi_max_misses=3)
+    clip = synth.ClipSpec(1920, 1080, 40, seed=1011, target_segments=[(0, 39)], face_px=(70, 110))
+    frames = np.stack([clip.frame(i) for i in range(clip.n_frames)])
+    ref_img = synth.reference_image(1, 512, seed=1011)
+    spans = [(0, 18), (22, 39)]
+    key = lambda h: (h["idx"], h["site"], tuple(h["face_box"]), h["fd"])
+    runs = []
+    dev = PS.DeviceClip(eng.to_device(frames))
+    noise = torch.empty((64 << 20,), dtype=torch.uint8, device=eng.tdev)
+    for mode in ("dev", "dev", "host"):
+        face = FaceEmbedder("cuda:0", "scrfd_2.5g_bnkps", conf=cfg.face_det_conf, engine=eng)
+        bank = PS.build_reference_bank(face, [ref_img], cfg)
+        noise.random_(0, 255)                      # work on torch's current stream while the engine's stream runs the pass
+        src = dev if mode == "dev" else PS.HostClip(lambda i: frames[i], len(frames))
+        hits = MP.main_pass(src, 24.0, spans, face, bank, cfg, device_frames=(mode == "dev"))
+        runs.append([key(h) for h in hits])
+    assert runs[0] == runs[1] == runs[2]
+    assert len(runs[0]) >= 20 and any(k[1] == "lock_roi" for k in runs[0])
 
 
 def test_fullframe_identity_batched_matches_per_frame_extract(engine_25g_r50):
