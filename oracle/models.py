@@ -9,8 +9,8 @@ here, so this file *defines* the architectures from the upstream InsightFace con
 both sides (oracle and CUDA path) load the same exported weight file.
 
 parity unpinned for the graphs: the reference ships no tests or golden vectors for them
-(SURVEY.md F2); torch-CPU fp32 stands in for ONNX Runtime CPU (not installed, F4) and is
-cross-checked against cv2.dnn running the exported ONNX file (tests/test_oracle_onnx.py).
+(SURVEY.md F2); torch-CPU fp32 stands in for ONNX Runtime CPU (not installed, F4; the `onnx` package is absent too, so
+the graphs cannot be exported and cross-checked through cv2.dnn here).
 
 Weight file format ("folded", one .npz per model): every conv `name` has
   name.w      float16 [Cout, Cin, kh, kw]   (values exactly representable in fp16)

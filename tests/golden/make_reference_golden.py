@@ -214,6 +214,29 @@ def gen_prescan(ga, out):
         print(f"prescan[{name}]: {len(face.calls)} extract calls, spans {spans}, bank rows {0 if bank is None else len(bank)}")
 
 
+def gen_prescan_full(fe, ga, out):
+    """The reference's _prescan driving the reference's FaceEmbedder (both unmodified) over a rendered clip: the composition
+    of the loop's knob changes with the embedder's rotation / flip state, frame downscale included."""
+    rec = RecordingScrfd(SCRFDOracle(H.oracle_scrfd(S.EXTRACT_SCRFD)))
+    R = RH.make_reference_embedder(fe, rec, H.proj_arcface, conf=0.5)
+    frames, ref_img = S.full_clip_frames()
+    cfg = make_cfg(ga, S.FULL_CFG)
+    rfaces = R.extract(ref_img)
+    ref = np.asarray(max(rfaces, key=lambda f: f["quality"])["feat"], np.float32)[None]
+    P = make_processor(ga, cfg, S.FULL_FPS, S.FULL_N)
+    spans, bank = P._prescan(S.FrameCap(frames), S.FULL_FPS, S.FULL_N, R, ref, cfg)
+    out["pf_call_meta"] = np.array([[0, c["crc"], c["h"], c["w"], c["size"], len(c["det"])] for c in rec.calls], np.int64).reshape(-1, 6)
+    out["pf_call_thresh"] = np.array([c["thresh"] for c in rec.calls], np.float64)
+    out["pf_det"] = np.concatenate([c["det"] for c in rec.calls])
+    out["pf_kps"] = np.concatenate([c["kps"] for c in rec.calls])
+    out["pf_ref"] = ref
+    out["pf_spans"] = np.asarray(spans, np.int64).reshape(-1, 2)
+    out["pf_bank"] = np.asarray(bank, np.float32).reshape(-1, 512)
+    out["pf_state"] = np.array([R._no_face_streak, R._rot_cycle, R._prescan_rr, R._frame_idx, R._last_face_idx, int(R._fast_prescan),
+                                int(R._prescan_escalate), int(R.rot_adaptive)], np.int64)
+    print(f"prescan_full: {len(rec.calls)} SCRFD passes, spans {spans}, bank rows {len(bank)}")
+
+
 def gen_cache(ga, out):
     import shutil
     video, ref = S.cache_files()
@@ -289,6 +312,7 @@ def main():
     gen_bank(ga, out)
     gen_prescan(ga, out)
     gen_cache(ga, out)
+    gen_prescan_full(fe, ga, out)
     gen_extract(fe, out)
     np.savez_compressed(OUT, **out)
     print("wrote", OUT, os.path.getsize(OUT), "bytes,", len(out), "arrays")

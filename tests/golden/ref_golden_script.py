@@ -238,7 +238,8 @@ class RecordingFakeFace(FakeFace):
 
 
 _BASE_CFG = dict(prescan_max_width=10 ** 6, prescan_fd_add=0.3, prescan_add_cooldown_samples=2, face_quality_min=50.0,
-                 prescan_min_segment_sec=0.25, prescan_pad_sec=0.1, prescan_exit_cooldown_sec=0.2, prescan_boundary_refine_sec=0.0)
+                 prescan_min_segment_sec=0.25, prescan_pad_sec=0.1, prescan_exit_cooldown_sec=0.2, prescan_boundary_refine_sec=0.0,
+                 prescan_refine_budget_sec=0.0)          # no wall-clock cap on the refine pass: the vectors must not depend on timing
 
 
 def prescan_cases():
@@ -274,6 +275,29 @@ def prescan_inputs(case):
     else:
         ref = unit(target + rng.normal(0, 0.03, 512))[None]
     return sc, ref
+
+
+class FrameCap(PipeLikeCap):
+    """PipeLikeCap over real frames."""
+
+    def __init__(self, frames):
+        super().__init__(len(frames))
+        self.frames = frames
+
+    def frame(self, i):
+        return self.frames[i] if 0 <= i < self.n else None
+
+
+FULL_CFG = dict(face_model="scrfd_2.5g_bnkps", prescan_stride=3, prescan_max_width=416, prescan_fd_enter=0.25, prescan_fd_exit=0.32,
+                prescan_fd_add=0.12, face_quality_min=40.0, prescan_min_segment_sec=0.5, prescan_pad_sec=0.25, prescan_bridge_gap_sec=0.25,
+                prescan_exit_cooldown_sec=0.25, prescan_boundary_refine_sec=0.5, prescan_add_cooldown_samples=2, prescan_probe_imgsz=384,
+                prescan_refine_budget_sec=0.0)     # 0 disables the reference's wall-clock cap on the refine pass (timing dependent, SURVEY H7)
+FULL_N, FULL_FPS, FULL_SEED = 144, 24, 1001
+
+
+def full_clip_frames():
+    clip = synth.ClipSpec(640, 360, FULL_N, seed=FULL_SEED)
+    return [clip.frame(i) for i in range(FULL_N)], synth.reference_image(1, 512, seed=FULL_SEED)
 
 
 # ------------------------------------------------------------------------------------------------- curator

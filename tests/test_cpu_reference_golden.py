@@ -60,8 +60,9 @@ class ReplayScrfd:
     """Returns the detections the reference's run recorded, and demands that the caller made the SAME detector call:
     same input image (CRC + shape), same input size, same threshold, in the same order."""
 
-    def __init__(self):
-        self.meta, self.thresh = G["ex_call_meta"], G["ex_call_thresh"]
+    def __init__(self, prefix="ex"):
+        self.prefix = prefix
+        self.meta, self.thresh = G[prefix + "_call_meta"], G[prefix + "_call_thresh"]
         self.off = np.concatenate([[0], np.cumsum(self.meta[:, 5])]).astype(np.int64)
         self.k = 0
         self.cur_extract = 0
@@ -77,7 +78,7 @@ class ReplayScrfd:
         assert crc(img) == c, f"pass {k}: detector input image differs from the reference's"
         self.k += 1
         a, b = self.off[k], self.off[k + 1]
-        return G["ex_det"][a:b].copy(), G["ex_kps"][a:b].copy()
+        return G[self.prefix + "_det"][a:b].copy(), G[self.prefix + "_kps"][a:b].copy()
 
 
 def test_extract_matches_reference():
@@ -218,6 +219,27 @@ def test_prescan_matches_reference(name):
         pb = np.zeros((0, 512), np.float32) if pb is None else pb
         np.testing.assert_allclose(pb, want_bank if len(want_bank) else pb, rtol=0, atol=2e-7)
         assert len(pb) == len(want_bank) or (ref is not None and len(want_bank) == len(np.atleast_2d(ref)) and len(pb) == len(want_bank))
+
+
+def test_prescan_with_real_embedder_matches_reference():
+    """Processor._prescan driving FaceEmbedder.extract (both the reference's own code) over a rendered 640x360 clip, against
+    the oracle's prescan driving the oracle's embedder: same detector calls in the same order (frame downscale, probe sizes,
+    rotation cadence under rr / full mode, thresholds), same spans after bridge + refine, same grown bank, same final state."""
+    rep = ReplayScrfd("pf")
+    O = OF.FaceEmbedderOracle(rep, H.ProjArcface(), conf=0.5)
+    frames, ref_img = S.full_clip_frames()
+    cfg = _cfg(S.FULL_CFG)
+    rfaces = O.extract(ref_img)
+    ref = np.asarray(max(rfaces, key=lambda f: f["quality"])["feat"], np.float32)[None]
+    np.testing.assert_allclose(ref, G["pf_ref"], rtol=0, atol=1e-6)
+    spans, bank = OP.prescan(lambda i: frames[i] if 0 <= i < len(frames) else None, S.FULL_FPS, S.FULL_N, O, G["pf_ref"], cfg)
+    assert rep.k == len(G["pf_call_meta"])                       # every pass of the reference's run, none more
+    assert [tuple(int(v) for v in sp) for sp in spans] == [tuple(int(v) for v in r) for r in G["pf_spans"]] and len(spans) >= 2
+    np.testing.assert_allclose(np.asarray(bank, np.float32), G["pf_bank"], rtol=0, atol=1e-6)
+    assert len(G["pf_bank"]) > 1
+    st = G["pf_state"]
+    assert (O._no_face_streak, O._rot_cycle, O._prescan_rr, O._frame_idx, O._last_face_idx, int(O._fast_prescan),
+            int(O._prescan_escalate), int(O.rot_adaptive)) == tuple(int(v) for v in st)
 
 
 # ------------------------------------------------------------------------------------------------- cache
