@@ -1444,7 +1444,8 @@ int pcb_conv_tc2(pcb_ctx* c, const ConvArgs& a) {
     if (mode != 0 && (p.residual || p.out2)) return pcb_fail(c, PCB_ERR_ARG, "conv_tc2: fp32 outputs take no residual / second output");
     const int key = mode == 0 ? (p.act * 4 + (p.residual ? 2 : 0) + (p.out2 ? 1 : 0)) : (100 + mode * 4 + p.act);
     cudaError_t le = cudaErrorInvalidValue;
-    // programmatic dependent launch (see the kernel's prologue); off while the per-launch profile or the stall counters are on
+    // programmatic dependent launch (see the kernel's prologue); PCB_CONV_PDL=0 launches without the attribute.  Always off while
+    // the per-launch profile or the stall counters are on (an event between two launches serialises them anyway).
     static const int pdl_mode = env_int("PCB_CONV_PDL", 1);
     const bool pdl = pdl_mode != 0 && !c->profile && !p.dbg;
 #define PCB_TC2_LAUNCH(ACT, RES, OUT2, MODE, VAR)                                                                       \

@@ -86,7 +86,12 @@ constexpr int kLbDet = 2 * kLbTile + 1;     // det pixels needed per edge (33)
 // kPlain: no rotation, no replicate border, bilinear tables (the upright pass of every frame): source pixels are addressed directly
 template <bool kPlain>
 __global__ void __launch_bounds__(256) letterbox_kernel(const LetterboxParams p) {
-  __shared__ uint8_t tile[kLbDet][kLbDet][4];   // [.][.][3] = 1 when the det pixel is inside [0,S)
+  __shared__ __align__(4) uint8_t tile[kLbDet][kLbDet][4];   // [.][.][3] = 1 when the det pixel is inside [0,S)
+  // (v - 127.5) / 128 as fp16, tabulated per byte value (exact: the float expression has 9 significant bits); entry 256 = the
+  // zero of taps outside the detector image.  Replaces four conversions / multiplies per tap, 27 taps per output pixel.
+  __shared__ __half lut[257];
+  lut[threadIdx.x] = __float2half_rn(((float)threadIdx.x - 127.5f) * (1.0f / 128.0f));
+  if (threadIdx.x == 0) lut[256] = __float2half_rn(0.f);
   const int img = blockIdx.z;
   const int oy0 = blockIdx.y * kLbTile, ox0 = blockIdx.x * kLbTile;
   const int dy0 = 2 * oy0 - 1, dx0 = 2 * ox0 - 1;
@@ -145,7 +150,7 @@ __global__ void __launch_bounds__(256) letterbox_kernel(const LetterboxParams p)
         d[0] = o[0]; d[1] = o[1]; d[2] = o[2];
       }
     }
-    tile[ty][tx][0] = o[0]; tile[ty][tx][1] = o[1]; tile[ty][tx][2] = o[2]; tile[ty][tx][3] = inside;
+    *(uint32_t*)tile[ty][tx] = (uint32_t)o[0] | ((uint32_t)o[1] << 8) | ((uint32_t)o[2] << 16) | ((uint32_t)inside << 24);
   }
   __syncthreads();
   const int ly = threadIdx.x / kLbTile, lx = threadIdx.x % kLbTile;
@@ -156,13 +161,13 @@ __global__ void __launch_bounds__(256) letterbox_kernel(const LetterboxParams p)
   for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
     for (int kx = 0; kx < 3; ++kx) {
-      const uint8_t* t = tile[2 * ly + ky][2 * lx + kx];
-      const bool in = t[3] != 0;
+      const uint32_t t = *(const uint32_t*)tile[2 * ly + ky][2 * lx + kx];      // B | G << 8 | R << 16 | inside << 24
+      const bool in = (t >> 24) != 0;
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         // blobFromImage(swapRB): channel c of the blob is BGR channel 2-c; (v - 127.5) / 128 is exact in fp16
-        const float f = in ? ((float)t[2 - c] - 127.5f) * (1.0f / 128.0f) : 0.f;
-        vals[(ky * 3 + kx) * 3 + c] = __float2half_rn(f);
+        const uint32_t v = (t >> (8 * (2 - c))) & 0xffu;
+        vals[(ky * 3 + kx) * 3 + c] = lut[in ? v : 256u];
       }
     }
 #pragma unroll

@@ -246,14 +246,15 @@ class Engine:
         bank on the device already carries it -- a 10 000-row bank is 20 MB."""
         if token is not None and token == getattr(self, "_bank_token", None):
             return
-        self._bank_token = token
+        self._bank_token = None          # a failed upload must not look like a cached one
         if bank is None or np.asarray(bank).size == 0:
             self._check(self.lib.pcb_set_bank(self.ctx, None, 0), "pcb_set_bank")
             self.bank_rows = 0
-            return
-        b = np.ascontiguousarray(np.asarray(bank, np.float32).reshape(-1, L.FEAT_DIM))
-        self._check(self.lib.pcb_set_bank(self.ctx, b.ctypes.data_as(C.c_void_p), b.shape[0]), "pcb_set_bank")
-        self.bank_rows = b.shape[0]
+        else:
+            b = np.ascontiguousarray(np.asarray(bank, np.float32).reshape(-1, L.FEAT_DIM))
+            self._check(self.lib.pcb_set_bank(self.ctx, b.ctypes.data_as(C.c_void_p), b.shape[0]), "pcb_set_bank")
+            self.bank_rows = b.shape[0]
+        self._bank_token = token
 
     def match(self, emb: torch.Tensor, emb_flip: Optional[torch.Tensor], use_flip: Optional[torch.Tensor], f: int,
               want_feat: bool = True):

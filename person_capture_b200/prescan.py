@@ -23,6 +23,7 @@ from __future__ import annotations
 import ast
 import hashlib
 import json
+import itertools
 import os
 from dataclasses import dataclass, field
 from pathlib import Path
@@ -99,11 +100,18 @@ def _weights3(cfg) -> Tuple[float, float, float]:
     return 0.70, 0.25, 0.05
 
 
+_BANK_SERIAL = itertools.count(1)
+
+
 class RefBank:
     """The live reference bank (rows are unit vectors) with the reference's streaming update."""
 
     def __init__(self, cfg, rows: Optional[np.ndarray] = None):
         self.cfg = cfg
+        # identity for Engine.set_bank's "already uploaded" check.  NOT id(self): CPython hands the address of a freed bank to
+        # the next one, and a new bank (version 0) then looked like the previous main pass's bank -- distances were computed
+        # against a stale device bank (found by test_main_pass_on_device_frames_is_repeatable_* after another main-pass test)
+        self.serial = next(_BANK_SERIAL)
         self.rows: List[np.ndarray] = []
         if rows is not None:
             arr = np.asarray(rows, dtype=np.float32)
@@ -321,7 +329,7 @@ def _fds_for_last_faces(face: FaceEmbedder, bank: RefBank) -> np.ndarray:
     eng = face.engine
     feats = face.last_feats_dev
     f = face.last_face_count
-    eng.set_bank(bank.array(), token=(id(bank), bank.version))
+    eng.set_bank(bank.array(), token=(bank.serial, bank.version))
     _, sim, _ = eng.match(feats, None, None, f, want_feat=False)
     eng.sync()
     return 1.0 - sim[:f].cpu().numpy().astype(np.float64)

@@ -298,3 +298,15 @@ def test_replay_dup_filter_is_a_pure_shortcut(seed, bank_max, monkeypatch):
     assert res["0"][:3] == res["1"][:3]
     assert np.array_equal(res["0"][3], res["1"][3])
     assert res["0"][1] >= 3
+
+
+def test_bank_identity_survives_address_reuse():
+    """Engine.set_bank skips the upload when the bank's (serial, version) is already on the device.  The identity must not be
+    id(bank): CPython reuses the address of a freed object, and a new bank then passed for the previous one."""
+    cfg = PrescanParams()
+    seen = set()
+    for _ in range(200):
+        b = PS.RefBank(cfg, unit(np.random.default_rng(0).normal(size=512))[None])
+        assert (b.serial, b.version) not in seen
+        seen.add((b.serial, b.version))
+        del b

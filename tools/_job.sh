@@ -1,13 +1,14 @@
-mkdir -p gpurun_out/r3d
-N=${NG:-8}
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus $N --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r3d/bench_n$N.json 2> gpurun_out/r3d/bench_n$N.err
-timeout 400 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r3d/bench_n1_on$N.json 2> gpurun_out/r3d/bench_n1_on$N.err
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29551 tools/bench_mainpass.py --steps 3 --warmup 1 > gpurun_out/r3d/mp_n$N.json 2> gpurun_out/r3d/mp_n$N.err
+O=gpurun_out/r3i; mkdir -p $O
+for i in 1 2; do timeout 1500 python -m pytest tests -m gpu -x -q > $O/pytest_$i.log 2>&1; echo "full run $i: $(tail -1 $O/pytest_$i.log)"; grep -E "^FAILED|At index" $O/pytest_$i.log | cut -c1-200; done
+for i in 1 2; do timeout 600 python -m pytest tests/test_gpu_e2e.py -m gpu -q > $O/e2e_$i.log 2>&1; echo "e2e run $i: $(tail -1 $O/e2e_$i.log)"; grep -E "^FAILED|At index" $O/e2e_$i.log | cut -c1-200; done
+python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1; tail -1 $O/smoke.log
+timeout 600 python bench.py > $O/bench_default.json 2> $O/bench_default.err
+timeout 600 python bench.py --impl reference > $O/bench_reference.json 2> $O/bench_reference.err
+timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline > $O/bench_20.json 2> $O/bench_20.err
+python tools/bench_configs.py > $O/configs.txt 2>&1; grep -E "^C[345]" $O/configs.txt
 python - <<PY
 import json
-for f in ("bench_n$N","bench_n1_on$N"):
-    d=json.loads(open("gpurun_out/r3d/%s.json"%f).read().strip().splitlines()[-1])
-    print(f, "value", round(d["value"]), "with-events", round(d["value_with_launch_events"]["value"]), "e2e", round(d["e2e"]["value"]), "frac", round(d["roofline"]["frac"],4), d["phase_ms_last_step"], d["phase_ms_last_e2e_step"], d["bank_last_step"], d.get("multi_gpu_check"))
-d=json.loads(open("gpurun_out/r3d/mp_n$N.json").read().strip().splitlines()[-1])
-print("mainpass", d["n_gpus"], round(d["value"],1), d["equals_sequential_main_pass"], d["hits"], d["fixup_rounds"])
+for f in ("bench_default","bench_20"):
+    d=json.loads(open("$O/%s.json"%f).read().strip().splitlines()[-1])
+    print(f, "value", round(d["value"]), "with-events", round(d["value_with_launch_events"]["value"]), "e2e", round(d["e2e"]["value"]), "frac", round(d["roofline"]["frac"],4), d["phase_ms_last_step"], d.get("parity",{}).get("spans_equal"))
 PY
