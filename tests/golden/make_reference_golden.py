@@ -274,6 +274,14 @@ def gen_cache(ga, out):
     shutil.rmtree(S.CACHE_DIR, ignore_errors=True)
 
 
+def gen_geometry(ga, out):
+    cases, pairs = S.geometry_cases()
+    P = make_processor(ga, make_cfg(ga, {}), 24, 10)
+    out["geo_expand"] = np.array([ga.Processor._expand_xyxy(b, px, py, W, Hh) for b, px, py, W, Hh in cases], np.int64)
+    out["geo_clip"] = np.array([ga.Processor._clip_to_frame(b[0], b[1], b[2], b[3], W, Hh) for b, px, py, W, Hh in cases], np.int64)
+    out["geo_iou"] = np.array([P._iou(a, b) for a, b in pairs], np.float64)
+
+
 def gen_curator(out):
     import importlib
     dc = importlib.import_module("person_capture.dataset_curator")
@@ -308,6 +316,7 @@ def main():
     fe, ga = RH.import_reference()
     out = {}
     gen_curator(out)
+    gen_geometry(ga, out)
     gen_units(fe, out)
     gen_bank(ga, out)
     gen_prescan(ga, out)

@@ -327,6 +327,27 @@ def curator_images():
     return [cv2.GaussianBlur(rng.integers(0, 256, (h, w, 3), dtype=np.uint8), (0, 0), 1.0) for h, w in shapes]
 
 
+# ------------------------------------------------------------------------------------------------- main-pass geometry
+def geometry_cases():
+    """[(box xyxy float, pad_x, pad_y, W, H)] incl. boxes at / beyond the frame edges, and box pairs for IoU."""
+    rng = np.random.default_rng(404)
+    cases = []
+    for _ in range(60):
+        W, Hh = int(rng.integers(64, 4000)), int(rng.integers(64, 2200))
+        x1, y1 = float(rng.uniform(-40, W)), float(rng.uniform(-40, Hh))
+        w, h = float(rng.uniform(0.5, 600)), float(rng.uniform(0.5, 600))
+        cases.append(((x1, y1, x1 + w, y1 + h), float(rng.uniform(0, 200)), float(rng.uniform(0, 200)), W, Hh))
+    cases.append(((0.0, 0.0, 10.0, 10.0), 16.0, 16.0, 100, 100))
+    cases.append(((95.5, 95.5, 130.0, 130.0), 3.25, 0.0, 100, 100))
+    cases.append(((-50.0, -50.0, -10.0, -10.0), 1.0, 1.0, 64, 64))
+    pairs = [(tuple(float(v) for v in rng.uniform(0, 300, 4)), tuple(float(v) for v in rng.uniform(0, 300, 4))) for _ in range(40)]
+    pairs = [((min(a[0], a[2]), min(a[1], a[3]), max(a[0], a[2]), max(a[1], a[3])), (min(b[0], b[2]), min(b[1], b[3]), max(b[0], b[2]), max(b[1], b[3])))
+             for a, b in pairs]
+    pairs.append(((0.0, 0.0, 10.0, 10.0), (10.0, 10.0, 20.0, 20.0)))
+    pairs.append(((5.0, 5.0, 5.0, 5.0), (0.0, 0.0, 10.0, 10.0)))
+    return cases, pairs
+
+
 CACHE_DIR = "/tmp/pcb_reference_golden_cache"
 CACHE_CFG = dict(prescan_stride=5, prescan_max_width=512, prescan_fd_enter=0.41, prescan_weights=(0.6, 0.3, 0.1), face_model="scrfd_10g_bnkps")
 

@@ -307,3 +307,16 @@ def test_curator_identity_matches_reference():
     assert [crc(cv) for (cv, _, _, _) in lb] == [int(v) for v in G["cur_lb_crc"]]
     C.ref_feat = None
     assert C.fd_min(S.unit_vec(1)) == float(G["cur_fd_noref"][0])
+
+
+# ------------------------------------------------------------------------------------------------- main-pass geometry
+def test_main_pass_geometry_matches_reference():
+    """Processor._expand_xyxy (lock-face ROI geometry, gui_app.py:4186-4199) and Processor._iou (:3484-3493), oracle and product."""
+    from oracle import mainpass as OM
+    from person_capture_b200 import mainpass as MP
+    cases, pairs = S.geometry_cases()
+    for mod in (OM, MP):
+        got = np.array([mod.expand_xyxy(b, px, py, W, Hh) for b, px, py, W, Hh in cases], np.int64)
+        assert np.array_equal(got, G["geo_expand"]), mod.__name__
+    np.testing.assert_allclose([OM.iou_xyxy(a, b) for a, b in pairs], G["geo_iou"], rtol=0, atol=0)
+    np.testing.assert_allclose([MP.box_iou(a, b) for a, b in pairs], G["geo_iou"], rtol=0, atol=1e-15)
