@@ -44,11 +44,12 @@ def make_cfg():
                          face_quality_min=40.0)
 
 
-def make_pool(n: int, seed: int = 1002):
+def make_pool(n: int, seed: int = 1002, distractor_prob: float = 1.0):
     """`n` distinct synthetic 1080p frames + reference image.  SURVEY.md 8(d) C2: about one face per frame -- a distractor
-    identity in every frame, the target identity on top of it in two stretches (48 % of the frames)."""
+    identity in every frame, the target identity on top of it in two stretches (48 % of the frames).  distractor_prob < 1
+    (secondary measurement) leaves frames without any face: rotated probes, heavy passes and the fd9 gate then carry load."""
     from person_capture_b200 import synth
-    clip = synth.ClipSpec(1920, 1080, n, seed=seed, target=1, others=(2, 3, 4), distractor_prob=1.0)
+    clip = synth.ClipSpec(1920, 1080, n, seed=seed, target=1, others=(2, 3, 4), distractor_prob=float(distractor_prob))
     frames = np.stack([clip.frame(i) for i in range(n)])
     return frames, synth.reference_image(1, 512, seed=seed)
 
@@ -183,7 +184,7 @@ def run_reference_arm(args):
     cfg = make_cfg()
     threads = os.cpu_count() or 1
     sample = args.ref_sample
-    frames, ref_img = make_pool(min(sample, args.pool))
+    frames, ref_img = make_pool(min(sample, args.pool), distractor_prob=args.distractor_prob)
     rates = []
     for s in range(args.warmup + args.steps):
         r, _ = cpu_oracle_rate(frames, ref_img, cfg, sample, threads)
@@ -213,6 +214,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=96, help="frames of the clip the CPU oracle is timed on (cpu_baseline + parity block)")
     ap.add_argument("--ref-sample", type=int, default=48, help="frames per step of the --impl reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--distractor-prob", type=float, default=1.0,
+                    help="share of 24-frame blocks with a non-target face (default 1.0 = the headline workload; lower: frames without faces)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -232,7 +235,7 @@ def main():
     face = FaceEmbedder(f"cuda:{local}", "scrfd_10g_bnkps", conf=cfg.face_det_conf, arcface_model="arcface_r100")
     eng = face.engine
 
-    frames_np, ref_img = make_pool(args.pool)
+    frames_np, ref_img = make_pool(args.pool, distractor_prob=args.distractor_prob)
     bank = PS.build_reference_bank(face, [ref_img], cfg)
     if bank is None:
         raise RuntimeError("reference image produced no face: cannot benchmark the matching stage")
@@ -353,7 +356,8 @@ def main():
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": args.frames_per_step, "batch": args.batch,
-                   "pool_frames": args.pool, "l2_policy": "inputs larger than L2 (pool 398 MB of 1080p frames, cycled)",
+                   "pool_frames": args.pool, "distractor_prob": args.distractor_prob,
+                   "l2_policy": "inputs larger than L2 (pool 398 MB of 1080p frames, cycled)",
                    "detector_input": 512, "kept_spans": faces_seen.get("spans"), "spans_sha": digest, "faces_per_step_per_gpu": faces_seen["n"], "arcface_passes_per_step_per_gpu": faces_seen["passes"],
                    "flip_tta": "e(flip x) only for faces evaluated while a span is active (as the reference); N>1 ranks embed both variants before the all-gather",
                    "weights": "SCRFD trained on synthetic faces; ArcFace seeded random + calibrated affine (no checkpoints offline)",
@@ -368,10 +372,14 @@ def main():
                                      "note": "the roofline region: same K steps with a CUDA-event pair around every convolution launch"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(h2d),
-                # device->host per step: normalised features of every face (plain + the flip features that were computed), per-face
-                # box / quality / counts, per-batch detection counts, and the live-distance read-backs of the replay
-                "d2h_bytes_per_step": int(faces_seen["passes"] * 2048 + faces_seen["n"] * (16 + 8 + 4) + (args.frames_per_step // args.batch + 1) * 3 * 4 * args.batch
-                                          + (faces_seen.get("bank") or {}).get("distance_refreshes", 0) * faces_seen["n"] * 8)},
+                # device->host per step, from the sizes of the tensors the step reads back: per face its box / quality / count
+                # (16 + 8 + 4 B), its distance to the initial bank for the flip prediction (4 B) and the final plain + flip
+                # distances for the refine probes (8 B); per frame batch the three detection counts; per distance refresh the
+                # plain + flip similarities of the rows still ahead (upper bound: all rows); per accepted bank offer one
+                # 2 KB feature row (the features themselves stay on the device)
+                "d2h_bytes_per_step": int(faces_seen["n"] * (16 + 8 + 4 + 4 + 8) + (args.frames_per_step // args.batch + 1) * 3 * 4 * args.batch
+                                          + (faces_seen.get("bank") or {}).get("distance_refreshes", 0) * faces_seen["n"] * 8
+                                          + ((faces_seen.get("bank") or {}).get("bank_versions", 0) or 0) * 2048)},
         "roofline": {"kernel": "conv_tc2_kernel", "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": achieved / peak_tf if peak_tf else None,
                      # DRAM bytes per launch of the dominant layer shape, read from the committed ncu --set full capture
