@@ -242,7 +242,7 @@ class Engine:
         return emb, emb_flip
 
     def set_bank(self, bank: Optional[np.ndarray], token=None):
-        """Upload the reference bank.  `token` (any hashable, e.g. (id(bank_object), version)): skip the upload when the
+        """Upload the reference bank.  `token` (any hashable that is unique to the bank CONTENT, e.g. (RefBank.serial, version) -- never id(obj): addresses are reused): skip the upload when the
         bank on the device already carries it -- a 10 000-row bank is 20 MB."""
         if token is not None and token == getattr(self, "_bank_token", None):
             return
