@@ -1,9 +1,3 @@
-O=gpurun_out/r3j; mkdir -p $O
-timeout 600 python bench.py --distractor-prob 0.4 --steps 5 > $O/bench_mixed.json 2> $O/bench_mixed.err
-python - <<PY
-import json
-d=json.loads(open("$O/bench_mixed.json").read().strip().splitlines()[-1])
-print("value", round(d["value"]), "e2e", round(d["e2e"]["value"]), "frac", round(d["roofline"]["frac"],4), d["phase_ms_last_step"], d["config"]["kept_spans"], d["config"]["faces_per_step_per_gpu"], d["config"]["arcface_passes_per_step_per_gpu"], d["bank_last_step"])
-print(d["parity"]); print(d["cpu_baseline"])
-PY
-tail -3 $O/bench_mixed.err
+O=gpurun_out/r3k; mkdir -p $O
+python tools/scrfd_pass.py > $O/scrfd_plain.log 2>&1 && ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:conv_tc2 -s 3 -c 2 -o $O/scrfd_128 python tools/scrfd_pass.py > $O/ncu_scrfd_full.log 2>&1
+tail -2 $O/scrfd_plain.log; tail -3 $O/ncu_scrfd_full.log
