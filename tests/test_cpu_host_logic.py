@@ -310,3 +310,55 @@ def test_bank_identity_survives_address_reuse():
         assert (b.serial, b.version) not in seen
         seen.add((b.serial, b.version))
         del b
+
+
+@pytest.mark.parametrize("seed,trim,skip_trailing", [(0, True, True), (3, True, False), (5, False, False), (12, True, False)])
+def test_refine_from_the_face_table_equals_probing_every_frame(seed, trim, skip_trailing):
+    """_refine_edges_batched with `known` (stride 1: every probe frame is a sample of the main scan) reads the probe results
+    from the face table -- variant choice in "full" mode (upright, else 90 then 270 where the probe hit and the heavy pass found
+    a face), flip-TTA distance to the final bank -- and must return what the oracle's _refine_edges returns when it extracts
+    every probe frame again."""
+    import types
+    rng = np.random.default_rng(seed)
+    n = 200
+    target = unit(rng.normal(size=512))
+    sc = make_scenario(rng, n, target)
+    cfg = PrescanParams(prescan_stride=1, prescan_max_width=10 ** 6, prescan_min_segment_sec=0.25, prescan_pad_sec=0.25,
+                        prescan_boundary_refine_sec=0.5, prescan_trim_pad=trim, prescan_skip_trailing_refine=skip_trailing,
+                        prescan_fd_enter=0.45)
+    bank_rows = np.stack([unit(target + rng.normal(0, 0.03, 512)), unit(target + rng.normal(0, 0.05, 512))])
+    spans = [(10, 45), (70, 120), (150, n - 1)]
+
+    def frame(i):
+        if i < 0 or i >= n:
+            return None
+        a = np.zeros((1, 1, 3), np.uint8)
+        a[0, 0, 0], a[0, 0, 1] = i % 256, i // 256
+        return a
+
+    want = OP._refine_edges(list(spans), frame, 24, n, FakeFace(sc), bank_rows, None, cfg, int(round(cfg.prescan_min_segment_sec * 24)),
+                            10 ** 6, float(cfg.prescan_fd_enter))
+
+    records, P, Fl = to_records(sc)
+    idxs = PS.sample_indices(n, 1)
+    meta, _, _ = PS.encode_records(records, idxs, len(P))
+    import torch
+    table = types.SimpleNamespace(plain=torch.as_tensor(P), flip=torch.as_tensor(Fl), count=len(P), lazy=False)
+    bank = PS.RefBank(cfg, bank_rows)
+    dist_calls = []
+
+    class Dist:
+        def get(self, b):
+            dist_calls.append(b.version)
+            return NumpyDistances(P, Fl).get(b)
+
+        def invalidate(self):
+            pass
+
+    known = dict(pos={int(j): k for k, j in enumerate(idxs)}, meta=meta, table=table, dist=Dist())
+    clip = types.SimpleNamespace(total_frames=n)
+    trk = PS.SpanTracker(cfg, 24, n)
+    got = PS._refine_edges_batched(list(spans), clip, 24, FakeFace(sc), bank, None, cfg, trk, 16, known=known)
+    assert got == want
+    assert dist_calls                                  # the table was consulted; compute_superset (GPU) was never needed
+    assert want != spans or not trim                   # the case moves at least one edge when trimming is on
