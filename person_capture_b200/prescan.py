@@ -56,6 +56,69 @@ class HostClip:
         return eng.to_device(np.stack([self._get(i) for i in idxs]), stream=stream)
 
 
+class VideoFileClip:
+    """Frames decoded on the HOST by OpenCV's FFmpeg reader -- the reference's default SDR reader
+    (`cv2.VideoCapture(video_path, cv2.CAP_FFMPEG)`, gui_app.py:4667-4721; its pre-scan walks it with grab / retrieve,
+    :1417-1464).  Each batch is decoded straight into a pinned buffer and copied to HBM on the copy stream, so the
+    host-resident pre-scan (prefetch three batches ahead, ArcFace on the second context) applies unchanged.  Decode itself stays
+    on the CPU (a few ms per 1080p frame): this is the functional bridge from a file to the identity path, not a fast one -- an
+    NVDEC source is not built.  Sequential access costs one `read` per frame; any other index seeks first."""
+    host_resident = True
+
+    def __init__(self, path: str):
+        import cv2
+        self._cv2 = cv2
+        self.path = str(path)
+        self.cap = cv2.VideoCapture(self.path, cv2.CAP_FFMPEG)
+        if not self.cap.isOpened():
+            self.cap = cv2.VideoCapture(self.path)
+        if not self.cap.isOpened():
+            raise L.PcbError(f"cannot open video {self.path!r}")
+        self.total_frames = int(self.cap.get(cv2.CAP_PROP_FRAME_COUNT) or 0)
+        self.fps = float(self.cap.get(cv2.CAP_PROP_FPS) or 0.0)
+        self.width = int(self.cap.get(cv2.CAP_PROP_FRAME_WIDTH) or 0)
+        self.height = int(self.cap.get(cv2.CAP_PROP_FRAME_HEIGHT) or 0)
+        if self.total_frames <= 0 or self.width <= 0 or self.height <= 0:
+            raise L.PcbError(f"video {self.path!r} reports no frames / no size")
+        self._next = 0
+        self.decoded = 0                # frames decoded so far (sequential reads and seeks alike)
+        self.seeks = 0
+
+    def _read_into(self, i: int, out: Optional[np.ndarray]) -> np.ndarray:
+        if i < 0 or i >= self.total_frames:
+            raise IndexError(i)
+        if i != self._next:
+            self.cap.set(self._cv2.CAP_PROP_POS_FRAMES, int(i))
+            self.seeks += 1
+        ok, frame = self.cap.read() if out is None else self.cap.read(out)
+        if not ok or frame is None:
+            raise L.PcbError(f"video {self.path!r}: frame {i} of {self.total_frames} could not be decoded")
+        self._next = i + 1
+        self.decoded += 1
+        if out is not None and frame is not out:
+            np.copyto(out, frame)
+            return out
+        return frame
+
+    def host(self, i: int) -> np.ndarray:
+        return self._read_into(int(i), None)
+
+    def device_batch(self, eng, idxs: Sequence[int], stream=None) -> torch.Tensor:
+        # a fresh pinned tensor per batch: torch's host allocator recycles the block only after the copy that reads it has
+        # completed on its stream, so batches prefetched ahead never overwrite one another
+        buf = torch.empty((len(idxs), self.height, self.width, 3), dtype=torch.uint8, pin_memory=True)
+        view = buf.numpy()
+        for k, i in enumerate(idxs):
+            self._read_into(int(i), view[k])
+        with torch.cuda.stream(stream if stream is not None else eng.stream):
+            return buf.to(eng.tdev, non_blocking=True)
+
+    def close(self):
+        if self.cap is not None:
+            self.cap.release()
+            self.cap = None
+
+
 class DeviceClip:
     """Frames already resident in HBM as a uint8 tensor [N,H,W,3] (north_star: pre-decoded in HBM)."""
 

@@ -362,3 +362,43 @@ def test_refine_from_the_face_table_equals_probing_every_frame(seed, trim, skip_
     assert got == want
     assert dist_calls                                  # the table was consulted; compute_superset (GPU) was never needed
     assert want != spans or not trim                   # the case moves at least one edge when trimming is on
+
+
+def test_video_file_clip_decodes_what_cv2_decodes(tmp_path):
+    """VideoFileClip (CPU decode through OpenCV's FFmpeg reader, the reference's default SDR reader): sequential reads, reads
+    into a caller's buffer and random access all return the frames a plain cv2.VideoCapture walk returns."""
+    import cv2
+    path = str(tmp_path / "clip.avi")
+    rng = np.random.default_rng(5)
+    w, h, n = 96, 64, 24
+    vw = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"MJPG"), 24.0, (w, h))
+    if not vw.isOpened():
+        pytest.skip("no MJPG writer in this OpenCV build")
+    for i in range(n):
+        f = cv2.GaussianBlur(rng.integers(0, 256, (h, w, 3), dtype=np.uint8), (0, 0), 2.0)
+        cv2.putText(f, str(i), (5, 40), cv2.FONT_HERSHEY_SIMPLEX, 1.0, (255, 255, 255), 2)
+        vw.write(f)
+    vw.release()
+    cap = cv2.VideoCapture(path)
+    want = []
+    while True:
+        ok, f = cap.read()
+        if not ok:
+            break
+        want.append(f)
+    cap.release()
+    assert len(want) == n
+    clip = PS.VideoFileClip(path)
+    assert clip.total_frames == n and (clip.height, clip.width) == (h, w) and clip.host_resident and abs(clip.fps - 24.0) < 1e-6
+    for i in range(n):
+        assert np.array_equal(clip.host(i), want[i]), i
+    assert clip.seeks == 0 and clip.decoded == n
+    buf = np.zeros((h, w, 3), np.uint8)
+    for i in (17, 3, 4, 23, 0):                       # random access (MJPG is intra-only: seeks are exact), decode into a buffer
+        assert clip._read_into(i, buf) is buf and np.array_equal(buf, want[i]), i
+    assert clip.seeks == 4                             # 3 -> 4 was sequential
+    with pytest.raises(IndexError):
+        clip.host(n)
+    clip.close()
+    with pytest.raises(PS.L.PcbError):
+        PS.VideoFileClip(str(tmp_path / "missing.mp4"))

@@ -299,6 +299,40 @@ def test_refine_reuses_main_scan_records_without_changing_spans(engine_25g_r50, 
     assert out["1"][2] < out["0"][2]              # fewer faces went through detection + embedding
 
 
+def test_prescan_from_a_video_file_equals_prescan_from_its_decoded_frames(engine_25g_r50, tmp_path):
+    """VideoFileClip (CPU decode via OpenCV's FFmpeg reader into pinned batches, H2D on the copy stream, three batches ahead)
+    feeds the host-resident pre-scan: spans, bank and per-sample log equal the run over the same decoded frames held in memory."""
+    from person_capture_b200 import prescan as PS
+    from person_capture_b200.face_embedder import FaceEmbedder
+    cfg, clip, ref_img = _make_case(1003, 640, 360, 144, 2, prescan_add_cooldown_samples=2)
+    path = str(tmp_path / "clip.avi")
+    vw = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"MJPG"), 24.0, (640, 360))
+    if not vw.isOpened():
+        pytest.skip("no MJPG writer in this OpenCV build")
+    for i in range(clip.n_frames):
+        vw.write(clip.frame(i))
+    vw.release()
+    cap = cv2.VideoCapture(path)
+    frames = []
+    while True:
+        ok, f = cap.read()
+        if not ok:
+            break
+        frames.append(f)
+    cap.release()
+    assert len(frames) == clip.n_frames
+    face = FaceEmbedder("cuda:0", "scrfd_2.5g_bnkps", conf=cfg.face_det_conf, engine=engine_25g_r50, arcface_model="arcface_r50")
+    bank = PS.build_reference_bank(face, [ref_img], cfg)
+    l1, l2 = [], []
+    s1, b1 = PS.prescan_batched(PS.HostClip(lambda i: frames[i], len(frames)), 24, face, bank, cfg, batch=16, log=l1)
+    vclip = PS.VideoFileClip(path)
+    s2, b2 = PS.prescan_batched(vclip, 24, face, bank, cfg, batch=16, log=l2)
+    vclip.close()
+    assert s1 == s2 and len(s1) >= 1
+    assert np.array_equal(np.asarray(b1), np.asarray(b2))
+    assert [(r["idx"], r["skip"], r["nfaces"], r["best"]) for r in l1] == [(r["idx"], r["skip"], r["nfaces"], r["best"]) for r in l2]
+
+
 def test_prescan_cache_roundtrip_with_gpu_result(engine_25g_r50, tmp_path):
     from oracle import prescan as OP
     from person_capture_b200 import prescan as PS
