@@ -1542,8 +1542,18 @@ def prescan_batched(clip, fps: int, face: FaceEmbedder, ref_feat, cfg, batch: in
     eng = face.engine
     import time as _time
     tmark = [("start", _time.perf_counter())]
+    # NVTX ranges per phase (PCB_NVTX=1): what a profiler's timeline shows as superset / predicted_flips / gather / replay / refine
+    _PHASES = ("superset", "predicted_flips", "gather", "replay", "refine")
+    nvtx = torch.cuda.nvtx if (os.environ.get("PCB_NVTX", "0") == "1" and torch.cuda.is_available()) else None
+    if nvtx is not None:
+        nvtx.range_push("prescan:" + _PHASES[0])
 
     def mark(name):
+        if nvtx is not None:
+            nvtx.range_pop()
+            k = _PHASES.index(name) + 1
+            if k < len(_PHASES):
+                nvtx.range_push("prescan:" + _PHASES[k])
         if stats is not None:
             eng.sync()
             tmark.append((name, _time.perf_counter()))
