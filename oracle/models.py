@@ -9,8 +9,9 @@ here, so this file *defines* the architectures from the upstream InsightFace con
 both sides (oracle and CUDA path) load the same exported weight file.
 
 parity unpinned for the graphs: the reference ships no tests or golden vectors for them
-(SURVEY.md F2); torch-CPU fp32 stands in for ONNX Runtime CPU (not installed, F4; the `onnx` package is absent too, so
-the graphs cannot be exported and cross-checked through cv2.dnn here).
+(SURVEY.md F2); torch-CPU fp32 stands in for ONNX Runtime CPU (not installed, F4).  The graphs ARE exported to ONNX
+(oracle/onnx_export.py writes the protobuf by hand -- the `onnx` package is absent too) and executed by an independent engine,
+cv2.dnn: tests/test_cpu_onnx_export.py holds these torch executors to it for all four networks.
 
 Weight file format ("folded", one .npz per model): every conv `name` has
   name.w      float16 [Cout, Cin, kh, kw]   (values exactly representable in fp16)

@@ -237,6 +237,64 @@ def gen_prescan_full(fe, ga, out):
     print(f"prescan_full: {len(rec.calls)} SCRFD passes, spans {spans}, bank rows {len(bank)}")
 
 
+class DnnScrfdNet:
+    """SCRFDOracle's `net.run(blob)` on cv2.dnn executing the ONNX export of the graph (one fixed-size file per S)."""
+
+    def __init__(self, name, workdir):
+        from person_capture_b200 import weights
+        self.name, self.params, self.dir, self.nets = name, weights.load_params(name), workdir, {}
+
+    def run(self, blob):
+        from oracle import onnx_export as X
+        S = int(blob.shape[2])
+        if S not in self.nets:
+            path = os.path.join(self.dir, f"{self.name}_{S}.onnx")
+            names = X.export_scrfd(self.name, self.params, S, path, layout="insightface")
+            self.nets[S] = (cv2.dnn.readNetFromONNX(path), names)
+        net, names = self.nets[S]
+        net.setInput(np.ascontiguousarray(blob, np.float32))
+        return [np.asarray(o).copy() for o in net.forward(names)]
+
+
+def gen_reference_onnx(fe, out):
+    """The unmodified reference FaceEmbedder whose two sessions execute the EXPORTED ONNX GRAPHS through cv2.dnn (an engine
+    independent of torch and of our oracle's executors): the offline stand-in for "the reference's ONNX Runtime CPU run of the
+    same graphs".  The GPU tests hold the CUDA path to these vectors directly -- no oracle in between."""
+    from oracle import onnx_export as X
+    from person_capture_b200 import weights
+    with tempfile.TemporaryDirectory() as td:
+        arc_path = os.path.join(td, "arc.onnx")
+        arc_out = X.export_iresnet(S.RO_ARC, weights.load_params(S.RO_ARC), arc_path)
+        arc_net = cv2.dnn.readNetFromONNX(arc_path)
+
+        def arc_fn(x):
+            rows = []
+            for k in range(x.shape[0]):
+                arc_net.setInput(np.ascontiguousarray(x[k:k + 1], np.float32))
+                rows.append(np.asarray(arc_net.forward(arc_out)).reshape(512).copy())
+            return np.stack(rows).astype(np.float32)
+
+        R = RH.make_reference_embedder(fe, SCRFDOracle(DnnScrfdNet(S.RO_SCRFD, td)), arc_fn, conf=0.5)
+        R.configure_rotation_strategy(adaptive=False)
+        R.set_prescan_fast(True, mode="rr")
+        R._prescan_probe_imgsz = 512
+        counts, bbox, quality, feat = [], [], [], []
+        for k, key in enumerate(S.RO_FRAMES):
+            R.set_prescan_hint(escalate=bool(k % 2))
+            faces = R.extract(S.ro_frame(key))
+            counts.append(len(faces))
+            for f in faces:
+                bbox.append(np.asarray(f["bbox"], np.int32))
+                quality.append(float(f["quality"]))
+                feat.append(np.asarray(f["feat"], np.float32))
+        out["ro_counts"] = np.array(counts, np.int32)
+        out["ro_bbox"] = np.array(bbox, np.int32).reshape(-1, 4)
+        out["ro_quality"] = np.array(quality, np.float64)
+        out["ro_feat"] = np.array(feat, np.float32).reshape(-1, 512)
+        out["ro_state"] = np.array([R._prescan_rr, R._no_face_streak, R._frame_idx], np.int64)
+        print(f"reference x onnx: {counts} faces per frame")
+
+
 def gen_cache(ga, out):
     import shutil
     video, ref = S.cache_files()
@@ -322,6 +380,7 @@ def main():
     gen_prescan(ga, out)
     gen_cache(ga, out)
     gen_prescan_full(fe, ga, out)
+    gen_reference_onnx(fe, out)
     gen_extract(fe, out)
     np.savez_compressed(OUT, **out)
     print("wrote", OUT, os.path.getsize(OUT), "bytes,", len(out), "arrays")

@@ -348,6 +348,16 @@ def geometry_cases():
     return cases, pairs
 
 
+# ------------------------------------------------------------------------------------------------- reference x ONNX graphs
+RO_SCRFD, RO_ARC = "scrfd_2.5g_bnkps", "arcface_r50"
+RO_FRAMES = [(416, 234, 77, i) for i in (0, 9, 18, 27, 36, 45, 54, 63)]          # (W, H, clip seed, frame): test_extract_matches_oracle's clip
+
+
+def ro_frame(key):
+    W, Hh, seed, i = key
+    return synth.ClipSpec(W, Hh, 120, seed=seed).frame(i)
+
+
 CACHE_DIR = "/tmp/pcb_reference_golden_cache"
 CACHE_CFG = dict(prescan_stride=5, prescan_max_width=512, prescan_fd_enter=0.41, prescan_weights=(0.6, 0.3, 0.1), face_model="scrfd_10g_bnkps")
 

@@ -320,3 +320,26 @@ def test_main_pass_geometry_matches_reference():
         assert np.array_equal(got, G["geo_expand"]), mod.__name__
     np.testing.assert_allclose([OM.iou_xyxy(a, b) for a, b in pairs], G["geo_iou"], rtol=0, atol=0)
     np.testing.assert_allclose([MP.box_iou(a, b) for a, b in pairs], G["geo_iou"], rtol=0, atol=1e-15)
+
+
+# ------------------------------------------------------------------------------------------------- reference x ONNX graphs
+def test_oracle_matches_reference_running_the_onnx_graphs():
+    """`ro_*`: the unmodified reference FaceEmbedder with both sessions executing the EXPORTED ONNX graphs through cv2.dnn
+    (make_reference_golden.gen_reference_onnx).  The oracle (torch-CPU executors of the same weights) must see the same faces:
+    identical boxes, counters and rotation state; quality and features to the rounding two inference engines differ by."""
+    O = H.oracle_embedder(S.RO_SCRFD, S.RO_ARC, conf=0.5)
+    O.configure_rotation_strategy(adaptive=False)
+    O.set_prescan_fast(True, mode="rr")
+    O._prescan_probe_imgsz = 512
+    off = np.concatenate([[0], np.cumsum(G["ro_counts"])]).astype(int)
+    for k, key in enumerate(S.RO_FRAMES):
+        O.set_prescan_hint(escalate=bool(k % 2))
+        faces = O.extract(S.ro_frame(key))
+        a, b = off[k], off[k + 1]
+        assert len(faces) == b - a, k
+        for j, f in enumerate(faces):
+            assert np.array_equal(np.asarray(f["bbox"], np.int32), G["ro_bbox"][a + j]), (k, j)
+            assert abs(f["quality"] - G["ro_quality"][a + j]) <= 1e-3 * max(1.0, G["ro_quality"][a + j]), (k, j)
+            assert H.cos(f["feat"], G["ro_feat"][a + j]) >= 0.9999, (k, j)
+    assert (O._prescan_rr, O._no_face_streak, O._frame_idx) == tuple(int(v) for v in G["ro_state"])
+    assert G["ro_counts"].sum() >= 8 and (G["ro_counts"] == 0).any()

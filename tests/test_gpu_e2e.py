@@ -86,6 +86,44 @@ def test_extract_matches_oracle(request, scrfd, fix, W, Hh, fast):
     assert face._prescan_rr == ora._prescan_rr and face._no_face_streak == ora._no_face_streak
 
 
+def test_extract_matches_the_reference_running_the_onnx_graphs(engine_25g_r50):
+    """No oracle in between: the CUDA path against vectors produced by the UNMODIFIED reference FaceEmbedder whose two sessions
+    executed the exported ONNX graphs of the same weights through cv2.dnn (tests/golden/make_reference_golden.py,
+    gen_reference_onnx; fast pre-scan mode, flip-TTA on every other frame, frames with and without faces).  Same faces and
+    rotation state; boxes identical (an edge may move by one pixel across an int() truncation on a fp16-vs-fp32 difference);
+    embeddings to cosine >= 0.999 and quality to 5 % wherever the box is identical."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import ref_golden_script as S
+    from person_capture_b200.face_embedder import FaceEmbedder
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_golden.npz"), allow_pickle=False)
+    face = FaceEmbedder("cuda:0", S.RO_SCRFD, conf=0.5, engine=engine_25g_r50, arcface_model=S.RO_ARC)
+    face.configure_rotation_strategy(adaptive=False)
+    face.set_prescan_fast(True, mode="rr")
+    face._prescan_probe_imgsz = 512
+    off = np.concatenate([[0], np.cumsum(G["ro_counts"])]).astype(int)
+    faces_n = exact = tight = 0
+    for k, key in enumerate(S.RO_FRAMES):
+        face.set_prescan_hint(escalate=bool(k % 2))
+        got = face.extract(S.ro_frame(key))
+        a, b = off[k], off[k + 1]
+        assert len(got) == b - a, (k, len(got), b - a)
+        for j, g in enumerate(got):
+            faces_n += 1
+            d = np.abs(np.asarray(g["bbox"], np.int64) - G["ro_bbox"][a + j].astype(np.int64)).max()
+            assert d <= 1, (k, j, g["bbox"], G["ro_bbox"][a + j])
+            c = H.cos(g["feat"], G["ro_feat"][a + j])
+            dq = abs(g["quality"] - G["ro_quality"][a + j]) / max(1.0, G["ro_quality"][a + j])
+            assert c >= 0.93 and dq <= 0.25, (k, j, c, dq)
+            if d == 0:
+                exact += 1
+                tight += int(c >= 0.999 and dq <= 0.05)
+    assert faces_n == int(G["ro_counts"].sum()) >= 8
+    assert exact >= int(0.8 * faces_n) and tight >= int(0.85 * exact), (faces_n, exact, tight)
+    assert (face._prescan_rr, face._no_face_streak, face._frame_idx) == tuple(int(v) for v in G["ro_state"])
+
+
 def test_extract_rotated_and_empty_frames(engine_25g_r50):
     """Frames with no upright face: rotation probes + heavy pass (fast pre-scan) and the scale-TTA /
     pad-probe chain (normal mode) must take the same branches as the oracle."""
