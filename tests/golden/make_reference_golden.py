@@ -294,6 +294,67 @@ def gen_reference_onnx(fe, out):
         out["ro_state"] = np.array([R._prescan_rr, R._no_face_streak, R._frame_idx], np.int64)
         print(f"reference x onnx: {counts} faces per frame")
 
+        # the bench's models on the bench's frame shape: SCRFD-10G + iResNet-100, 960x540
+        arc100_path = os.path.join(td, "arc100.onnx")
+        arc100_out = X.export_iresnet(S.RH_ARC, weights.load_params(S.RH_ARC), arc100_path)
+        arc100 = cv2.dnn.readNetFromONNX(arc100_path)
+
+        def arc100_fn(x):
+            rows = []
+            for k in range(x.shape[0]):
+                arc100.setInput(np.ascontiguousarray(x[k:k + 1], np.float32))
+                rows.append(np.asarray(arc100.forward(arc100_out)).reshape(512).copy())
+            return np.stack(rows).astype(np.float32)
+
+        RH_ = RH.make_reference_embedder(fe, SCRFDOracle(DnnScrfdNet(S.RH_SCRFD, td)), arc100_fn, conf=0.5)
+        RH_.configure_rotation_strategy(adaptive=False)
+        RH_.set_prescan_fast(True, mode="rr")
+        RH_._prescan_probe_imgsz = 512
+        counts, bbox, quality, feat = [], [], [], []
+        for k, i in enumerate(S.RH_FRAME_IDS):
+            RH_.set_prescan_hint(escalate=bool(k % 2))
+            faces = RH_.extract(S.rh_frame(i))
+            counts.append(len(faces))
+            for f in faces:
+                bbox.append(np.asarray(f["bbox"], np.int32))
+                quality.append(float(f["quality"]))
+                feat.append(np.asarray(f["feat"], np.float32))
+        out["rh_counts"] = np.array(counts, np.int32)
+        out["rh_bbox"] = np.array(bbox, np.int32).reshape(-1, 4)
+        out["rh_quality"] = np.array(quality, np.float64)
+        out["rh_feat"] = np.array(feat, np.float32).reshape(-1, 512)
+        out["rh_state"] = np.array([RH_._prescan_rr, RH_._no_face_streak, RH_._frame_idx], np.int64)
+        print(f"reference x onnx (10G + R100, 960x540): {counts} faces per frame")
+
+        # and the whole pre-scan: Processor._prescan x FaceEmbedder x ONNX graphs, reference bank built the reference's way
+        # (gui_app.py:4517-4556: each reference image and its mirror, best face, streaming update)
+        import importlib
+        ga = importlib.import_module("person_capture.gui_app")
+        R2 = RH.make_reference_embedder(fe, SCRFDOracle(DnnScrfdNet(S.RO_SCRFD, td)), arc_fn, conf=0.5)
+        frames, ref_img = S.rp_clip_frames()
+        cfg = make_cfg(ga, S.RP_CFG)
+        R2.conf = float(cfg.face_det_conf)
+        P = make_processor(ga, cfg, S.RP_FPS, S.RP_N)
+        bank_list, ref = [], None
+        for aug in (ref_img, cv2.flip(ref_img, 1)):
+            bf = fe.FaceEmbedder.best_face(R2.extract(aug))
+            if bf and bf.get("feat") is not None:
+                ref, _, _ = P._stream_ref_bank_update(bank_list, ref, bf["feat"], float(bf.get("quality", 0.0)), cfg)
+        n_ext = [0]
+        inner = R2.extract
+
+        def counted(img, **kw):
+            n_ext[0] += 1
+            return inner(img, **kw)
+
+        R2.extract = counted
+        spans, bank = P._prescan(S.FrameCap(frames), S.RP_FPS, S.RP_N, R2, ref, cfg)
+        out["rp_ref"] = np.asarray(ref, np.float32).reshape(-1, 512)
+        out["rp_spans"] = np.asarray(spans, np.int64).reshape(-1, 2)
+        out["rp_bank"] = np.asarray(bank, np.float32).reshape(-1, 512)
+        out["rp_extracts"] = np.array([n_ext[0]], np.int64)
+        print(f"reference x onnx pre-scan: {n_ext[0]} extract calls, spans {spans}, bank {len(ref)} -> {len(bank)} rows")
+
 
 def gen_cache(ga, out):
     import shutil

@@ -358,6 +358,28 @@ def ro_frame(key):
     return synth.ClipSpec(W, Hh, 120, seed=seed).frame(i)
 
 
+# the bench's models on the bench's frame shape (tests/test_gpu_headline.py::test_extract_960x540_r100_matches_oracle)
+RH_SCRFD, RH_ARC = "scrfd_10g_bnkps", "arcface_r100"
+RH_FRAME_IDS = list(range(4, 120, 11))
+
+
+def rh_frame(i):
+    clip = _CLIPS.setdefault(("rh", 1002), synth.ClipSpec(1920, 1080, 120, seed=1002, distractor_prob=1.0))
+    return cv2.resize(clip.frame(i), (960, 540), interpolation=cv2.INTER_AREA)
+
+
+# the pre-scan of tests/test_gpu_e2e.py::test_prescan_spans_match_oracle (seed 1006, stride 3), run by the reference on ONNX graphs
+RP_CFG = dict(face_model="scrfd_2.5g_bnkps", prescan_stride=3, prescan_max_width=416, prescan_fd_enter=0.62, prescan_fd_exit=0.72,
+              prescan_fd_add=0.50, face_quality_min=40.0, prescan_min_segment_sec=0.5, prescan_pad_sec=0.25, prescan_bridge_gap_sec=0.25,
+              prescan_exit_cooldown_sec=0.25, prescan_boundary_refine_sec=0.5, prescan_refine_budget_sec=0.0)
+RP_SEED, RP_N, RP_FPS = 1006, 144, 24
+
+
+def rp_clip_frames():
+    clip = synth.ClipSpec(640, 360, RP_N, seed=RP_SEED)
+    return [clip.frame(i) for i in range(RP_N)], synth.reference_image(1, 512, seed=RP_SEED)
+
+
 CACHE_DIR = "/tmp/pcb_reference_golden_cache"
 CACHE_CFG = dict(prescan_stride=5, prescan_max_width=512, prescan_fd_enter=0.41, prescan_weights=(0.6, 0.3, 0.1), face_model="scrfd_10g_bnkps")
 

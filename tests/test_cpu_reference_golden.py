@@ -343,3 +343,38 @@ def test_oracle_matches_reference_running_the_onnx_graphs():
             assert H.cos(f["feat"], G["ro_feat"][a + j]) >= 0.9999, (k, j)
     assert (O._prescan_rr, O._no_face_streak, O._frame_idx) == tuple(int(v) for v in G["ro_state"])
     assert G["ro_counts"].sum() >= 8 and (G["ro_counts"] == 0).any()
+
+
+def test_oracle_prescan_matches_reference_prescan_on_the_onnx_graphs():
+    """`rp_*`: Processor._prescan x FaceEmbedder (unmodified) x the exported ONNX graphs through cv2.dnn over the 144-frame clip of
+    tests/test_gpu_e2e.py::test_prescan_spans_match_oracle.  The oracle (torch executors) builds the same reference bank and keeps
+    the same spans and bank."""
+    frames, ref_img = S.rp_clip_frames()
+    cfg = _cfg(S.RP_CFG)
+    ora = H.oracle_embedder(S.RO_SCRFD, S.RO_ARC, conf=cfg.face_det_conf)
+    bank0 = OP.build_reference_bank(ora, [ref_img], cfg)
+    assert bank0.shape == G["rp_ref"].shape
+    for a, b in zip(bank0, G["rp_ref"]):
+        assert H.cos(a, b) >= 0.9999
+    n_ext = [0]
+    inner = ora.extract
+
+    def counted(img, **kw):
+        n_ext[0] += 1
+        return inner(img, **kw)
+
+    ora.extract = counted
+    spans, bank = OP.prescan(lambda i: frames[i] if 0 <= i < len(frames) else None, S.RP_FPS, S.RP_N, ora, bank0, cfg)
+    assert [tuple(int(v) for v in sp) for sp in spans] == [tuple(int(v) for v in r) for r in G["rp_spans"]] and len(spans) >= 2
+    assert n_ext[0] == int(G["rp_extracts"][0])
+    assert np.asarray(bank).shape == G["rp_bank"].shape and len(G["rp_bank"]) > len(G["rp_ref"])
+    for a, b in zip(np.asarray(bank), G["rp_bank"]):
+        assert H.cos(a, b) >= 0.9999
+
+
+def test_reference_onnx_vectors_of_the_headline_models_are_present():
+    """`rh_*` (SCRFD-10G + iResNet-100 on 960x540 frames, the bench configuration) are consumed by the GPU test
+    tests/test_gpu_headline.py::test_extract_960x540_r100_matches_the_reference_running_the_onnx_graphs; here: shape sanity."""
+    assert G["rh_counts"].sum() == len(G["rh_bbox"]) == len(G["rh_quality"]) == len(G["rh_feat"]) >= 10
+    assert np.allclose(np.linalg.norm(G["rh_feat"], axis=1), 1.0, atol=1e-5)
+    assert len(G["rh_counts"]) == len(S.RH_FRAME_IDS)

@@ -124,6 +124,37 @@ def test_extract_matches_the_reference_running_the_onnx_graphs(engine_25g_r50):
     assert (face._prescan_rr, face._no_face_streak, face._frame_idx) == tuple(int(v) for v in G["ro_state"])
 
 
+@pytest.mark.parametrize("driver", ["sequential", "batched"])
+def test_prescan_matches_the_reference_prescan_on_the_onnx_graphs(engine_25g_r50, driver):
+    """north_star's "bit-identical kept spans versus the ONNX Runtime CPU reference", as far as it can be stated offline: the
+    UNMODIFIED Processor._prescan + FaceEmbedder ran the exported ONNX graphs (cv2.dnn as the executor) over a 144-frame clip
+    (tests/golden/make_reference_golden.py, `rp_*`); both GPU drivers must build the same reference bank, keep the same spans
+    and grow the bank by the same rows."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import ref_golden_script as S
+    from person_capture_b200 import prescan as PS
+    from person_capture_b200.face_embedder import FaceEmbedder
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_golden.npz"), allow_pickle=False)
+    frames, ref_img = S.rp_clip_frames()
+    cfg = PrescanParams(**S.RP_CFG)
+    face = FaceEmbedder("cuda:0", S.RO_SCRFD, conf=cfg.face_det_conf, engine=engine_25g_r50, arcface_model=S.RO_ARC)
+    bank0 = PS.build_reference_bank(face, [ref_img], cfg)
+    assert bank0 is not None and bank0.shape == G["rp_ref"].shape
+    for a, b in zip(bank0, G["rp_ref"]):
+        assert H.cos(a, b) >= 0.999
+    src = PS.HostClip(lambda i: frames[i], len(frames))
+    if driver == "sequential":
+        spans, bank = PS.prescan_sequential(src, S.RP_FPS, face, bank0, cfg)
+    else:
+        spans, bank = PS.prescan_batched(src, S.RP_FPS, face, bank0, cfg, batch=16)
+    assert [tuple(int(v) for v in sp) for sp in spans] == [tuple(int(v) for v in r) for r in G["rp_spans"]]
+    assert np.asarray(bank).shape == G["rp_bank"].shape
+    for a, b in zip(np.asarray(bank), G["rp_bank"]):
+        assert H.cos(a, b) >= 0.999
+
+
 def test_extract_rotated_and_empty_frames(engine_25g_r50):
     """Frames with no upright face: rotation probes + heavy pass (fast pre-scan) and the scale-TTA /
     pad-probe chain (normal mode) must take the same branches as the oracle."""

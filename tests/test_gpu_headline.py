@@ -199,6 +199,45 @@ def test_extract_960x540_r100_matches_oracle(engine_10g_r100):
     assert face._prescan_rr == ora._prescan_rr and face._no_face_streak == ora._no_face_streak
 
 
+def test_extract_960x540_r100_matches_the_reference_running_the_onnx_graphs(engine_10g_r100):
+    """The bench's models on the bench's frame shape against the UNMODIFIED reference FaceEmbedder executing the exported ONNX
+    graphs (SCRFD-10G, iResNet-100) through cv2.dnn -- vectors `rh_*` of tests/golden/reference_golden.npz, no oracle in
+    between.  Same faces and rotation state, boxes within one pixel, cosine >= 0.999 / quality within 5 % where the box is identical."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import ref_golden_script as S
+    from person_capture_b200.face_embedder import FaceEmbedder
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_golden.npz"), allow_pickle=False)
+    face = FaceEmbedder("cuda:0", S.RH_SCRFD, conf=0.5, engine=engine_10g_r100)
+    face.configure_rotation_strategy(adaptive=False)
+    face.set_prescan_fast(True, mode="rr")
+    face._prescan_probe_imgsz = 512
+    off = np.concatenate([[0], np.cumsum(G["rh_counts"])]).astype(int)
+    faces_n = exact = tight = 0
+    worst = 1.0
+    for k, i in enumerate(S.RH_FRAME_IDS):
+        face.set_prescan_hint(escalate=bool(k % 2))
+        got = face.extract(S.rh_frame(i))
+        a, b = off[k], off[k + 1]
+        assert len(got) == b - a, (i, len(got), b - a)
+        for j, g in enumerate(got):
+            faces_n += 1
+            d = np.abs(np.asarray(g["bbox"], np.int64) - G["rh_bbox"][a + j].astype(np.int64)).max()
+            assert d <= 1, (i, j, g["bbox"], G["rh_bbox"][a + j])
+            c = H.cos(g["feat"], G["rh_feat"][a + j])
+            dq = abs(g["quality"] - G["rh_quality"][a + j]) / max(1.0, G["rh_quality"][a + j])
+            assert c >= 0.93 and dq <= 0.25, (i, j, c, dq)
+            if d == 0:
+                exact += 1
+                tight += int(c >= 0.999 and dq <= 0.05)
+                worst = min(worst, c)
+    _note("extract_960x540_r100_vs_reference_onnx", dict(faces=faces_n, exact_boxes=exact, tight=tight, worst_cos=worst))
+    assert faces_n == int(G["rh_counts"].sum()) >= 10
+    assert exact >= int(0.8 * faces_n) and tight >= int(0.85 * exact), (faces_n, exact, tight)
+    assert (face._prescan_rr, face._no_face_streak, face._frame_idx) == tuple(int(v) for v in G["rh_state"])
+
+
 # ------------------------------------------------------------------------------------------- config 2: pre-scan, 1080p clip
 PRESCAN_SEED, PRESCAN_STRIDE, PRESCAN_FRAMES = 2001, 2, 72     # chosen with the CPU oracle: no sample within the band (asserted)
 
