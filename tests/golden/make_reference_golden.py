@@ -355,6 +355,23 @@ def gen_reference_onnx(fe, out):
         out["rp_extracts"] = np.array([n_ext[0]], np.int64)
         print(f"reference x onnx pre-scan: {n_ext[0]} extract calls, spans {spans}, bank {len(ref)} -> {len(bank)} rows")
 
+        # the same with the bench's models on a 1080p clip (pre-scan downscale to 960 wide inside the reference's loop)
+        R3 = RH.make_reference_embedder(fe, SCRFDOracle(DnnScrfdNet(S.RH_SCRFD, td)), arc100_fn, conf=0.5)
+        frames, ref_img = S.rq_clip_frames()
+        cfg = make_cfg(ga, S.RQ_CFG)
+        R3.conf = float(cfg.face_det_conf)
+        P = make_processor(ga, cfg, S.RQ_FPS, S.RQ_N)
+        bank_list, ref = [], None
+        for aug in (ref_img, cv2.flip(ref_img, 1)):
+            bf = fe.FaceEmbedder.best_face(R3.extract(aug))
+            if bf and bf.get("feat") is not None:
+                ref, _, _ = P._stream_ref_bank_update(bank_list, ref, bf["feat"], float(bf.get("quality", 0.0)), cfg)
+        spans, bank = P._prescan(S.FrameCap(frames), S.RQ_FPS, S.RQ_N, R3, ref, cfg)
+        out["rq_ref"] = np.asarray(ref, np.float32).reshape(-1, 512)
+        out["rq_spans"] = np.asarray(spans, np.int64).reshape(-1, 2)
+        out["rq_bank"] = np.asarray(bank, np.float32).reshape(-1, 512)
+        print(f"reference x onnx pre-scan (10G + R100, 1080p): spans {spans}, bank {len(ref)} -> {len(bank)} rows")
+
 
 def gen_cache(ga, out):
     import shutil

@@ -380,6 +380,18 @@ def rp_clip_frames():
     return [clip.frame(i) for i in range(RP_N)], synth.reference_image(1, 512, seed=RP_SEED)
 
 
+# the headline pre-scan of tests/test_gpu_headline.py (SCRFD-10G + iResNet-100, 1080p -> 960 wide, stride 2)
+RQ_CFG = dict(face_model="scrfd_10g_bnkps", prescan_stride=2, prescan_max_width=960, prescan_fd_enter=0.62, prescan_fd_exit=0.72,
+              prescan_fd_add=0.50, face_quality_min=40.0, prescan_min_segment_sec=0.5, prescan_pad_sec=0.25, prescan_bridge_gap_sec=0.25,
+              prescan_exit_cooldown_sec=0.25, prescan_boundary_refine_sec=0.5, prescan_refine_budget_sec=0.0)
+RQ_SEED, RQ_N, RQ_FPS = 2001, 72, 24
+
+
+def rq_clip_frames():
+    clip = synth.ClipSpec(1920, 1080, RQ_N, seed=RQ_SEED)
+    return [clip.frame(i) for i in range(RQ_N)], synth.reference_image(1, 512, seed=RQ_SEED)
+
+
 CACHE_DIR = "/tmp/pcb_reference_golden_cache"
 CACHE_CFG = dict(prescan_stride=5, prescan_max_width=512, prescan_fd_enter=0.41, prescan_weights=(0.6, 0.3, 0.1), face_model="scrfd_10g_bnkps")
 

@@ -378,3 +378,11 @@ def test_reference_onnx_vectors_of_the_headline_models_are_present():
     assert G["rh_counts"].sum() == len(G["rh_bbox"]) == len(G["rh_quality"]) == len(G["rh_feat"]) >= 10
     assert np.allclose(np.linalg.norm(G["rh_feat"], axis=1), 1.0, atol=1e-5)
     assert len(G["rh_counts"]) == len(S.RH_FRAME_IDS)
+
+
+def test_reference_onnx_prescan_vectors_of_the_headline_models_are_present():
+    """`rq_*` (the unmodified _prescan x FaceEmbedder x ONNX graphs with SCRFD-10G + iResNet-100 over a 1080p clip) are consumed
+    by tests/test_gpu_headline.py::test_prescan_1080p_r100_matches_the_reference_prescan_on_the_onnx_graphs; here: shape sanity."""
+    assert G["rq_spans"].shape[1] == 2 and len(G["rq_spans"]) >= 1 and (G["rq_spans"][:, 1] >= G["rq_spans"][:, 0]).all()
+    assert len(G["rq_bank"]) > len(G["rq_ref"]) >= 1
+    assert np.allclose(np.linalg.norm(G["rq_bank"], axis=1), 1.0, atol=1e-5)

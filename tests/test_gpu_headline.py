@@ -295,6 +295,37 @@ def test_prescan_1080p_r100_spans_match_oracle(engine_10g_r100):
     assert len(ospans) >= 1 and np.asarray(obank2).shape[0] > np.asarray(obank).shape[0]     # spans were built and the bank grew
 
 
+def test_prescan_1080p_r100_matches_the_reference_prescan_on_the_onnx_graphs(engine_10g_r100):
+    """The bench configuration against the reference itself: the UNMODIFIED Processor._prescan + FaceEmbedder executed the exported
+    ONNX graphs (SCRFD-10G, iResNet-100; cv2.dnn as the executor) over the 72-frame 1080p clip of the test above (vectors `rq_*`
+    of tests/golden/reference_golden.npz).  prescan_batched on the B200 builds the same reference bank, keeps the same spans and
+    grows the bank by the same rows."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import ref_golden_script as S
+    from person_capture_b200 import prescan as PS
+    from person_capture_b200.face_embedder import FaceEmbedder
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_golden.npz"), allow_pickle=False)
+    frames, ref_img = S.rq_clip_frames()
+    cfg = PrescanParams(**S.RQ_CFG)
+    face = FaceEmbedder("cuda:0", S.RH_SCRFD, conf=cfg.face_det_conf, engine=engine_10g_r100)
+    bank0 = PS.build_reference_bank(face, [ref_img], cfg)
+    assert bank0 is not None and bank0.shape == G["rq_ref"].shape
+    assert min(H.cos(a, b) for a, b in zip(bank0, G["rq_ref"])) >= 0.999
+    dev = PS.DeviceClip(engine_10g_r100.to_device(np.stack(frames)))
+    spans, bank = PS.prescan_batched(dev, S.RQ_FPS, face, bank0, cfg, batch=16)
+    assert [tuple(int(v) for v in sp) for sp in spans] == [tuple(int(v) for v in r) for r in G["rq_spans"]]
+    assert np.asarray(bank).shape == G["rq_bank"].shape and len(G["rq_bank"]) > len(G["rq_ref"])
+    worst = min(H.cos(a, b) for a, b in zip(np.asarray(bank), G["rq_bank"]))
+    _note("prescan_1080p_r100_vs_reference_onnx", dict(spans=[list(map(int, sp)) for sp in spans], bank_rows=int(len(bank)), worst_bank_cos=worst))
+    # spans, decisions and the number of bank rows are the reference's.  The rows themselves are features of individual chips,
+    # and cv2.estimateAffinePartial2D(LMEDS) is discontinuous in the landmarks (see the test above): measured on the B200, the
+    # worst of the six rows has cosine 0.951 to the reference's (a differently aligned chip of the same face), the floor every
+    # extract test of this suite uses for that effect is 0.93.
+    assert worst >= 0.93, worst
+
+
 # ------------------------------------------------------------------------------------------- config 3: S = 1280 on a 4K frame
 def test_detect_1280_on_4k_matches_oracle(engine_10g_r100):
     """One SCRFD-10G pass at S=1280 on 3840x2160 frames (det_scale 1/3): head maps vs the fp32 oracle, then the full
